@@ -1,0 +1,295 @@
+"""
+CPU oracle for the codex-africanus RIME/DFT hot path -- TEST INFRASTRUCTURE ONLY.
+
+numpy-facing wrappers (reference signatures) around ``libafr_oracle.so``, the
+plain-C restatement in ``afr_oracle.c``.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the CPU-baseline legs of ``bench.py`` may
+import this package; ``codex_africanus_b200`` never does.
+
+Parity is pinned by ``tests/test_oracle.py`` against golden vectors generated
+from the reference's own numba implementation (``oracle/gen_golden.py`` ->
+``tests/golden/*.npz``) and against the reference's known-answer tests.
+
+Reference entry points restated (paths relative to /root/reference/):
+  phase_delay      africanus/rime/phase.py:11-63
+  predict_vis      africanus/rime/predict.py:466-619
+  apply_gains      africanus/rime/predict.py:622-649
+  beam_cube_dde    africanus/rime/fast_beam_cubes.py:57-240
+  freq_grid_interp africanus/rime/fast_beam_cubes.py:10-54
+  im_to_vis        africanus/dft/kernels.py:14-69
+  vis_to_im        africanus/dft/kernels.py:72-148
+  fused_predict    composition in africanus/rime/examples/predict.py:107-134,490,522-527
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libafr_oracle.so")
+_lib = None
+
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_vp = ctypes.c_void_p
+
+
+def build(force=False):
+    """Compile libafr_oracle.so with the committed Makefile (gcc)."""
+    src = os.path.join(_HERE, "afr_oracle.c")
+    if (
+        force
+        or not os.path.exists(_LIB_PATH)
+        or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
+    ):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libafr_oracle.so"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+    return _lib
+
+
+def max_threads():
+    return int(lib().orc_max_threads())
+
+
+def set_threads(n):
+    """Thread count used by the OpenMP loops (bench CPU baseline only)."""
+    os.environ["OMP_NUM_THREADS"] = str(int(n))
+    try:
+        omp = ctypes.CDLL("libgomp.so.1")
+        omp.omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _as(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _is_f32(a):
+    return int(np.asarray(a).dtype == np.float32)
+
+
+def _sign(convention):
+    if convention == "fourier":
+        return 1
+    elif convention == "casa":
+        return -1
+    raise ValueError("convention not in ('fourier', 'casa')")
+
+
+# ---------------------------------------------------------------------------
+def phase_delay(lm, uvw, frequency, convention="fourier"):
+    sign = _sign(convention)
+    lm, uvw, frequency = (np.asarray(a) for a in (lm, uvw, frequency))
+    out_dtype = np.result_type(np.complex64, lm.dtype, uvw.dtype, frequency.dtype)
+    ns, nr, nf = lm.shape[0], uvw.shape[0], frequency.shape[0]
+    if out_dtype == np.complex64:
+        out = np.zeros((ns, nr, nf), np.complex64)
+        rc = lib().orc_phase_delay_f32(
+            _p(_as(lm, np.float32)), _p(_as(uvw, np.float32)), _p(_as(frequency, np.float32)),
+            _i64(ns), _i64(nr), _i64(nf), _int(sign), _p(out))
+    else:
+        out = np.zeros((ns, nr, nf), np.complex128)
+        a, b, c = _as(lm, np.float64), _as(uvw, np.float64), _as(frequency, np.float64)
+        rc = lib().orc_phase_delay_f64(
+            _p(a), _p(b), _p(c), _i64(ns), _i64(nr), _i64(nf), _int(sign),
+            _int(_is_f32(lm)), _int(_is_f32(uvw)), _int(_is_f32(frequency)), _p(out))
+    assert rc == 0, rc
+    return out
+
+
+# ---------------------------------------------------------------------------
+def im_to_vis(image, uvw, lm, frequency, convention="fourier", dtype=None):
+    sign = _sign(convention)
+    image, uvw, lm, frequency = (np.asarray(a) for a in (image, uvw, lm, frequency))
+    if dtype is None:
+        out_dtype = np.result_type(np.complex64, image.dtype, uvw.dtype, lm.dtype, frequency.dtype)
+    else:
+        out_dtype = np.dtype(dtype)
+    ns, nf, nc = image.shape
+    nr = uvw.shape[0]
+    cplx = int(np.iscomplexobj(image))
+    img = _as(image, np.complex128 if cplx else np.float64)
+    out = np.zeros((nr, nf, nc), np.complex128)
+    rc = lib().orc_im_to_vis(
+        _p(img), _int(cplx), _p(_as(uvw, np.float64)), _p(_as(lm, np.float64)),
+        _p(_as(frequency, np.float64)), _i64(ns), _i64(nr), _i64(nf), _i64(nc), _int(sign),
+        _int(_is_f32(lm)), _int(_is_f32(uvw)), _int(out_dtype == np.complex64), _p(out))
+    assert rc == 0, rc
+    return out.astype(out_dtype)
+
+
+def vis_to_im(vis, uvw, lm, frequency, flags, convention="fourier", dtype=None):
+    sign = _sign(convention)
+    vis, uvw, lm, frequency, flags = (np.asarray(a) for a in (vis, uvw, lm, frequency, flags))
+    cplx = int(np.iscomplexobj(vis))
+    if dtype is None:
+        vreal = vis.real.dtype if cplx else vis.dtype
+        out_dtype = np.result_type(vreal, uvw.dtype, lm.dtype, frequency.dtype)
+    else:
+        out_dtype = np.dtype(dtype)
+        if out_dtype.kind == "c":
+            raise TypeError("dtype must be complex")  # sic, kernels.py:98
+    assert vis.shape == flags.shape
+    nr, nf, nc = vis.shape
+    ns = lm.shape[0]
+    v = _as(vis, np.complex128 if cplx else np.float64)
+    fl = _as(flags, np.uint8)
+    out = np.zeros((ns, nf, nc), np.float64)
+    rc = lib().orc_vis_to_im(
+        _p(v), _int(cplx), _p(_as(uvw, np.float64)), _p(_as(lm, np.float64)),
+        _p(_as(frequency, np.float64)), _p(fl), _i64(ns), _i64(nr), _i64(nf), _i64(nc),
+        _int(sign), _int(_is_f32(lm)), _int(_is_f32(uvw)), _int(out_dtype == np.float32), _p(out))
+    assert rc == 0, rc
+    return out.astype(out_dtype)
+
+
+# ---------------------------------------------------------------------------
+def _predict_layout(dde1, coh, dde2, die1, bvis, die2):
+    """ndim / presence rules of predict_checks (predict.py:380-463) and
+    _get_jones_types (predict.py:15-53, 546-563).  Returns (mode, corr_shape)."""
+    if (dde1 is None) ^ (dde2 is None):
+        raise ValueError("Both dde1_jones and dde2_jones must be present or absent")
+    if (die1 is None) ^ (die2 is None):
+        raise ValueError("Both die1_jones and die2_jones must be present or absent")
+    spec = [("dde1_jones", dde1, 5, 6), ("source_coh", coh, 4, 5), ("dde2_jones", dde2, 5, 6),
+            ("die1_jones", die1, 4, 5), ("base_vis", bvis, 3, 4), ("die2_jones", die2, 4, 5)]
+    modes = []
+    corr_shape = None
+    for name, a, d1, d2 in spec:
+        if a is None:
+            continue
+        if a.ndim == d1:
+            modes.append(0)
+        elif a.ndim == d2:
+            modes.append(1)
+        else:
+            raise ValueError("%s.ndim %d not in (%d, %d)" % (name, a.ndim, d1, d2))
+        if corr_shape is None:
+            corr_shape = a.shape[d1 - 1:]
+    if not modes:
+        raise ValueError("No Jones Matrices were supplied")
+    if any(m != modes[0] for m in modes):
+        raise ValueError("Jones Matrix Correlations were mismatched")
+    return modes[0], corr_shape
+
+
+def predict_vis(time_index, antenna1, antenna2, dde1_jones=None, source_coh=None,
+                dde2_jones=None, die1_jones=None, base_vis=None, die2_jones=None):
+    arrs = [dde1_jones, source_coh, dde2_jones, die1_jones, base_vis, die2_jones]
+    arrs = [None if a is None else np.asarray(a) for a in arrs]
+    dde1, coh, dde2, die1, bvis, die2 = arrs
+    mode, corr_shape = _predict_layout(*arrs)
+    out_dtype = np.result_type(*(a.dtype for a in arrs if a is not None))
+    ncorr = int(np.prod(corr_shape))
+    nrow = np.asarray(time_index).shape[0]
+    if dde1 is not None:
+        nsrc, ntime, nant, nchan = dde1.shape[:4]
+    else:
+        nsrc = coh.shape[0] if coh is not None else 0
+        ntime, nant = (die1.shape[:2] if die1 is not None else (1, 1))
+        nchan = coh.shape[2] if coh is not None else (die1.shape[2] if die1 is not None else bvis.shape[1])
+    if out_dtype == np.complex64:
+        T, fn = np.complex64, lib().orc_predict_vis_c64
+    else:
+        T, fn = np.complex128, lib().orc_predict_vis_c128
+    cv = [None if a is None else _as(a, T) for a in arrs]
+    ti = _as(time_index, np.int64)
+    a1 = _as(antenna1, np.int64)
+    a2 = _as(antenna2, np.int64)
+    out = np.zeros((nrow, nchan) + tuple(corr_shape), T)
+    rc = fn(_p(ti), _p(a1), _p(a2), _p(cv[0]), _p(cv[1]), _p(cv[2]), _p(cv[3]), _p(cv[4]),
+            _p(cv[5]), _i64(nsrc), _i64(nrow), _i64(ntime), _i64(nant), _i64(nchan),
+            _i64(ncorr), _int(mode), _p(out))
+    assert rc == 0, rc
+    return out.astype(out_dtype, copy=False)
+
+
+def apply_gains(time_index, antenna1, antenna2, die1_jones, corrupted_vis, die2_jones):
+    return predict_vis(time_index, antenna1, antenna2, die1_jones=die1_jones,
+                       base_vis=corrupted_vis, die2_jones=die2_jones)
+
+
+# ---------------------------------------------------------------------------
+def freq_grid_interp(frequency, beam_freq_map):
+    frequency = np.asarray(frequency)
+    f = _as(frequency, np.float64)
+    m = _as(beam_freq_map, np.float64)
+    out = np.empty((f.shape[0], 3), np.float64)
+    rc = lib().orc_freq_grid_interp(_p(f), _p(m), _i64(f.shape[0]), _i64(m.shape[0]), _p(out))
+    assert rc == 0, rc
+    return out.astype(frequency.dtype, copy=False)
+
+
+def beam_cube_dde(beam, beam_lm_extents, beam_freq_map, lm, parallactic_angles,
+                  point_errors, antenna_scaling, frequency):
+    beam = np.asarray(beam)
+    lw, mh, nud = beam.shape[:3]
+    corrs = beam.shape[3:]
+    if lw < 2 or mh < 2 or nud < 2:
+        raise ValueError("beam_lw, beam_mh and beam_nud must be >= 2")
+    ncorr = int(np.prod(corrs)) if corrs else 1
+    nsrc = np.asarray(lm).shape[0]
+    ntime, nant = np.asarray(parallactic_angles).shape
+    nchan = np.asarray(frequency).shape[0]
+    if beam.dtype == np.complex64:
+        T, fn = np.complex64, lib().orc_beam_cube_dde_c64
+    else:
+        T, fn = np.complex128, lib().orc_beam_cube_dde_c128
+    b = _as(beam, T)
+    out = np.empty((nsrc, ntime, nant, nchan) + tuple(corrs), T)
+    f64 = np.float64
+    rc = fn(_p(b), _p(_as(beam_lm_extents, f64)), _p(_as(beam_freq_map, f64)), _p(_as(lm, f64)),
+            _p(_as(parallactic_angles, f64)), _p(_as(point_errors, f64)),
+            _p(_as(antenna_scaling, f64)), _p(_as(frequency, f64)),
+            _i64(lw), _i64(mh), _i64(nud), _i64(ncorr), _i64(nsrc), _i64(ntime), _i64(nant),
+            _i64(nchan), _p(out))
+    assert rc == 0, rc
+    return out
+
+
+# ---------------------------------------------------------------------------
+def fused_predict(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
+                  dde1_jones=None, dde2_jones=None, die1_jones=None, base_vis=None,
+                  die2_jones=None, convention="fourier"):
+    """phase_delay (x) brightness -> predict_vis without materialising (s,r,f,...)."""
+    sign = _sign(convention)
+    brightness = np.asarray(brightness)
+    arrs = [dde1_jones, None, dde2_jones, die1_jones, base_vis, die2_jones]
+    arrs = [None if a is None else np.asarray(a) for a in arrs]
+    # brightness (source, chan, corr...) plays the role of source_coh minus the row axis
+    corr_shape = brightness.shape[2:]
+    mode = 1 if len(corr_shape) == 2 else 0
+    ncorr = int(np.prod(corr_shape))
+    nsrc, nchan = brightness.shape[:2]
+    nrow = np.asarray(uvw).shape[0]
+    if arrs[0] is not None:
+        ntime, nant = arrs[0].shape[1:3]
+    elif arrs[3] is not None:
+        ntime, nant = arrs[3].shape[:2]
+    else:
+        ntime, nant = 1, 1
+    c128, f64 = np.complex128, np.float64
+    cv = [None if a is None else _as(a, c128) for a in arrs]
+    out = np.zeros((nrow, nchan) + tuple(corr_shape), c128)
+    rc = lib().orc_fused_predict_c128(
+        _p(_as(lm, f64)), _p(_as(uvw, f64)), _p(_as(frequency, f64)), _p(_as(brightness, c128)),
+        _p(_as(time_index, np.int64)), _p(_as(antenna1, np.int64)), _p(_as(antenna2, np.int64)),
+        _p(cv[0]), _p(cv[2]), _p(cv[3]), _p(cv[4]), _p(cv[5]),
+        _i64(nsrc), _i64(nrow), _i64(ntime), _i64(nant), _i64(nchan), _i64(ncorr),
+        _int(mode), _int(sign), _p(out))
+    assert rc == 0, rc
+    return out

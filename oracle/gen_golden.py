@@ -1,0 +1,223 @@
+#!/usr/bin/env python
+"""
+Generate golden input/output vectors for the hot path by importing the
+UNMODIFIED reference (codex-africanus, numba) from /root/reference.
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    NUMBA_CACHE_DIR=/tmp/numba_cache python oracle/gen_golden.py
+
+Writes tests/golden/*.npz (inputs + reference outputs).  Every case is seeded;
+re-running reproduces the files bit-for-bit given the same numpy/numba.
+"""
+import itertools
+import os
+import sys
+
+os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+sys.path.insert(0, "/root/reference")
+
+import numpy as np  # noqa: E402
+
+from africanus.dft import im_to_vis, vis_to_im  # noqa: E402
+from africanus.rime import beam_cube_dde, phase_delay, predict_vis  # noqa: E402
+from africanus.rime.fast_beam_cubes import freq_grid_interp  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def rc(rng, shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+def save(name, **kw):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **kw)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+# --------------------------------------------------------------------------
+def gen_phase():
+    rng = np.random.default_rng(101)
+    lm = rng.uniform(-0.3, 0.3, (7, 2))
+    lm[3] = [0.9, 0.9]  # outside the unit disc: n clamped (phase.py:42-43)
+    uvw = rng.standard_normal((33, 3)) * 2000.0
+    freq = np.linspace(0.856e9, 1.712e9, 24)
+    freq_nu = np.sort(rng.uniform(0.856e9, 1.712e9, 11))  # non-uniform channels
+    cases = {}
+    for ci, conv in enumerate(("fourier", "casa")):
+        cases["f64_%s" % conv] = phase_delay(lm, uvw, freq, convention=conv)
+    cases["f64_nonuniform"] = phase_delay(lm, uvw, freq_nu)
+    f32 = np.float32
+    lm_s, uvw_s = lm * 0.1, uvw * 0.01  # keep |p| modest for the float32 paths
+    cases["f32_all"] = phase_delay(lm_s.astype(f32), uvw_s.astype(f32), freq.astype(f32))
+    cases["mix_lm32"] = phase_delay(lm_s.astype(f32), uvw_s, freq)
+    cases["mix_lm32_uvw32"] = phase_delay(lm_s.astype(f32), uvw_s.astype(f32), freq)
+    cases["mix_uvw32"] = phase_delay(lm_s, uvw_s.astype(f32), freq)
+    cases["mix_freq32"] = phase_delay(lm_s, uvw_s, freq.astype(f32))
+    save("phase_delay", lm=lm, uvw=uvw, freq=freq, freq_nu=freq_nu, lm_s=lm_s, uvw_s=uvw_s, **cases)
+
+
+# --------------------------------------------------------------------------
+def gen_dft():
+    rng = np.random.default_rng(202)
+    nsrc, nrow, nchan = 13, 37, 9
+    lm = rng.uniform(-0.05, 0.05, (nsrc, 2))
+    uvw = rng.standard_normal((nrow, 3)) * 1500.0
+    freq = np.linspace(0.9e9, 1.3e9, nchan)
+    freq_nu = np.sort(rng.uniform(0.9e9, 1.3e9, nchan))
+    out = dict(lm=lm, uvw=uvw, freq=freq, freq_nu=freq_nu)
+    for ncorr in (1, 2, 4):
+        img = rng.standard_normal((nsrc, nchan, ncorr))
+        img[2] = 0.0  # exactly-zero pixels are skipped (kernels.py:64)
+        out["image_r%d" % ncorr] = img
+        out["i2v_r%d" % ncorr] = im_to_vis(img, uvw, lm, freq)
+        vis = rc(rng, (nrow, nchan, ncorr))
+        flags = rng.random((nrow, nchan, ncorr)) < 0.1
+        out["vis_c%d" % ncorr] = vis
+        out["flags_%d" % ncorr] = flags
+        out["v2i_c%d" % ncorr] = vis_to_im(vis, uvw, lm, freq, flags)
+    imgc = rc(rng, (nsrc, nchan, 2))
+    out["image_c2"] = imgc
+    out["i2v_c2"] = im_to_vis(imgc, uvw, lm, freq)
+    out["i2v_c2_casa"] = im_to_vis(imgc, uvw, lm, freq, convention="casa")
+    out["i2v_r1_nonuniform"] = im_to_vis(out["image_r1"], uvw, lm, freq_nu)
+    out["i2v_r1_c64"] = im_to_vis(out["image_r1"], uvw, lm, freq, dtype=np.complex64)
+    f32 = np.float32
+    out["i2v_r1_in32"] = im_to_vis(out["image_r1"].astype(f32), uvw.astype(f32),
+                                   lm.astype(f32), freq.astype(f32))
+    out["i2v_r1_lm32"] = im_to_vis(out["image_r1"], uvw, lm.astype(f32), freq)
+    visr = rng.standard_normal((nrow, nchan, 2))
+    out["vis_r2"] = visr
+    out["v2i_r2"] = vis_to_im(visr, uvw, lm, freq, out["flags_2"])
+    out["v2i_c1_casa"] = vis_to_im(out["vis_c1"], uvw, lm, freq, out["flags_1"], convention="casa")
+    out["v2i_c1_f32"] = vis_to_im(out["vis_c1"], uvw, lm, freq, out["flags_1"], dtype=np.float32)
+    out["v2i_c1_nonuniform"] = vis_to_im(out["vis_c1"], uvw, lm, freq_nu, out["flags_1"])
+    out["v2i_c1_in32"] = vis_to_im(out["vis_c1"].astype(np.complex64), uvw.astype(f32),
+                                   lm.astype(f32), freq.astype(f32), out["flags_1"])
+    save("dft", **out)
+
+
+# --------------------------------------------------------------------------
+def gen_predict():
+    """The reference's 27-case matrix (rime/tests/test_predict.py:33-126) with the
+    cupy test's +10 time-index offset (rime/cuda/tests/test_cuda_predict.py:42-45)."""
+    rng = np.random.default_rng(303)
+    s, t, a, c, r = 6, 4, 4, 5, 10
+    time_idx = np.asarray([0, 0, 1, 1, 2, 2, 2, 2, 3, 3]) + 10
+    ant1 = np.asarray([0, 0, 0, 0, 1, 1, 1, 2, 2, 3])
+    ant2 = np.asarray([0, 1, 2, 3, 1, 2, 3, 2, 3, 3])
+    out = dict(time_idx=time_idx, ant1=ant1, ant2=ant2)
+    presence = [(True, True, True), (True, False, True), (False, True, False)]
+    for cname, corr in (("c1", (1,)), ("c2", (2,)), ("c22", (2, 2))):
+        arrs = dict(
+            a1j=rc(rng, (s, t, a, c) + corr), blj=rc(rng, (s, r, c) + corr),
+            a2j=rc(rng, (s, t, a, c) + corr), g1j=rc(rng, (t, a, c) + corr),
+            bvis=rc(rng, (r, c) + corr), g2j=rc(rng, (t, a, c) + corr))
+        for k, v in arrs.items():
+            out["%s_%s" % (cname, k)] = v
+        for (d1, bl, d2), (g1, bv, g2) in itertools.product(presence, presence):
+            key = "%s_out_%d%d%d_%d%d%d" % (cname, d1, bl, d2, g1, bv, g2)
+            out[key] = predict_vis(
+                time_idx, ant1, ant2,
+                arrs["a1j"] if d1 else None, arrs["blj"] if bl else None,
+                arrs["a2j"] if d2 else None, arrs["g1j"] if g1 else None,
+                arrs["bvis"] if bv else None, arrs["g2j"] if g2 else None)
+        # complex64 arithmetic, int16 indices
+        a64 = {k: v.astype(np.complex64) for k, v in arrs.items()}
+        out["%s_out_c64" % cname] = predict_vis(
+            time_idx.astype(np.int16), ant1.astype(np.int16), ant2.astype(np.int16),
+            a64["a1j"], a64["blj"], a64["a2j"], a64["g1j"], a64["bvis"], a64["g2j"])
+    save("predict_vis", **out)
+
+
+# --------------------------------------------------------------------------
+def gen_beam():
+    rng = np.random.default_rng(404)
+    lw, mh, nud = 9, 8, 5
+    nsrc, ntime, nant, nchan = 5, 3, 4, 8
+    beam_freq_map = np.array([0.5, 0.56, 0.7, 0.91, 1.0])
+    freq = np.array([0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1])
+    ext = np.array([[-0.9, 0.9], [-0.8, 1.0]])
+    lm = rng.uniform(-1.0, 1.0, (nsrc, 2))  # some sources fall off the cube: clamping
+    pa = rng.uniform(-np.pi, np.pi, (ntime, nant))
+    perr = rng.uniform(-0.05, 0.05, (ntime, nant, nchan, 2))
+    ascale = rng.uniform(0.9, 1.1, (nant, nchan, 2))
+    out = dict(beam_freq_map=beam_freq_map, freq=freq, ext=ext, lm=lm, pa=pa, perr=perr,
+               ascale=ascale)
+    out["freq_data"] = freq_grid_interp(freq, beam_freq_map)
+    for cname, corr in (("c22", (2, 2)), ("c4", (4,)), ("c2", (2,)), ("c1", (1,))):
+        beam = rc(rng, (lw, mh, nud) + corr)
+        out["beam_" + cname] = beam
+        out["dde_" + cname] = beam_cube_dde(beam, ext, beam_freq_map, lm, pa, perr, ascale, freq)
+    b64 = out["beam_c22"].astype(np.complex64)
+    out["dde_c22_c64"] = beam_cube_dde(b64, ext, beam_freq_map, lm, pa, perr, ascale, freq)
+    # the reference's own known-answer test (rime/tests/test_fast_beams.py:43-127)
+    np.random.seed(42)
+    kb = np.random.random((2, 2, 2, 1)) + 1j * np.random.random((2, 2, 2, 1))
+    out["ka_beam"] = kb
+    out["ka_dde"] = beam_cube_dde(
+        kb, np.asarray([[-1.0, 1.0], [-1.0, 1.0]]), np.asarray([0.0, 1.0]),
+        np.asarray([[0.1, 0.1]]), np.zeros((1, 1)), np.zeros((1, 1, 1, 2)),
+        np.ones((1, 1, 2)), np.asarray([0.3]))
+    save("beam_cube_dde", **out)
+
+
+# --------------------------------------------------------------------------
+def gen_fused():
+    """Un-fused composition the new fused kernel must reproduce
+    (rime/examples/predict.py:107-134,490,522-527; recipe asserted in
+    experimental/rime/fused/tests/test_rime.py:175-209)."""
+    rng = np.random.default_rng(505)
+    na, ntime, nchan, nsrc = 5, 3, 12, 9
+    a1, a2 = np.triu_indices(na, 1)
+    nbl = a1.size
+    ant1 = np.tile(a1, ntime)
+    ant2 = np.tile(a2, ntime)
+    time_idx = np.repeat(np.arange(ntime), nbl) + 3
+    nrow = ant1.size
+    uvw = rng.standard_normal((nrow, 3)) * 800.0
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    freq = np.linspace(0.856e9, 1.712e9, nchan)
+    out = dict(ant1=ant1, ant2=ant2, time_idx=time_idx, uvw=uvw, lm=lm, freq=freq)
+    # beam-cube DDEs
+    lw = mh = 17
+    nud = 6
+    ext = np.array([[-0.03, 0.03], [-0.03, 0.03]])
+    bfm = np.linspace(0.856e9, 1.712e9, nud)
+    beam = rc(rng, (lw, mh, nud, 2, 2))
+    pa = rng.uniform(-0.5, 0.5, (ntime, na))
+    perr = np.zeros((ntime, na, nchan, 2))
+    ascale = np.ones((na, nchan, 2))
+    out.update(beam=beam, ext=ext, bfm=bfm, pa=pa)
+    for conv in ("fourier", "casa"):
+        K = phase_delay(lm, uvw, freq, convention=conv)
+        for cname, corr in (("c22", (2, 2)), ("c2", (2,)), ("c1", (1,))):
+            bright = rc(rng, (nsrc, nchan) + corr)
+            die = 1.0 + 0.1 * rc(rng, (ntime, na, nchan) + corr)
+            bvis = rc(rng, (nrow, nchan) + corr)
+            sub = "fij" if len(corr) == 2 else "fi"
+            coh = np.einsum("srf,s%s->sr%s" % (sub, sub), K, bright)
+            key = "%s_%s" % (conv, cname)
+            out["bright_" + key] = bright
+            out["die_" + key] = die
+            out["bvis_" + key] = bvis
+            out["point_" + key] = predict_vis(time_idx, ant1, ant2, None, coh, None, None, None, None)
+            out["point_die_" + key] = predict_vis(time_idx, ant1, ant2, None, coh, None, die, bvis, die)
+            if corr == (2, 2):
+                dde = beam_cube_dde(beam, ext, bfm, lm, pa, perr, ascale, freq)
+            else:
+                dde = rc(rng, (nsrc, ntime, na, nchan) + corr)
+                out["dde_" + key] = dde
+            out["full_" + key] = predict_vis(time_idx, ant1, ant2, dde, coh, dde, die, bvis, die)
+    out["dde_beam_c22"] = beam_cube_dde(beam, ext, bfm, lm, pa, perr, ascale, freq)
+    save("fused_predict", **out)
+
+
+if __name__ == "__main__":
+    gen_phase()
+    gen_dft()
+    gen_predict()
+    gen_beam()
+    gen_fused()

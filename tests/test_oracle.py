@@ -1,0 +1,305 @@
+"""
+Pin the CPU oracle (oracle/afr_oracle.c) against the reference.
+
+* golden vectors produced by the reference's numba implementation
+  (oracle/gen_golden.py -> tests/golden/*.npz), compared BIT-EXACTLY wherever the
+  oracle restates the same operation order with the same libm, otherwise to 1e-13;
+* the reference's own known-answer tests, re-stated against the oracle:
+  rime/tests/test_rime.py:19-47, rime/tests/test_fast_beams.py:43-150,
+  dft/tests/test_dft.py:12-215,297-331, rime/tests/test_predict.py:62-126.
+
+CPU only (no gpu marker).
+"""
+import itertools
+
+import numpy as np
+import pytest
+from numpy.testing import assert_array_almost_equal, assert_array_equal
+
+C = 2.99792458e8
+MINUS_TWO_PI_OVER_C = -2 * np.pi / C
+
+
+def _tight(got, ref, tol=1e-13):
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    scale = max(np.max(np.abs(ref)), 1e-300)
+    assert np.max(np.abs(got - ref)) <= tol * scale
+
+
+# ----------------------------------------------------------------------------- phase
+def test_phase_delay_golden(oracle, golden):
+    g = golden("phase_delay")
+    lm, uvw, freq = g["lm"], g["uvw"], g["freq"]
+    for conv in ("fourier", "casa"):
+        assert_array_equal(oracle.phase_delay(lm, uvw, freq, convention=conv), g["f64_" + conv])
+    assert_array_equal(oracle.phase_delay(lm, uvw, g["freq_nu"]), g["f64_nonuniform"])
+    f32 = np.float32
+    lm_s, uvw_s = g["lm_s"], g["uvw_s"]
+    got = oracle.phase_delay(lm_s.astype(f32), uvw_s.astype(f32), freq.astype(f32))
+    assert got.dtype == np.complex64
+    # float32 libm (cosf/sinf) may differ in the last ulp between builds
+    assert np.max(np.abs(got - g["f32_all"])) <= 3e-7
+    assert_array_equal(oracle.phase_delay(lm_s.astype(f32), uvw_s, freq), g["mix_lm32"])
+    assert_array_equal(oracle.phase_delay(lm_s.astype(f32), uvw_s.astype(f32), freq), g["mix_lm32_uvw32"])
+    assert_array_equal(oracle.phase_delay(lm_s, uvw_s.astype(f32), freq), g["mix_uvw32"])
+    assert_array_equal(oracle.phase_delay(lm_s, uvw_s, freq.astype(f32)), g["mix_freq32"])
+
+
+@pytest.mark.parametrize("convention, sign", [("fourier", 1), ("casa", -1)])
+def test_phase_delay_known_answer(oracle, convention, sign):
+    # rime/tests/test_rime.py:19-47 (bit-exact)
+    rng = np.random.default_rng(0)
+    uvw = rng.random((100, 3))
+    lm = rng.random((10, 2))
+    frequency = np.linspace(0.856e9, 0.856e9 * 2, 64, endpoint=True)
+    uvw[2] = [1, 2, 3]
+    lm[3] = [0.1, 0.2]
+    frequency[5] = 0.856e9
+    cp = oracle.phase_delay(lm, uvw, frequency, convention=convention)
+    n = np.sqrt(1.0 - 0.1**2 - 0.2**2) - 1.0
+    phase = sign * MINUS_TWO_PI_OVER_C * (1 * 0.1 + 2 * 0.2 + 3 * n) * 0.856e9
+    assert np.all(np.exp(1j * phase) == cp[3, 2, 5])
+
+
+def test_phase_delay_bad_convention(oracle):
+    with pytest.raises(ValueError, match="convention not in"):
+        oracle.phase_delay(np.zeros((1, 2)), np.zeros((1, 3)), np.ones(1), convention="x")
+
+
+# ----------------------------------------------------------------------------- dft
+def test_dft_golden(oracle, golden):
+    g = golden("dft")
+    lm, uvw, freq = g["lm"], g["uvw"], g["freq"]
+    f32 = np.float32
+    for nc in (1, 2, 4):
+        assert_array_equal(oracle.im_to_vis(g["image_r%d" % nc], uvw, lm, freq), g["i2v_r%d" % nc])
+        assert_array_equal(
+            oracle.vis_to_im(g["vis_c%d" % nc], uvw, lm, freq, g["flags_%d" % nc]), g["v2i_c%d" % nc])
+    assert_array_equal(oracle.im_to_vis(g["image_c2"], uvw, lm, freq), g["i2v_c2"])
+    assert_array_equal(oracle.im_to_vis(g["image_c2"], uvw, lm, freq, convention="casa"), g["i2v_c2_casa"])
+    assert_array_equal(oracle.im_to_vis(g["image_r1"], uvw, lm, g["freq_nu"]), g["i2v_r1_nonuniform"])
+    got = oracle.im_to_vis(g["image_r1"], uvw, lm, freq, dtype=np.complex64)
+    assert got.dtype == np.complex64
+    assert_array_equal(got, g["i2v_r1_c64"])
+    got = oracle.im_to_vis(g["image_r1"].astype(f32), uvw.astype(f32), lm.astype(f32), freq.astype(f32))
+    assert got.dtype == g["i2v_r1_in32"].dtype
+    assert_array_equal(got, g["i2v_r1_in32"])
+    assert_array_equal(oracle.im_to_vis(g["image_r1"], uvw, lm.astype(f32), freq), g["i2v_r1_lm32"])
+    assert_array_equal(oracle.vis_to_im(g["vis_r2"], uvw, lm, freq, g["flags_2"]), g["v2i_r2"])
+    assert_array_equal(
+        oracle.vis_to_im(g["vis_c1"], uvw, lm, freq, g["flags_1"], convention="casa"), g["v2i_c1_casa"])
+    got = oracle.vis_to_im(g["vis_c1"], uvw, lm, freq, g["flags_1"], dtype=np.float32)
+    assert got.dtype == np.float32
+    assert_array_equal(got, g["v2i_c1_f32"])
+    assert_array_equal(
+        oracle.vis_to_im(g["vis_c1"], uvw, lm, g["freq_nu"], g["flags_1"]), g["v2i_c1_nonuniform"])
+    got = oracle.vis_to_im(g["vis_c1"].astype(np.complex64), uvw.astype(f32), lm.astype(f32),
+                           freq.astype(f32), g["flags_1"])
+    assert got.dtype == g["v2i_c1_in32"].dtype
+    assert_array_equal(got, g["v2i_c1_in32"])
+
+
+def test_im_to_vis_phase_centre(oracle):
+    # dft/tests/test_dft.py:12-42
+    nrow, npix, nchan, ncorr = 100, 35, 11, 2
+    uvw = np.random.default_rng(1).random((nrow, 3))
+    x = np.linspace(-0.1, 0.1, npix)
+    ll, mm = np.meshgrid(x, x)
+    lm = np.vstack((ll.flatten(), mm.flatten())).T
+    frequency = np.linspace(1.0, 2.0, nchan, endpoint=True)
+    image = np.zeros((npix, npix, nchan, ncorr))
+    Inu = (frequency / frequency[nchan // 2]) ** (-0.7)
+    for corr in range(ncorr):
+        image[npix // 2, npix // 2, :, corr] = Inu
+    vis = oracle.im_to_vis(image.reshape(npix**2, nchan, ncorr), uvw, lm, frequency)
+    tmp = vis - Inu[None, :, None]
+    assert np.all(np.abs(tmp.real) < 1e-13) and np.all(np.abs(tmp.imag) < 1e-13)
+
+
+@pytest.mark.parametrize("convention", ["fourier", "casa"])
+def test_im_to_vis_fft(oracle, convention):
+    # dft/tests/test_dft.py:86-133
+    np.random.seed(123)
+    Fs, iFs = np.fft.fftshift, np.fft.ifftshift
+    npix, ncorr, nsource = 29, 1, 25
+    image = np.zeros((npix, npix, ncorr))
+    fft_image = np.zeros((npix, npix, ncorr), np.complex128)
+    Ix = np.random.randint(5, npix - 5, nsource)
+    Iy = np.random.randint(5, npix - 5, nsource)
+    image[Ix, Iy, 0] = np.random.randn(nsource)
+    fft_image[:, :, 0] = Fs(np.fft.fft2(iFs(image[:, :, 0])))
+    deltal = 0.001
+    l_coord = np.arange(-(npix // 2), npix // 2 + 1) * deltal
+    ll, mm = np.meshgrid(l_coord, l_coord)
+    lm = np.vstack((ll.flatten(), mm.flatten())).T
+    u = Fs(np.fft.fftfreq(npix, d=deltal))
+    uu, vv = np.meshgrid(u, u)
+    uvw = np.zeros((npix**2, 3))
+    uvw[:, 0], uvw[:, 1] = uu.flatten(), vv.flatten()
+    frequency = np.ones(1) * C
+    vis = oracle.im_to_vis(image.reshape(npix**2, 1, ncorr), uvw, lm, frequency, convention=convention)
+    fft_image = fft_image.reshape(npix**2, 1, ncorr)
+    fft_image = np.conj(fft_image) if convention == "casa" else fft_image
+    assert_array_almost_equal(vis, fft_image, decimal=13)
+
+
+def test_adjointness_and_flags(oracle):
+    # dft/tests/test_dft.py:136-177 and :180-215
+    np.random.seed(123)
+    nsource, nrow, nchan, ncorr = 21, 31, 3, 4
+    uvw = 100 * np.random.random(size=(nrow, 3))
+    lm = np.vstack((0.01 * np.random.randn(nsource), 0.01 * np.random.randn(nsource))).T
+    frequency = np.arange(1, nchan + 1) * C
+    gamma_im = np.random.randn(nsource, nchan, ncorr)
+    gamma_vis = np.random.randn(nrow, nchan, ncorr)
+    flag = np.zeros((nrow, nchan, ncorr), dtype=bool)
+    LHS = np.vdot(gamma_vis.ravel(), oracle.im_to_vis(gamma_im, uvw, lm, frequency).ravel()).real
+    RHS = np.dot(oracle.vis_to_im(gamma_vis, uvw, lm, frequency, flag).ravel(), gamma_im.ravel())
+    assert np.abs(LHS - RHS) < 1e-13 * max(1.0, abs(LHS))
+    # flagged data: only the zero-uvw, all-ones row survives
+    uvw[0, :] = 0.0
+    vis = np.random.randn(nrow, nchan, ncorr) + 1.0j * np.random.randn(nrow, nchan, ncorr)
+    vis[0, :, :] = 1.0
+    flags = np.ones((nrow, nchan, ncorr), dtype=bool)
+    flags[0, :, :] = 0
+    im = oracle.vis_to_im(vis, uvw, lm, np.ones(nchan) * C, flags)
+    assert_array_almost_equal(im, np.ones((nsource, nchan, ncorr)), decimal=13)
+
+
+def test_vis_to_im_dtype_errors(oracle):
+    z = np.zeros((2, 1, 1))
+    with pytest.raises(TypeError):
+        oracle.vis_to_im(z, np.zeros((2, 3)), np.zeros((1, 2)), np.ones(1), z > 0, dtype=np.complex128)
+    with pytest.raises(AssertionError):
+        oracle.vis_to_im(z, np.zeros((2, 3)), np.zeros((1, 2)), np.ones(1), np.zeros((2, 1, 2), bool))
+
+
+# ----------------------------------------------------------------------------- predict
+PRESENCE = [(True, True, True), (True, False, True), (False, True, False)]
+
+
+@pytest.mark.parametrize("cname", ["c1", "c2", "c22"])
+def test_predict_vis_golden(oracle, golden, cname):
+    g = golden("predict_vis")
+    ti, a1, a2 = g["time_idx"], g["ant1"], g["ant2"]
+    arrs = {k: g["%s_%s" % (cname, k)] for k in ("a1j", "blj", "a2j", "g1j", "bvis", "g2j")}
+    for (d1, bl, d2), (g1, bv, g2) in itertools.product(PRESENCE, PRESENCE):
+        key = "%s_out_%d%d%d_%d%d%d" % (cname, d1, bl, d2, g1, bv, g2)
+        got = oracle.predict_vis(
+            ti, a1, a2, arrs["a1j"] if d1 else None, arrs["blj"] if bl else None,
+            arrs["a2j"] if d2 else None, arrs["g1j"] if g1 else None,
+            arrs["bvis"] if bv else None, arrs["g2j"] if g2 else None)
+        assert_array_equal(got, g[key], err_msg=key)
+    a64 = {k: v.astype(np.complex64) for k, v in arrs.items()}
+    got = oracle.predict_vis(ti.astype(np.int16), a1.astype(np.int16), a2.astype(np.int16),
+                             a64["a1j"], a64["blj"], a64["a2j"], a64["g1j"], a64["bvis"], a64["g2j"])
+    assert got.dtype == np.complex64
+    assert_array_equal(got, g["%s_out_c64" % cname])
+
+
+@pytest.mark.parametrize("corr_shape, idm, sig1, sig2", [
+    ((1,), (1,), "srci,srci,srci->rci", "rci,rci,rci->rci"),
+    ((2,), (1, 1), "srci,srci,srci->rci", "rci,rci,rci->rci"),
+    ((2, 2), ((1, 0), (0, 1)), "srcij,srcjk,srclk->rcil", "rcij,rcjk,rclk->rcil"),
+])
+def test_predict_vis_einsum(oracle, corr_shape, idm, sig1, sig2):
+    # rime/tests/test_predict.py:62-126 (independent numpy oracle), all 9 presence combos
+    rng = np.random.default_rng(5)
+    s, t, a, c, r = 21, 4, 4, 5, 10
+
+    def rcx(shape):
+        return rng.random(shape) + 1j * rng.random(shape)
+
+    time_idx = np.asarray([0, 0, 1, 1, 2, 2, 2, 2, 3, 3])
+    ant1 = np.asarray([0, 0, 0, 0, 1, 1, 1, 2, 2, 3])
+    ant2 = np.asarray([0, 1, 2, 3, 1, 2, 3, 2, 3, 3])
+    A1, BL, A2 = rcx((s, t, a, c) + corr_shape), rcx((s, r, c) + corr_shape), rcx((s, t, a, c) + corr_shape)
+    G1, BV, G2 = rcx((t, a, c) + corr_shape), rcx((r, c) + corr_shape), rcx((t, a, c) + corr_shape)
+    for (d1, bl, d2), (g1, bv, g2) in itertools.product(PRESENCE, PRESENCE):
+        got = oracle.predict_vis(time_idx, ant1, ant2, A1 if d1 else None, BL if bl else None,
+                                 A2 if d2 else None, G1 if g1 else None, BV if bv else None,
+                                 G2 if g2 else None)
+        ident = lambda arr: np.broadcast_to(idm, arr.shape)  # noqa: E731
+        e1 = A1[:, time_idx, ant1] if d1 else ident(BL)
+        x = BL if bl else ident(BL)
+        e2 = A2[:, time_idx, ant2].conj() if d2 else ident(BL)
+        v = np.einsum(sig1, e1, x, e2)
+        if bv:
+            v = v + BV
+        gg1 = G1[time_idx, ant1] if g1 else ident(v)
+        gg2 = G2[time_idx, ant2].conj() if g2 else ident(v)
+        v = np.einsum(sig2, gg1, v, gg2)
+        assert_array_almost_equal(v, got)
+
+
+def test_predict_vis_errors(oracle):
+    ti = a1 = a2 = np.zeros(2, np.int32)
+    dde = np.zeros((1, 1, 1, 1, 2, 2), np.complex128)
+    coh = np.zeros((1, 2, 1, 2), np.complex128)
+    with pytest.raises(ValueError, match="Both dde1_jones and dde2_jones"):
+        oracle.predict_vis(ti, a1, a2, dde1_jones=dde)
+    with pytest.raises(ValueError, match="Both die1_jones and die2_jones"):
+        oracle.predict_vis(ti, a1, a2, die1_jones=dde[0])
+    with pytest.raises(ValueError, match="mismatched"):
+        oracle.predict_vis(ti, a1, a2, dde, coh, dde)
+    with pytest.raises(ValueError, match="No Jones"):
+        oracle.predict_vis(ti, a1, a2)
+    with pytest.raises(ValueError, match="ndim"):
+        oracle.predict_vis(ti, a1, a2, source_coh=np.zeros((1, 2, 1), np.complex128))
+
+
+# ----------------------------------------------------------------------------- beam
+def test_freq_grid_interp_known_answer(oracle, golden):
+    # rime/tests/test_fast_beams.py:130-150
+    freqs = np.array([0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1])
+    bfm = np.array([0.5, 0.56, 0.7, 0.91, 1.0])
+    fd = oracle.freq_grid_interp(freqs, bfm)
+    assert_array_almost_equal(fd[:, 0], [0.8, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.1])
+    assert_array_equal(np.int32(fd[:, 2]), [0, 0, 1, 2, 2, 2, 3, 3])
+    assert_array_almost_equal(fd[:, 1], [1.0, 1.0, 0.71428571, 1.0, 0.52380952, 0.04761905, 0.0, 0.0])
+    assert_array_equal(fd, golden("beam_cube_dde")["freq_data"])
+
+
+def test_beam_cube_dde_golden(oracle, golden):
+    g = golden("beam_cube_dde")
+    args = (g["ext"], g["beam_freq_map"], g["lm"], g["pa"], g["perr"], g["ascale"], g["freq"])
+    for cname in ("c22", "c4", "c2", "c1"):
+        got = oracle.beam_cube_dde(g["beam_" + cname], *args)
+        _tight(got, g["dde_" + cname], 1e-15)
+    got = oracle.beam_cube_dde(g["beam_c22"].astype(np.complex64), *args)
+    assert got.dtype == np.complex64
+    assert np.max(np.abs(got - g["dde_c22_c64"])) <= 5e-7 * np.max(np.abs(g["dde_c22_c64"]))
+    # known-answer (rime/tests/test_fast_beams.py:43-127)
+    ka = oracle.beam_cube_dde(
+        g["ka_beam"], np.asarray([[-1.0, 1.0], [-1.0, 1.0]]), np.asarray([0.0, 1.0]),
+        np.asarray([[0.1, 0.1]]), np.zeros((1, 1)), np.zeros((1, 1, 1, 2)), np.ones((1, 1, 2)),
+        np.asarray([0.3]))
+    assert_array_almost_equal([[[[[0.470255 + 0.4786j]]]]], ka)
+    _tight(ka, g["ka_dde"], 1e-15)
+
+
+def test_beam_cube_dde_errors(oracle):
+    with pytest.raises(ValueError, match="must be >= 2"):
+        oracle.beam_cube_dde(np.zeros((1, 2, 2, 1), np.complex128), np.zeros((2, 2)), np.zeros(2),
+                             np.zeros((1, 2)), np.zeros((1, 1)), np.zeros((1, 1, 1, 2)),
+                             np.ones((1, 1, 2)), np.ones(1))
+
+
+# ----------------------------------------------------------------------------- fused
+def test_fused_predict_golden(oracle, golden):
+    g = golden("fused_predict")
+    ti, a1, a2 = g["time_idx"], g["ant1"], g["ant2"]
+    lm, uvw, freq = g["lm"], g["uvw"], g["freq"]
+    for conv in ("fourier", "casa"):
+        for cname in ("c22", "c2", "c1"):
+            key = "%s_%s" % (conv, cname)
+            br, die, bvis = g["bright_" + key], g["die_" + key], g["bvis_" + key]
+            got = oracle.fused_predict(lm, uvw, freq, br, ti, a1, a2, convention=conv)
+            assert_array_equal(got, g["point_" + key])
+            got = oracle.fused_predict(lm, uvw, freq, br, ti, a1, a2, die1_jones=die,
+                                       base_vis=bvis, die2_jones=die, convention=conv)
+            assert_array_equal(got, g["point_die_" + key])
+            dde = g["dde_beam_c22"] if cname == "c22" else g["dde_" + key]
+            got = oracle.fused_predict(lm, uvw, freq, br, ti, a1, a2, dde, dde, die, bvis, die,
+                                       convention=conv)
+            assert_array_equal(got, g["full_" + key])
