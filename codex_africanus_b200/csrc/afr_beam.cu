@@ -1,0 +1,234 @@
+// beam_cube_dde + freq_grid_interp (africanus/rime/fast_beam_cubes.py:57-240, :10-54)
+// for sm_100a.
+//
+// Bound by the 8 scattered corner gathers from the beam cube and the coalesced store of
+// the (source,time,ant,chan,corr) output.  One thread produces one output element (all of
+// its correlations); threads run along chan (the output's fastest axis apart from corr) so
+// stores are contiguous and the per-channel interpolation data is a coalesced read.  The
+// coordinate arithmetic uses explicitly rounded operations in the reference's order so the
+// grid cell chosen by floor() is the reference's.
+#include "afr_common.cuh"
+
+namespace afr {
+namespace {
+
+// fast_beam_cubes.py:10-54
+__global__ void freq_grid_interp_kernel(const double *freq, const double *bfm, long long nchan,
+                                        long long nud, double *fd) {
+    const long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (f >= nchan) return;
+    const double nu = freq[f];
+    long long lo = 0, hi = nud - 1;
+    while (lo <= hi) {
+        const long long mid = lo + (hi - lo) / 2;
+        const double bf = bfm[mid];
+        if (bf < nu) {
+            lo = mid + 1;
+        } else if (bf > nu) {
+            hi = mid - 1;
+        } else {
+            lo = mid;
+            break;
+        }
+    }
+    if (hi < lo) lo = hi;
+    hi = lo + 1;
+    double scale, wlo, glo;
+    if (lo == -1) {
+        scale = __ddiv_rn(nu, bfm[0]);
+        wlo = 1.0;
+        glo = 0.0;
+    } else if (hi == nud) {
+        scale = __ddiv_rn(nu, bfm[nud - 1]);
+        wlo = 0.0;
+        glo = (double)(nud - 2);
+    } else {
+        scale = 1.0;
+        const double flo = bfm[lo], fhi = bfm[hi];
+        wlo = __ddiv_rn(__dsub_rn(fhi, nu), __dsub_rn(fhi, flo));
+        glo = (double)lo;
+    }
+    fd[3 * f] = scale;
+    fd[3 * f + 1] = wlo;
+    fd[3 * f + 2] = glo;
+}
+
+struct BeamParams {
+    const void *beam;  // (lw,mh,nud,ncorr) complex
+    const double *fd;  // (nchan,3)
+    const double *lm, *pa, *perr, *ascale;
+    void *out;  // (nsrc,ntime,nant,nchan,ncorr)
+    double lower_l, lower_m, lscale, mscale, lmaxf, mmaxf;
+    long long lw, mh, nud, nsrc, ntime, nant, nchan;
+    int ncorr, coff;
+};
+
+__device__ __forceinline__ double habs(double re, double im) { return hypot(re, im); }
+__device__ __forceinline__ float habs(float re, float im) { return hypotf(re, im); }
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) {
+    const T *beam = (const T *)p.beam;
+    T *out = (T *)p.out;
+    const long long total = p.nsrc * p.ntime * p.nant * p.nchan;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i % p.nchan;
+        long long rest = i / p.nchan;
+        const long long a = rest % p.nant;
+        rest /= p.nant;
+        const long long t = rest % p.ntime;
+        const long long s = rest / p.ntime;
+
+        double sin_pa, cos_pa;
+        sincos(p.pa[t * p.nant + a], &sin_pa, &cos_pa);
+        const double l = p.lm[2 * s], m = p.lm[2 * s + 1];
+        const double fscale = p.fd[3 * f], nudw = p.fd[3 * f + 1];
+        const double inv_nud = __dsub_rn(1.0, nudw);
+        const long long gc0 = (long long)(int)p.fd[3 * f + 2], gc1 = gc0 + 1;
+
+        // fast_beam_cubes.py:130-151
+        const double sl = __dmul_rn(l, fscale), sm = __dmul_rn(m, fscale);
+        const double *pe = p.perr + ((t * p.nant + a) * p.nchan + f) * 2;
+        const double tl = __dadd_rn(sl, pe[0]), tm = __dadd_rn(sm, pe[1]);
+        double vl = __dsub_rn(__dmul_rn(tl, cos_pa), __dmul_rn(tm, sin_pa));
+        double vm = __dadd_rn(__dmul_rn(tl, sin_pa), __dmul_rn(tm, cos_pa));
+        const double *as = p.ascale + (a * p.nchan + f) * 2;
+        vl = __dmul_rn(vl, as[0]);
+        vm = __dmul_rn(vm, as[1]);
+        vl = __dmul_rn(p.lscale, __dsub_rn(vl, p.lower_l));
+        vm = __dmul_rn(p.mscale, __dsub_rn(vm, p.lower_m));
+        vl = fmax(0.0, fmin(vl, p.lmaxf));
+        vm = fmax(0.0, fmin(vm, p.mmaxf));
+        // :154-163
+        const long long gl0 = (long long)(int)floor(vl), gm0 = (long long)(int)floor(vm);
+        const long long gl1 = min(gl0 + 1, p.lw - 1), gm1 = min(gm0 + 1, p.mh - 1);
+        const double ld = __dsub_rn(vl, (double)gl0), md = __dsub_rn(vm, (double)gm0);
+        const double oml = __dsub_rn(1.0, ld), omm = __dsub_rn(1.0, md);
+
+        // eight corners in the reference's order (:169-225)
+        const long long gls[8] = {gl0, gl1, gl0, gl1, gl0, gl1, gl0, gl1};
+        const long long gms[8] = {gm0, gm0, gm1, gm1, gm0, gm0, gm1, gm1};
+        const double w4[4] = {__dmul_rn(oml, omm), __dmul_rn(ld, omm), __dmul_rn(oml, md),
+                              __dmul_rn(ld, md)};
+        T csr[NC], csi[NC], asum[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) csr[c] = csi[c] = asum[c] = T(0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const long long gc = k < 4 ? gc0 : gc1;
+            const double wt = __dmul_rn(w4[k & 3], k < 4 ? nudw : inv_nud);
+            const T *b = beam + (((gls[k] * p.mh + gms[k]) * p.nud + gc) * p.ncorr + p.coff) * 2;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const T br = b[2 * c], bi = b[2 * c + 1];
+                const T ab = habs(br, bi);
+                // accumulators live in the beam's precision, weights in float64 (:106-108)
+                asum[c] = (T)__dadd_rn((double)asum[c], __dmul_rn(wt, (double)ab));
+                csr[c] = (T)__dadd_rn((double)csr[c], __dmul_rn(wt, (double)br));
+                csi[c] = (T)__dadd_rn((double)csi[c], __dmul_rn(wt, (double)bi));
+            }
+        }
+        T *o = out + (i * p.ncorr + p.coff) * 2;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {  // :227-238
+            const T div = habs(csr[c], csi[c]);
+            const T k = (div == T(0)) ? asum[c] : asum[c] / div;
+            o[2 * c] = csr[c] * k;
+            o[2 * c + 1] = csi[c] * k;
+        }
+    }
+}
+
+int grid_for(long long total) {
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <typename T>
+int launch_beam(BeamParams p, cudaStream_t stream) {
+    const long long total = p.nsrc * p.ntime * p.nant * p.nchan;
+    if (total <= 0) return 0;
+    const int grid = grid_for(total);
+    int c = 0;
+    while (c < p.ncorr) {  // correlations are independent: blocks of 4, 2, 1
+        p.coff = c;
+        if (p.ncorr - c >= 4) {
+            beam_cube_dde_kernel<T, 4><<<grid, 256, 0, stream>>>(p);
+            c += 4;
+        } else if (p.ncorr - c >= 2) {
+            beam_cube_dde_kernel<T, 2><<<grid, 256, 0, stream>>>(p);
+            c += 2;
+        } else {
+            beam_cube_dde_kernel<T, 1><<<grid, 256, 0, stream>>>(p);
+            c += 1;
+        }
+        AFR_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace
+}  // namespace afr
+
+using namespace afr;
+
+extern "C" int afr_freq_grid_interp(const double *freq, const double *beam_freq_map,
+                                    int64_t nchan, int64_t nud, double *freq_data,
+                                    void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AFR_REQUIRE(nud >= 1 && nchan >= 0, "afr_freq_grid_interp: bad extent");
+    if (nchan == 0) return 0;
+    freq_grid_interp_kernel<<<(int)((nchan + 255) / 256), 256, 0, stream>>>(freq, beam_freq_map,
+                                                                          nchan, nud, freq_data);
+    AFR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int afr_beam_cube_dde(const void *beam, const double *ext_host_or_dev,
+                                 const double *beam_freq_map, const double *lm,
+                                 const double *parallactic_angles, const double *point_errors,
+                                 const double *antenna_scaling, const double *freq, int64_t lw,
+                                 int64_t mh, int64_t nud, int64_t ncorr, int64_t nsrc,
+                                 int64_t ntime, int64_t nant, int64_t nchan, int is_c64,
+                                 void *out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // fast_beam_cubes.py:74-75
+    AFR_REQUIRE(lw >= 2 && mh >= 2 && nud >= 2, "beam_lw, beam_mh and beam_nud must be >= 2");
+    AFR_REQUIRE(ncorr >= 1 && nsrc >= 0 && ntime >= 0 && nant >= 0 && nchan >= 0, "bad extent");
+    if (nsrc == 0 || ntime == 0 || nant == 0 || nchan == 0) return 0;
+    // the four extents are needed on the host to form lscale/mscale (:83-92)
+    double ext[4];
+    AFR_CUDA_OK(cudaMemcpyAsync(ext, ext_host_or_dev, sizeof(ext), cudaMemcpyDefault, stream));
+    AFR_CUDA_OK(cudaStreamSynchronize(stream));
+    Scratch fd;
+    AFR_CUDA_OK(fd.alloc(sizeof(double) * 3 * (size_t)nchan, stream));
+    int rc = afr_freq_grid_interp(freq, beam_freq_map, nchan, nud, (double *)fd.ptr, stream_);
+    if (rc) return rc;
+    BeamParams p{};
+    p.beam = beam;
+    p.fd = (const double *)fd.ptr;
+    p.lm = lm;
+    p.pa = parallactic_angles;
+    p.perr = point_errors;
+    p.ascale = antenna_scaling;
+    p.out = out;
+    p.lower_l = ext[0];
+    p.lower_m = ext[2];
+    p.lmaxf = (double)(lw - 1);
+    p.mmaxf = (double)(mh - 1);
+    p.lscale = p.lmaxf / (ext[1] - ext[0]);
+    p.mscale = p.mmaxf / (ext[3] - ext[2]);
+    p.lw = lw;
+    p.mh = mh;
+    p.nud = nud;
+    p.nsrc = nsrc;
+    p.ntime = ntime;
+    p.nant = nant;
+    p.nchan = nchan;
+    p.ncorr = (int)ncorr;
+    return is_c64 ? launch_beam<float>(p, stream) : launch_beam<double>(p, stream);
+}

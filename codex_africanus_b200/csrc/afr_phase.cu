@@ -1,0 +1,172 @@
+// phase_delay (africanus/rime/phase.py:11-63) for sm_100a.
+//
+// Stand-alone, the K term is bound by the HBM store of its (source,row,chan) output
+// (16 B/term complex128, 8 B/term complex64), so the kernel is organised around the
+// store: one thread produces a run of kRun consecutive channels (kRun * 16 B contiguous,
+// 128-bit stores), consecutive threads produce consecutive runs, and the phasor inside a
+// run advances by a complex rotation from a sincos anchor (equispaced channels) or by one
+// sincos per channel (arbitrary channels / float32 inputs, where the reference's per-channel
+// rounding of the phase must be reproduced).
+#include "afr_dft.cuh"
+
+namespace afr {
+namespace {
+
+constexpr int kRun = 8;  // channels per thread
+
+struct PhaseParams {
+    const double *lmn;   // (nsrc,3), n already clamped (rime/phase.py:42-43)
+    const double *uvw;   // (nrow,3)
+    const double *freq;  // (nchan,)
+    double *out;         // (nsrc,nrow,nchan) complex128
+    double cst;          // signed, lm.dtype-rounded (phase.py:25)
+    long long nsrc, nrow;
+    int nchan;
+    int all_f32_coords;  // lm and uvw were float32: l*u + m*v + n*w and cst*(.) in float32
+};
+
+__device__ __forceinline__ double real_phase(const PhaseParams &p, long long s, long long r) {
+    const double l = p.lmn[3 * s], m = p.lmn[3 * s + 1], n = p.lmn[3 * s + 2];
+    const double u = p.uvw[3 * r], v = p.uvw[3 * r + 1], w = p.uvw[3 * r + 2];
+    if (p.all_f32_coords) {
+        const float a = __fadd_rn(__fadd_rn(__fmul_rn((float)l, (float)u), __fmul_rn((float)m, (float)v)),
+                                  __fmul_rn((float)n, (float)w));
+        return (double)__fmul_rn((float)p.cst, a);
+    }
+    return __dmul_rn(p.cst, phase_dot(l, m, n, u, v, w, false));
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(256) phase_delay_f64_kernel(const PhaseParams p) {
+    const int runs = (p.nchan + kRun - 1) / kRun;
+    const long long total = p.nsrc * p.nrow * runs;
+    double dnu = 0.0;
+    if (!EXACT && p.nchan > 1) dnu = (p.freq[p.nchan - 1] - p.freq[0]) / (double)(p.nchan - 1);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long sr = i / runs;
+        const int k = (int)(i - sr * runs);
+        const long long s = sr / p.nrow, r = sr - s * p.nrow;
+        const double phi = real_phase(p, s, r);
+        const int f0 = k * kRun;
+        double2 *o = reinterpret_cast<double2 *>(p.out) + (sr * p.nchan + f0);
+        if (EXACT) {
+#pragma unroll
+            for (int j = 0; j < kRun; ++j) {
+                if (f0 + j < p.nchan) {
+                    const C2<double> z = cis(__dmul_rn(phi, p.freq[f0 + j]));
+                    o[j] = make_double2(z.re, z.im);
+                }
+            }
+        } else {
+            C2<double> z = cis(__dmul_rn(phi, p.freq[f0]));
+            const C2<double> d = cis(__dmul_rn(phi, dnu));
+#pragma unroll
+            for (int j = 0; j < kRun; ++j) {
+                if (f0 + j < p.nchan) o[j] = make_double2(z.re, z.im);
+                z = cmul(z, d);
+            }
+        }
+    }
+}
+
+// all-float32 inputs: the reference does the entire phase in float32 (phase.py:23-26);
+// p is rounded to float32 per channel, so no recurrence is possible.
+__global__ void __launch_bounds__(256)
+    phase_delay_f32_kernel(const float *lm, const float *uvw, const float *freq, float2 *out,
+                           float cst, long long nsrc, long long nrow, int nchan) {
+    const int runs = (nchan + kRun - 1) / kRun;
+    const long long total = nsrc * nrow * runs;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long sr = i / runs;
+        const int k = (int)(i - sr * runs);
+        const long long s = sr / nrow, r = sr - s * nrow;
+        const float l = lm[2 * s], m = lm[2 * s + 1];
+        float n = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(l, l)), __fmul_rn(m, m));
+        n = __fsub_rn(__fsqrt_rn(n < 0.0f ? 0.0f : n), 1.0f);
+        const float u = uvw[3 * r], v = uvw[3 * r + 1], w = uvw[3 * r + 2];
+        const float rp = __fmul_rn(
+            cst, __fadd_rn(__fadd_rn(__fmul_rn(l, u), __fmul_rn(m, v)), __fmul_rn(n, w)));
+        const int f0 = k * kRun;
+        float2 *o = out + (sr * nchan + f0);
+#pragma unroll
+        for (int j = 0; j < kRun; ++j) {
+            if (f0 + j < nchan) {
+                const float ph = __fmul_rn(rp, freq[f0 + j]);
+                float sn, cs;
+                sincosf(ph, &sn, &cs);
+                o[j] = make_float2(cs, sn);
+            }
+        }
+    }
+}
+
+int grid_for(long long total) {
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+}  // namespace afr
+
+using namespace afr;
+
+extern "C" int afr_phase_delay_f64(const double *lm, const double *uvw, const double *freq,
+                                   int64_t nsrc, int64_t nrow, int64_t nchan, int convention,
+                                   int f32_flags, int chan_mode, void *out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AFR_REQUIRE(convention == AFR_FOURIER || convention == AFR_CASA,
+                "convention not in ('fourier', 'casa')");
+    AFR_REQUIRE(nsrc >= 0 && nrow >= 0 && nchan >= 0 && nchan < (1LL << 30), "bad extent");
+    if (nsrc == 0 || nrow == 0 || nchan == 0) return 0;
+    const bool lm_f32 = (f32_flags & AFR_F32_LM) != 0;
+    const bool uvw_f32 = (f32_flags & AFR_F32_UVW) != 0;
+    Scratch lmn;
+    AFR_CUDA_OK(lmn.alloc(sizeof(double) * 3 * (size_t)nsrc, stream));
+    int rc = launch_lm_to_lmn(lm, nsrc, kLmnPhaseClamp, lm_f32, (double *)lmn.ptr, stream);
+    if (rc) return rc;
+    PhaseParams p{};
+    p.lmn = (const double *)lmn.ptr;
+    p.uvw = uvw;
+    p.freq = freq;
+    p.out = (double *)out;
+    double cst = -kTwoPiOverC;             // phase.py:25,30
+    if (lm_f32) cst = (double)(float)cst;  // constant typed as lm.dtype
+    if (convention == AFR_CASA) cst = -cst;
+    p.cst = cst;
+    p.nsrc = nsrc;
+    p.nrow = nrow;
+    p.nchan = (int)nchan;
+    p.all_f32_coords = (lm_f32 && uvw_f32) ? 1 : 0;
+    const long long total = nsrc * nrow * ((nchan + kRun - 1) / kRun);
+    // float32 coordinates or frequencies: the reference's per-channel rounding is
+    // reproduced by the exact path only
+    const bool exact = chan_mode == AFR_CHAN_EXACT || f32_flags != 0;
+    if (exact)
+        phase_delay_f64_kernel<true><<<grid_for(total), 256, 0, stream>>>(p);
+    else
+        phase_delay_f64_kernel<false><<<grid_for(total), 256, 0, stream>>>(p);
+    AFR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int afr_phase_delay_f32(const float *lm, const float *uvw, const float *freq,
+                                   int64_t nsrc, int64_t nrow, int64_t nchan, int convention,
+                                   void *out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AFR_REQUIRE(convention == AFR_FOURIER || convention == AFR_CASA,
+                "convention not in ('fourier', 'casa')");
+    AFR_REQUIRE(nsrc >= 0 && nrow >= 0 && nchan >= 0 && nchan < (1LL << 30), "bad extent");
+    if (nsrc == 0 || nrow == 0 || nchan == 0) return 0;
+    float cst = (float)(-kTwoPiOverC);
+    if (convention == AFR_CASA) cst = -cst;
+    const long long total = nsrc * nrow * ((nchan + kRun - 1) / kRun);
+    phase_delay_f32_kernel<<<grid_for(total), 256, 0, stream>>>(lm, uvw, freq, (float2 *)out, cst,
+                                                               nsrc, nrow, (int)nchan);
+    AFR_CUDA_OK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,118 @@
+// Library plumbing: error text, device queries, frequency-grid check and the
+// FMA pipe peak measurement used as the roofline denominator.
+#include <cmath>
+
+#include "afr_common.cuh"
+
+namespace afr {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int fail(const std::string &msg) {
+    g_last_error = msg;
+    return 1;
+}
+
+namespace {
+
+// Each thread runs kChains independent FMA chains; with 1024 resident threads per
+// SM this saturates the FP64 (or FP32) pipe.  2 FLOP per FMA.
+template <typename T, int kChains>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T *sink, int iters, T a, T b) {
+    T acc[kChains];
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) acc[k] = (T)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < kChains; ++k) acc[k] = fma(acc[k], a, b);
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) s += acc[k];
+    if (s == (T)123456789) sink[0] = s;  // never true; keeps the chains alive
+}
+
+}  // namespace
+}  // namespace afr
+
+using namespace afr;
+
+extern "C" int afr_version(void) { return AFR_VERSION; }
+
+extern "C" const char *afr_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int afr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int afr_set_device(int device) {
+    AFR_CUDA_OK(cudaSetDevice(device));
+    return 0;
+}
+
+extern "C" int afr_device_info(int device, int *sm_count_, int *cc_major, int *cc_minor,
+                               int *clock_khz) {
+    int v = 0;
+    AFR_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    if (sm_count_) *sm_count_ = v;
+    AFR_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, device));
+    if (cc_major) *cc_major = v;
+    AFR_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, device));
+    if (cc_minor) *cc_minor = v;
+    AFR_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device));
+    if (clock_khz) *clock_khz = v;
+    return 0;
+}
+
+extern "C" int afr_freq_is_uniform(const double *freq, int64_t nchan, double rtol) {
+    if (nchan <= 2) return 1;
+    const double step = (freq[nchan - 1] - freq[0]) / (double)(nchan - 1);
+    double amax = 0.0;
+    for (int64_t i = 0; i < nchan; ++i) amax = std::fmax(amax, std::fabs(freq[i]));
+    for (int64_t i = 0; i < nchan; ++i) {
+        const double want = freq[0] + step * (double)i;
+        if (!(std::fabs(freq[i] - want) <= rtol * amax)) return 0;
+    }
+    return 1;
+}
+
+extern "C" int afr_measure_fma_peak(int fp64, int iters, double *flops_per_s, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AFR_REQUIRE(iters > 0 && flops_per_s != nullptr, "afr_measure_fma_peak: bad arguments");
+    constexpr int kChains = 8;
+    const int blocks = sm_count() * 8;
+    void *sink = nullptr;
+    AFR_CUDA_OK(cudaMalloc(&sink, 64));
+    cudaEvent_t e0, e1;
+    AFR_CUDA_OK(cudaEventCreate(&e0));
+    AFR_CUDA_OK(cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {  // first rep is the warm-up
+        AFR_CUDA_OK(cudaEventRecord(e0, stream));
+        if (fp64)
+            fma_peak_kernel<double, kChains><<<blocks, 256, 0, stream>>>((double *)sink, iters,
+                                                                        0.999999, 1e-9);
+        else
+            fma_peak_kernel<float, kChains><<<blocks, 256, 0, stream>>>((float *)sink, iters,
+                                                                       0.999999f, 1e-9f);
+        AFR_CUDA_OK(cudaEventRecord(e1, stream));
+        AFR_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        AFR_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    AFR_CUDA_OK(cudaGetLastError());
+    const double fmas = (double)blocks * 256.0 * (double)kChains * (double)iters;
+    *flops_per_s = 2.0 * fmas / ((double)best_ms * 1e-3);
+    return 0;
+}

@@ -1,0 +1,9 @@
+"""RIME terms -- mirrors the hot-path subset of ``africanus.rime``
+(africanus/rime/__init__.py:3-10) plus the fused predict."""
+from .phase import phase_delay  # noqa: F401
+from .predict import apply_gains, predict_vis  # noqa: F401
+from .fast_beam_cubes import beam_cube_dde, freq_grid_interp  # noqa: F401
+from .fused import fused_predict_vis  # noqa: F401
+
+__all__ = ["phase_delay", "predict_vis", "apply_gains", "beam_cube_dde", "freq_grid_interp",
+           "fused_predict_vis"]

@@ -1,0 +1,147 @@
+/*
+ * africanus_b200.h -- C ABI of libafricanus_b200.so
+ *
+ * B200 (sm_100a) implementation of the codex-africanus RIME / DFT hot path.
+ * The reference (ratt-ru/codex-africanus 0.4.4) has no native ABI: its
+ * interface for this path is a set of Python callables
+ *     africanus/rime/__init__.py:3-10   phase_delay, predict_vis, apply_gains, beam_cube_dde
+ *     africanus/dft/__init__.py:3       im_to_vis, vis_to_im
+ * and alternative backends are sibling modules exporting the same names
+ * (africanus/rime/cuda/__init__.py:3-6).  The functions below are what a
+ * ctypes/cffi binding for such a sibling module binds; each cites the
+ * reference callable it stands behind.  See INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *  - every array pointer is a DEVICE pointer on the current CUDA device, dense
+ *    C-contiguous in the reference's documented layout; complex = interleaved
+ *    (re, im).  Inputs are read-only; outputs are caller-allocated.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    Calls are asynchronous with respect to the host unless stated otherwise.
+ *  - real coordinate inputs (uvw, lm, frequency ...) are float64.  Where the
+ *    reference rounds an intermediate to float32 because the caller's arrays
+ *    were float32, the AFR_F32_* flags request the same rounding (the caller
+ *    widens the values exactly and says what they were).
+ *  - return value 0 = success; non-zero = error, text in afr_last_error()
+ *    (thread-local).  The library is re-entrant and keeps no global mutable
+ *    state besides that thread-local string.
+ */
+#ifndef AFRICANUS_B200_H
+#define AFRICANUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFR_VERSION 100
+
+/* sign convention: africanus/rime/phase.py:29-34, africanus/dft/kernels.py:34-39,110-115 */
+#define AFR_FOURIER 1
+#define AFR_CASA (-1)
+
+/* dtype-origin flags (bitmask) */
+#define AFR_F32_LM 1   /* lm was float32   */
+#define AFR_F32_UVW 2  /* uvw was float32  */
+#define AFR_F32_FREQ 4 /* frequency was float32 */
+
+/* channel mode */
+#define AFR_CHAN_EXACT 0   /* one sincos per (source,row,chan): any frequency array */
+#define AFR_CHAN_UNIFORM 1 /* equispaced channels: anchored complex-rotation recurrence */
+
+/* Jones correlation mode: africanus/rime/predict.py:10-12 */
+#define AFR_JONES_DIAG 0 /* trailing (ncorr,) multiplied element-wise */
+#define AFR_JONES_2X2 1  /* trailing (2,2) matrix products, ncorr == 4 */
+
+/* ---- library / device ------------------------------------------------- */
+int afr_version(void);
+const char *afr_last_error(void);
+int afr_device_count(void);
+/* Select the CUDA device used by subsequent calls on this host thread.  The library
+ * links its own (static) CUDA runtime, whose current-device state is separate from any
+ * other runtime in the process (e.g. PyTorch's): bindings call this before each entry
+ * point with the device that owns the pointers. */
+int afr_set_device(int device);
+/* sm_count, compute capability and SM clock (kHz) of `device` */
+int afr_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, int *clock_khz);
+/* 1 if `freq` (HOST pointer) is equispaced to within rtol*max|freq| */
+int afr_freq_is_uniform(const double *freq_host, int64_t nchan, double rtol);
+
+/* Measured pipe peaks for the roofline denominators: runs a dependent-free
+ * DFMA (fp64 != 0) or FFMA chain on every SM for `iters` iterations and
+ * returns achieved FLOP/s (FMA = 2).  Synchronous. */
+int afr_measure_fma_peak(int fp64, int iters, double *flops_per_s, void *stream);
+
+/* ---- africanus.dft.im_to_vis  (africanus/dft/kernels.py:14-69) --------- */
+/* image (nsrc,nchan,ncorr) float64 or complex128 (image_complex);
+ * uvw (nrow,3); lm (nsrc,2); freq (nchan,);
+ * out (nrow,nchan,ncorr) complex128, or complex64 when out_c64. */
+int afr_im_to_vis(const void *image, int image_complex, const double *uvw, const double *lm,
+                  const double *freq, int64_t nsrc, int64_t nrow, int64_t nchan, int64_t ncorr,
+                  int convention, int f32_flags, int chan_mode, int out_c64, void *out,
+                  void *stream);
+
+/* ---- africanus.dft.vis_to_im  (africanus/dft/kernels.py:72-148) -------- */
+/* vis (nrow,nchan,ncorr) float64 or complex128 (vis_complex); flags uint8 same shape
+ * (NULL = nothing flagged); out (nsrc,nchan,ncorr) float64, or float32 when out_f32. */
+int afr_vis_to_im(const void *vis, int vis_complex, const double *uvw, const double *lm,
+                  const double *freq, const uint8_t *flags, int64_t nsrc, int64_t nrow,
+                  int64_t nchan, int64_t ncorr, int convention, int f32_flags, int chan_mode,
+                  int out_f32, void *out, void *stream);
+
+/* ---- africanus.rime.phase_delay  (africanus/rime/phase.py:11-63) ------- */
+/* out (nsrc,nrow,nchan) complex128.  f32_flags reproduce the lm.dtype-typed
+ * constants (phase.py:23-25).  All-float32 inputs use afr_phase_delay_f32. */
+int afr_phase_delay_f64(const double *lm, const double *uvw, const double *freq, int64_t nsrc,
+                        int64_t nrow, int64_t nchan, int convention, int f32_flags,
+                        int chan_mode, void *out, void *stream);
+/* all inputs float32, whole phase in float32, out complex64 (phase.py:23-26) */
+int afr_phase_delay_f32(const float *lm, const float *uvw, const float *freq, int64_t nsrc,
+                        int64_t nrow, int64_t nchan, int convention, void *out, void *stream);
+
+/* ---- africanus.rime.predict_vis / apply_gains (africanus/rime/predict.py:466-649) */
+/* time_index/antenna1/antenna2 (nrow,) int32, time_index ALREADY minus its minimum
+ * (predict.py:597).  dde{1,2} (nsrc,ntime,nant,nchan,C), source_coh (nsrc,nrow,nchan,C),
+ * die{1,2} (ntime,nant,nchan,C), base_vis (nrow,nchan,C), out (nrow,nchan,C); C = ncorr
+ * complex values; any of the inputs may be NULL subject to the reference's pairing
+ * rules (predict.py:403-407).  is_c64: all arrays complex64, else complex128. */
+int afr_predict_vis(const int32_t *time_index, const int32_t *antenna1, const int32_t *antenna2,
+                    const void *dde1, const void *source_coh, const void *dde2, const void *die1,
+                    const void *base_vis, const void *die2, int64_t nsrc, int64_t nrow,
+                    int64_t ntime, int64_t nant, int64_t nchan, int64_t ncorr, int jones_mode,
+                    int is_c64, void *out, void *stream);
+
+/* ---- fused phase_delay (x) brightness -> predict_vis -------------------- */
+/* The composition africanus/rime/examples/predict.py:107-134,490,522-527
+ * (asserted in africanus/experimental/rime/fused/tests/test_rime.py:175-209)
+ * without materialising the (source,row,chan[,corr]) intermediates:
+ *   V[r,f] = G1 (B[r,f] + sum_s E1 (K[s,r,f] Bright[s,f]) E2^H) G2^H
+ * brightness (nsrc,nchan,C) complex; other arrays as afr_predict_vis.
+ * out_c64: brightness/dde/die/base_vis/out are complex64 and the Jones chain
+ * runs in FP32, while the phase argument stays FP64. */
+int afr_predict_fused(const double *lm, const double *uvw, const double *freq,
+                      const void *brightness, const int32_t *time_index,
+                      const int32_t *antenna1, const int32_t *antenna2, const void *dde1,
+                      const void *dde2, const void *die1, const void *base_vis, const void *die2,
+                      int64_t nsrc, int64_t nrow, int64_t ntime, int64_t nant, int64_t nchan,
+                      int64_t ncorr, int jones_mode, int convention, int chan_mode, int out_c64,
+                      void *out, void *stream);
+
+/* ---- africanus.rime.beam_cube_dde (africanus/rime/fast_beam_cubes.py:57-240) */
+/* beam (lw,mh,nud,ncorr) complex; extents (2,2); beam_freq_map (nud,); lm (nsrc,2);
+ * parallactic_angles (ntime,nant); point_errors (ntime,nant,nchan,2);
+ * antenna_scaling (nant,nchan,2); freq (nchan,); out (nsrc,ntime,nant,nchan,ncorr). */
+int afr_beam_cube_dde(const void *beam, const double *beam_lm_extents,
+                      const double *beam_freq_map, const double *lm,
+                      const double *parallactic_angles, const double *point_errors,
+                      const double *antenna_scaling, const double *freq, int64_t lw, int64_t mh,
+                      int64_t nud, int64_t ncorr, int64_t nsrc, int64_t ntime, int64_t nant,
+                      int64_t nchan, int is_c64, void *out, void *stream);
+/* freq_grid_interp (fast_beam_cubes.py:10-54): freq_data (nchan,3) float64 */
+int afr_freq_grid_interp(const double *freq, const double *beam_freq_map, int64_t nchan,
+                         int64_t nud, double *freq_data, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFRICANUS_B200_H */

@@ -1,0 +1,407 @@
+"""
+GPU parity tests (B200): every entry point of codex_africanus_b200, called through the
+ctypes C-ABI, against (i) the committed golden vectors produced by the reference's numba
+implementation and (ii) the CPU oracle on fresh seeded inputs.
+
+Gates:  complex128 / float64 -> allclose(rtol=1e-10, atol=1e-10*max|ref|);
+complex64 / float32 -> ||got - ref||_2 <= 1e-5 ||ref||_2.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+from conftest import assert_c128_close, assert_c64_close, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+C = 2.99792458e8
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import codex_africanus_b200.dft as dft
+    import codex_africanus_b200.rime as rime
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.dft, ns.rime = dft, rime
+    return ns
+
+
+# ----------------------------------------------------------------------------- phase_delay
+def test_phase_delay_golden(b200, golden):
+    g = golden("phase_delay")
+    lm, uvw, freq = g["lm"], g["uvw"], g["freq"]
+    for conv in ("fourier", "casa"):
+        assert_c128_close(b200.rime.phase_delay(lm, uvw, freq, convention=conv), g["f64_" + conv])
+    assert_c128_close(b200.rime.phase_delay(lm, uvw, g["freq_nu"]), g["f64_nonuniform"])
+    f32 = np.float32
+    lm_s, uvw_s = g["lm_s"], g["uvw_s"]
+    got = b200.rime.phase_delay(lm_s.astype(f32), uvw_s.astype(f32), freq.astype(f32))
+    assert_c64_close(got, g["f32_all"])
+    assert np.max(np.abs(got - g["f32_all"])) < 2e-6
+    assert_c128_close(b200.rime.phase_delay(lm_s.astype(f32), uvw_s, freq), g["mix_lm32"])
+    assert_c128_close(b200.rime.phase_delay(lm_s.astype(f32), uvw_s.astype(f32), freq), g["mix_lm32_uvw32"])
+    assert_c128_close(b200.rime.phase_delay(lm_s, uvw_s.astype(f32), freq), g["mix_uvw32"])
+    assert_c128_close(b200.rime.phase_delay(lm_s, uvw_s, freq.astype(f32)), g["mix_freq32"])
+
+
+@pytest.mark.parametrize("convention, sign", [("fourier", 1), ("casa", -1)])
+def test_phase_delay_known_answer(b200, convention, sign):
+    # rime/tests/test_rime.py:19-47; the rotation recurrence is not bit-exact, so the
+    # reference's == becomes the project gate
+    rng = np.random.default_rng(0)
+    uvw = rng.random((100, 3))
+    lm = rng.random((10, 2))
+    frequency = np.linspace(0.856e9, 0.856e9 * 2, 64, endpoint=True)
+    uvw[2] = [1, 2, 3]
+    lm[3] = [0.1, 0.2]
+    cp = b200.rime.phase_delay(lm, uvw, frequency, convention=convention)
+    n = np.sqrt(1.0 - 0.1**2 - 0.2**2) - 1.0
+    phase = sign * (-2 * np.pi / C) * (1 * 0.1 + 2 * 0.2 + 3 * n) * frequency[5]
+    assert abs(np.exp(1j * phase) - cp[3, 2, 5]) < 1e-10
+
+
+def test_phase_delay_vs_oracle_ragged(b200, oracle):
+    rng = np.random.default_rng(11)
+    for nsrc, nrow, nchan in [(1, 1, 1), (3, 5, 7), (2, 129, 33), (5, 64, 256)]:
+        lm = rng.uniform(-0.1, 0.1, (nsrc, 2))
+        uvw = rng.standard_normal((nrow, 3)) * 3000
+        freq = np.linspace(0.856e9, 1.712e9, nchan) if nchan > 1 else np.array([1.0e9])
+        assert_c128_close(b200.rime.phase_delay(lm, uvw, freq), oracle.phase_delay(lm, uvw, freq))
+    out = b200.rime.phase_delay(np.zeros((0, 2)), np.zeros((4, 3)), np.ones(3))
+    assert out.shape == (0, 4, 3) and out.dtype == np.complex128
+
+
+# ----------------------------------------------------------------------------- dft
+def test_dft_golden(b200, golden):
+    g = golden("dft")
+    lm, uvw, freq = g["lm"], g["uvw"], g["freq"]
+    f32 = np.float32
+    for nc in (1, 2, 4):
+        assert_c128_close(b200.dft.im_to_vis(g["image_r%d" % nc], uvw, lm, freq), g["i2v_r%d" % nc])
+        got = b200.dft.vis_to_im(g["vis_c%d" % nc], uvw, lm, freq, g["flags_%d" % nc])
+        assert_c128_close(got, g["v2i_c%d" % nc])
+    assert_c128_close(b200.dft.im_to_vis(g["image_c2"], uvw, lm, freq), g["i2v_c2"])
+    assert_c128_close(b200.dft.im_to_vis(g["image_c2"], uvw, lm, freq, convention="casa"), g["i2v_c2_casa"])
+    assert_c128_close(b200.dft.im_to_vis(g["image_r1"], uvw, lm, g["freq_nu"]), g["i2v_r1_nonuniform"])
+    assert_c64_close(b200.dft.im_to_vis(g["image_r1"], uvw, lm, freq, dtype=np.complex64), g["i2v_r1_c64"])
+    got = b200.dft.im_to_vis(g["image_r1"].astype(f32), uvw.astype(f32), lm.astype(f32), freq.astype(f32))
+    assert_c64_close(got, g["i2v_r1_in32"], tol=2e-5)
+    assert_c128_close(b200.dft.im_to_vis(g["image_r1"], uvw, lm.astype(f32), freq), g["i2v_r1_lm32"])
+    assert_c128_close(b200.dft.vis_to_im(g["vis_r2"], uvw, lm, freq, g["flags_2"]), g["v2i_r2"])
+    assert_c128_close(
+        b200.dft.vis_to_im(g["vis_c1"], uvw, lm, freq, g["flags_1"], convention="casa"), g["v2i_c1_casa"])
+    assert_c64_close(
+        b200.dft.vis_to_im(g["vis_c1"], uvw, lm, freq, g["flags_1"], dtype=np.float32), g["v2i_c1_f32"])
+    assert_c128_close(
+        b200.dft.vis_to_im(g["vis_c1"], uvw, lm, g["freq_nu"], g["flags_1"]), g["v2i_c1_nonuniform"])
+    got = b200.dft.vis_to_im(g["vis_c1"].astype(np.complex64), uvw.astype(f32), lm.astype(f32),
+                             freq.astype(f32), g["flags_1"])
+    assert_c64_close(got, g["v2i_c1_in32"], tol=2e-5)
+
+
+@pytest.mark.parametrize("nsrc,nrow,nchan,ncorr", [
+    (1, 1, 1, 1), (7, 33, 5, 1), (40, 300, 64, 1), (19, 77, 256, 1), (9, 41, 300, 2),
+    (11, 65, 70, 4), (6, 35, 17, 3), (3000, 40, 16, 1),
+])
+def test_dft_vs_oracle_shapes(b200, oracle, nsrc, nrow, nchan, ncorr):
+    """ragged / non-multiple-of-tile shapes, channel tails, y-split path (many sources, few rows)"""
+    rng = np.random.default_rng(nsrc * 1000 + nrow)
+    lm = rng.uniform(-0.03, 0.03, (nsrc, 2))
+    uvw = rng.standard_normal((nrow, 3)) * 4000.0
+    freq = np.linspace(0.856e9, 1.712e9, nchan) if nchan > 1 else np.array([1.4e9])
+    image = rng.standard_normal((nsrc, nchan, ncorr))
+    assert_c128_close(b200.dft.im_to_vis(image, uvw, lm, freq), oracle.im_to_vis(image, uvw, lm, freq))
+    imagec = image + 1j * rng.standard_normal((nsrc, nchan, ncorr))
+    assert_c128_close(b200.dft.im_to_vis(imagec, uvw, lm, freq), oracle.im_to_vis(imagec, uvw, lm, freq))
+    vis = rng.standard_normal((nrow, nchan, ncorr)) + 1j * rng.standard_normal((nrow, nchan, ncorr))
+    flags = rng.random((nrow, nchan, ncorr)) < 0.05
+    assert_c128_close(b200.dft.vis_to_im(vis, uvw, lm, freq, flags),
+                      oracle.vis_to_im(vis, uvw, lm, freq, flags))
+    assert_c128_close(b200.dft.vis_to_im(vis.real.copy(), uvw, lm, freq, flags),
+                      oracle.vis_to_im(vis.real.copy(), uvw, lm, freq, flags))
+
+
+def test_dft_c64_vs_oracle(b200, oracle):
+    rng = np.random.default_rng(77)
+    nsrc, nrow, nchan = 500, 200, 64
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    uvw = rng.standard_normal((nrow, 3)) * 3000.0
+    freq = np.linspace(0.856e9, 1.712e9, nchan)
+    image = np.abs(rng.standard_normal((nsrc, nchan, 1)))
+    got = b200.dft.im_to_vis(image, uvw, lm, freq, dtype=np.complex64)
+    assert_c64_close(got, oracle.im_to_vis(image, uvw, lm, freq, dtype=np.complex64))
+    # the float64 oracle is the tighter yardstick for the FP32 kernel's own error
+    assert rel_l2(got.astype(np.complex128), oracle.im_to_vis(image, uvw, lm, freq)) < 1e-5
+    vis = rng.standard_normal((nrow, nchan, 1)) + 1j * rng.standard_normal((nrow, nchan, 1))
+    flags = rng.random((nrow, nchan, 1)) < 0.05
+    got = b200.dft.vis_to_im(vis, uvw, lm, freq, flags, dtype=np.float32)
+    assert_c64_close(got, oracle.vis_to_im(vis, uvw, lm, freq, flags, dtype=np.float32))
+
+
+def test_im_to_vis_phase_centre(b200):
+    # dft/tests/test_dft.py:12-42
+    nrow, npix, nchan, ncorr = 100, 35, 11, 2
+    uvw = np.random.default_rng(1).random((nrow, 3))
+    x = np.linspace(-0.1, 0.1, npix)
+    ll, mm = np.meshgrid(x, x)
+    lm = np.vstack((ll.flatten(), mm.flatten())).T
+    frequency = np.linspace(1.0, 2.0, nchan, endpoint=True)
+    image = np.zeros((npix, npix, nchan, ncorr))
+    Inu = (frequency / frequency[nchan // 2]) ** (-0.7)
+    for corr in range(ncorr):
+        image[npix // 2, npix // 2, :, corr] = Inu
+    vis = b200.dft.im_to_vis(image.reshape(npix**2, nchan, ncorr), uvw, lm, frequency)
+    tmp = vis - Inu[None, :, None]
+    assert np.all(np.abs(tmp.real) < 1e-13) and np.all(np.abs(tmp.imag) < 1e-13)
+
+
+@pytest.mark.parametrize("convention", ["fourier", "casa"])
+def test_im_to_vis_fft(b200, convention):
+    # dft/tests/test_dft.py:86-133
+    np.random.seed(123)
+    Fs, iFs = np.fft.fftshift, np.fft.ifftshift
+    npix, ncorr, nsource = 29, 1, 25
+    image = np.zeros((npix, npix, ncorr))
+    Ix = np.random.randint(5, npix - 5, nsource)
+    Iy = np.random.randint(5, npix - 5, nsource)
+    image[Ix, Iy, 0] = np.random.randn(nsource)
+    fft_image = Fs(np.fft.fft2(iFs(image[:, :, 0]))).reshape(npix**2, 1, 1)
+    deltal = 0.001
+    l_coord = np.arange(-(npix // 2), npix // 2 + 1) * deltal
+    ll, mm = np.meshgrid(l_coord, l_coord)
+    lm = np.vstack((ll.flatten(), mm.flatten())).T
+    u = Fs(np.fft.fftfreq(npix, d=deltal))
+    uu, vv = np.meshgrid(u, u)
+    uvw = np.zeros((npix**2, 3))
+    uvw[:, 0], uvw[:, 1] = uu.flatten(), vv.flatten()
+    vis = b200.dft.im_to_vis(image.reshape(npix**2, 1, ncorr), uvw, lm, np.ones(1) * C,
+                             convention=convention)
+    fft_image = np.conj(fft_image) if convention == "casa" else fft_image
+    np.testing.assert_array_almost_equal(vis, fft_image, decimal=12)
+
+
+def test_adjointness_flags_symmetry(b200):
+    # dft/tests/test_dft.py:136-177, :180-215, :297-331
+    np.random.seed(123)
+    nsource, nrow, nchan, ncorr = 21, 31, 3, 4
+    uvw = 100 * np.random.random(size=(nrow, 3))
+    lm = np.vstack((0.01 * np.random.randn(nsource), 0.01 * np.random.randn(nsource))).T
+    frequency = np.arange(1, nchan + 1) * C
+    gamma_im = np.random.randn(nsource, nchan, ncorr)
+    gamma_vis = np.random.randn(nrow, nchan, ncorr)
+    flag = np.zeros((nrow, nchan, ncorr), dtype=bool)
+    LHS = np.vdot(gamma_vis.ravel(), b200.dft.im_to_vis(gamma_im, uvw, lm, frequency).ravel()).real
+    RHS = np.dot(b200.dft.vis_to_im(gamma_vis, uvw, lm, frequency, flag).ravel(), gamma_im.ravel())
+    assert np.abs(LHS - RHS) < 1e-11 * max(1.0, abs(LHS))
+    uvw[0, :] = 0.0
+    vis = np.random.randn(nrow, nchan, ncorr) + 1.0j * np.random.randn(nrow, nchan, ncorr)
+    vis[0, :, :] = 1.0
+    flags = np.ones((nrow, nchan, ncorr), dtype=bool)
+    flags[0, :, :] = 0
+    im = b200.dft.vis_to_im(vis, uvw, lm, np.ones(nchan) * C, flags)
+    np.testing.assert_array_almost_equal(im, np.ones((nsource, nchan, ncorr)), decimal=13)
+    # R^H R symmetric
+    nsource = 25
+    lm = np.random.uniform(-0.05, 0.05, (nsource, 2))
+    uvw = np.random.randn(1000, 3) * 1000
+    uvw[:, 2] = 0.0
+    freq = np.array([1.0e9])
+    flags = np.zeros((1000, 1, 1), dtype=bool)
+    psf = np.zeros((nsource, nsource))
+    for s in range(nsource):
+        Ki = b200.dft.im_to_vis(np.ones((1, 1, 1)), uvw, lm[s].reshape(1, 2), freq)
+        psf[:, s] = b200.dft.vis_to_im(Ki, uvw, lm, freq, flags).squeeze()
+    np.testing.assert_array_almost_equal(psf, psf.T, decimal=9)
+
+
+def test_dft_torch_inputs_and_strides(b200, oracle):
+    import torch
+
+    rng = np.random.default_rng(5)
+    nsrc, nrow, nchan, ncorr = 17, 50, 32, 2
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    uvw = rng.standard_normal((nrow, 3)) * 1000.0
+    freq = np.linspace(1e9, 2e9, nchan)
+    image = rng.standard_normal((nsrc, nchan, ncorr))
+    ref = oracle.im_to_vis(image, uvw, lm, freq)
+    got = b200.dft.im_to_vis(torch.from_numpy(image).cuda(), torch.from_numpy(uvw).cuda(),
+                             torch.from_numpy(lm).cuda(), torch.from_numpy(freq).cuda())
+    assert isinstance(got, torch.Tensor) and got.is_cuda
+    assert_c128_close(got.cpu().numpy(), ref)
+    # non-contiguous (transposed) numpy inputs, as calibration/utils/tests/test_utils.py:57-70
+    image_t = np.ascontiguousarray(image.transpose(2, 0, 1)).transpose(1, 2, 0)
+    uvw_t = np.ascontiguousarray(uvw.T).T
+    assert not image_t.flags.c_contiguous
+    assert_c128_close(b200.dft.im_to_vis(image_t, uvw_t, lm, freq), ref)
+
+
+def test_dft_large_properties(b200):
+    """Size-independent checks at a size the oracle cannot reach: linearity and adjointness."""
+    rng = np.random.default_rng(2)
+    nsrc, nrow, nchan = 2000, 20000, 256
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    uvw = rng.standard_normal((nrow, 3)) * 3000.0
+    freq = np.linspace(0.856e9, 1.712e9, nchan)
+    a = rng.standard_normal((nsrc, nchan, 1))
+    b = rng.standard_normal((nsrc, nchan, 1))
+    va = b200.dft.im_to_vis(a, uvw, lm, freq)
+    vb = b200.dft.im_to_vis(b, uvw, lm, freq)
+    vab = b200.dft.im_to_vis(2.0 * a - 3.0 * b, uvw, lm, freq)
+    assert rel_l2(vab, 2.0 * va - 3.0 * vb) < 1e-12
+    y = rng.standard_normal((nrow, nchan, 1)) + 1j * rng.standard_normal((nrow, nchan, 1))
+    flags = np.zeros(y.shape, bool)
+    lhs = np.vdot(y.ravel(), va.ravel()).real
+    rhs = np.dot(b200.dft.vis_to_im(y, uvw, lm, freq, flags).ravel(), a.ravel())
+    assert abs(lhs - rhs) < 1e-10 * max(abs(lhs), np.linalg.norm(y) * np.linalg.norm(va))
+
+
+# ----------------------------------------------------------------------------- predict_vis
+PRESENCE = [(True, True, True), (True, False, True), (False, True, False)]
+
+
+@pytest.mark.parametrize("cname", ["c1", "c2", "c22"])
+def test_predict_vis_golden(b200, golden, cname):
+    g = golden("predict_vis")
+    ti, a1, a2 = g["time_idx"], g["ant1"], g["ant2"]
+    arrs = {k: g["%s_%s" % (cname, k)] for k in ("a1j", "blj", "a2j", "g1j", "bvis", "g2j")}
+    for (d1, bl, d2), (g1, bv, g2) in itertools.product(PRESENCE, PRESENCE):
+        key = "%s_out_%d%d%d_%d%d%d" % (cname, d1, bl, d2, g1, bv, g2)
+        got = b200.rime.predict_vis(
+            ti, a1, a2, arrs["a1j"] if d1 else None, arrs["blj"] if bl else None,
+            arrs["a2j"] if d2 else None, arrs["g1j"] if g1 else None,
+            arrs["bvis"] if bv else None, arrs["g2j"] if g2 else None)
+        assert_c128_close(got, g[key])
+    a64 = {k: v.astype(np.complex64) for k, v in arrs.items()}
+    got = b200.rime.predict_vis(ti.astype(np.int16), a1.astype(np.int16), a2.astype(np.int16),
+                                a64["a1j"], a64["blj"], a64["a2j"], a64["g1j"], a64["bvis"], a64["g2j"])
+    assert_c64_close(got, g["%s_out_c64" % cname])
+    got = b200.rime.apply_gains(ti, a1, a2, arrs["g1j"], arrs["bvis"], arrs["g2j"])
+    assert_c128_close(got, g["%s_out_000_111" % cname])
+
+
+def test_predict_vis_vs_oracle_larger(b200, oracle):
+    rng = np.random.default_rng(21)
+    na, ntime, nchan, nsrc = 7, 5, 19, 13
+    a1, a2 = np.triu_indices(na, 1)
+    ant1, ant2 = np.tile(a1, ntime), np.tile(a2, ntime)
+    ti = np.repeat(np.arange(ntime), a1.size) + 100
+    nrow = ant1.size
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    for corr in ((2, 2), (2,), (1,), (3,)):
+        dde = rc((nsrc, ntime, na, nchan) + corr)
+        coh = rc((nsrc, nrow, nchan) + corr)
+        die = rc((ntime, na, nchan) + corr)
+        bvis = rc((nrow, nchan) + corr)
+        got = b200.rime.predict_vis(ti, ant1, ant2, dde, coh, dde, die, bvis, die)
+        assert_c128_close(got, oracle.predict_vis(ti, ant1, ant2, dde, coh, dde, die, bvis, die))
+
+
+# ----------------------------------------------------------------------------- beam
+def test_beam_cube_dde_golden(b200, golden):
+    g = golden("beam_cube_dde")
+    args = (g["ext"], g["beam_freq_map"], g["lm"], g["pa"], g["perr"], g["ascale"], g["freq"])
+    for cname in ("c22", "c4", "c2", "c1"):
+        assert_c128_close(b200.rime.beam_cube_dde(g["beam_" + cname], *args), g["dde_" + cname])
+    got = b200.rime.beam_cube_dde(g["beam_c22"].astype(np.complex64), *args)
+    assert_c64_close(got, g["dde_c22_c64"])
+    ka = b200.rime.beam_cube_dde(
+        g["ka_beam"], np.asarray([[-1.0, 1.0], [-1.0, 1.0]]), np.asarray([0.0, 1.0]),
+        np.asarray([[0.1, 0.1]]), np.zeros((1, 1)), np.zeros((1, 1, 1, 2)), np.ones((1, 1, 2)),
+        np.asarray([0.3]))
+    np.testing.assert_array_almost_equal([[[[[0.470255 + 0.4786j]]]]], ka)  # test_fast_beams.py:126
+    assert_c128_close(ka, g["ka_dde"])
+    np.testing.assert_array_equal(b200.rime.freq_grid_interp(g["freq"], g["beam_freq_map"]), g["freq_data"])
+
+
+def test_beam_cube_dde_vs_oracle(b200, oracle):
+    rng = np.random.default_rng(31)
+    lw, mh, nud = 33, 31, 7
+    nsrc, ntime, nant, nchan = 23, 3, 5, 37
+    bfm = np.linspace(0.856e9, 1.712e9, nud)
+    freq = np.linspace(0.8e9, 1.8e9, nchan)
+    ext = np.array([[-0.05, 0.05], [-0.04, 0.06]])
+    lm = rng.uniform(-0.06, 0.06, (nsrc, 2))
+    pa = rng.uniform(-np.pi, np.pi, (ntime, nant))
+    perr = rng.uniform(-0.005, 0.005, (ntime, nant, nchan, 2))
+    ascale = rng.uniform(0.9, 1.1, (nant, nchan, 2))
+    for corr in ((2, 2), (3,)):
+        beam = rng.standard_normal((lw, mh, nud) + corr) + 1j * rng.standard_normal((lw, mh, nud) + corr)
+        got = b200.rime.beam_cube_dde(beam, ext, bfm, lm, pa, perr, ascale, freq)
+        assert_c128_close(got, oracle.beam_cube_dde(beam, ext, bfm, lm, pa, perr, ascale, freq))
+
+
+# ----------------------------------------------------------------------------- fused
+def test_fused_predict_golden(b200, golden):
+    g = golden("fused_predict")
+    ti, a1, a2 = g["time_idx"], g["ant1"], g["ant2"]
+    lm, uvw, freq = g["lm"], g["uvw"], g["freq"]
+    for conv in ("fourier", "casa"):
+        for cname in ("c22", "c2", "c1"):
+            key = "%s_%s" % (conv, cname)
+            br, die, bvis = g["bright_" + key], g["die_" + key], g["bvis_" + key]
+            got = b200.rime.fused_predict_vis(lm, uvw, freq, br, ti, a1, a2, convention=conv)
+            assert_c128_close(got, g["point_" + key])
+            got = b200.rime.fused_predict_vis(lm, uvw, freq, br, ti, a1, a2, die1_jones=die,
+                                              base_vis=bvis, die2_jones=die, convention=conv)
+            assert_c128_close(got, g["point_die_" + key])
+            dde = g["dde_beam_c22"] if cname == "c22" else g["dde_" + key]
+            got = b200.rime.fused_predict_vis(lm, uvw, freq, br, ti, a1, a2, dde, dde, die, bvis,
+                                              die, convention=conv)
+            assert_c128_close(got, g["full_" + key])
+    # beam_cube_dde -> fused predict end to end on the GPU (no host round trip for the DDEs)
+    import torch
+
+    nchan = freq.shape[0]
+    ntime, na = g["pa"].shape
+    dde = b200.rime.beam_cube_dde(
+        torch.from_numpy(g["beam"]).cuda(), g["ext"], g["bfm"], lm, g["pa"],
+        np.zeros((ntime, na, nchan, 2)), np.ones((na, nchan, 2)), freq)
+    key = "fourier_c22"
+    got = b200.rime.fused_predict_vis(lm, uvw, freq, g["bright_" + key], ti, a1, a2, dde, dde,
+                                      g["die_" + key], g["bvis_" + key], g["die_" + key])
+    assert_c128_close(got.cpu().numpy(), g["full_" + key])
+
+
+def test_fused_predict_vs_oracle(b200, oracle):
+    """MeerKAT-like slice: 12 antennas, 300 channels (recurrence across several runs/segments),
+    non-uniform channels (exact path), complex64 chain."""
+    rng = np.random.default_rng(41)
+    na, ntime, nsrc = 12, 3, 29
+    a1, a2 = np.triu_indices(na, 1)
+    ant1, ant2 = np.tile(a1, ntime), np.tile(a2, ntime)
+    ti = np.repeat(np.arange(ntime), a1.size) + 7
+    nrow = ant1.size
+    uvw = rng.standard_normal((nrow, 3)) * 2500.0
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    for nchan, uniform in ((300, True), (64, True), (40, False)):
+        freq = np.linspace(0.856e9, 1.712e9, nchan)
+        if not uniform:
+            freq = np.sort(rng.uniform(0.856e9, 1.712e9, nchan))
+        for corr in ((2, 2), (2,)):
+            bright = rc((nsrc, nchan) + corr)
+            dde = 1.0 + 0.2 * rc((nsrc, ntime, na, nchan) + corr)
+            die = 1.0 + 0.1 * rc((ntime, na, nchan) + corr)
+            bvis = rc((nrow, nchan) + corr)
+            ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2)
+            assert_c128_close(b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2), ref)
+            ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die)
+            got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die)
+            assert_c128_close(got, ref)
+            c64 = np.complex64
+            got = b200.rime.fused_predict_vis(lm, uvw, freq, bright.astype(c64), ti, ant1, ant2,
+                                              dde.astype(c64), dde.astype(c64), die.astype(c64),
+                                              bvis.astype(c64), die.astype(c64))
+            assert got.dtype == c64
+            assert rel_l2(got.astype(np.complex128), ref) < 1e-5
