@@ -8,48 +8,68 @@
 //
 // B200 mapping (the path is FP64-pipe bound, bytes/term << 1, no GEMM is pretended):
 //  * one lane owns one x (32 owners per warp), one warp owns a run of CH channels, so a
-//    thread keeps CH*ncorr accumulators in registers for the whole y loop;
-//  * y is streamed in tiles of kYT through shared memory: the W tile (read once per CTA,
-//    broadcast to all 32 lanes) and, per (x, y) pair, the channel-run ANCHORS
-//    exp(i*phi*nu_f0) plus the per-channel step exp(i*phi*dnu);
+//    thread keeps CH*ncorr accumulators in registers for the whole y loop; a CTA is NW warps
+//    = (owner groups) x (channel runs);
+//  * y is streamed in tiles of yt items through DOUBLE-BUFFERED shared memory with one
+//    barrier per tile: the W tile and the y coordinates arrive by cp.async (16-byte
+//    coalesced copies, zero-filled at the edges) issued one tile ahead, and the per-(x,y)
+//    ANCHORS for tile t+1 are computed by the same warps right after they consume tile t;
 //  * inside a channel run the phasor advances by ONE complex rotation per channel
-//    (2 DMUL + 2 DFMA) instead of a sincos; every run restarts from an anchor, so the
-//    recurrence never runs longer than CH <= 32 steps.  The anchors themselves come from
-//    3 sincos per (x, y) pair (first run, run-to-run step, channel step) and a rotation per
-//    further run -- amortised over all channels of the CTA;
+//    (2 DMUL + 2 DFMA) instead of a sincos; every run restarts from an anchor
+//    exp(i*phi*nu_f0), so the recurrence never runs longer than CH <= 32 steps.  Per (x,y)
+//    pair the anchors cost 2 sincos (first run, channel step d), log2(CH) complex squarings
+//    (run step D = d^CH) and one rotation per further run;
 //  * the phase argument phi = cst*(l*u + m*v + n*w) is formed in FP64 in the reference's
-//    operation order with explicitly rounded ops (no FMA contraction), and the anchor phase
-//    is fl(phi*nu_f0) exactly as the reference computes it;
+//    operation order with explicitly rounded ops (no FMA contraction), and the first anchor
+//    phase is fl(phi*nu_f0) exactly as the reference computes it;
 //  * non-equispaced channels (exact mode) take one sincos per term instead;
 //  * two y's are processed per inner iteration so each thread has two independent
-//    rotation chains in flight (DFMA latency hiding at 8 warps/SM).
+//    rotation chains in flight (measured DFMA latency 8.4 cycles, issue 1 per 2 cycles/SMSP).
+#include <algorithm>
+
 #include "afr_dft.cuh"
 
 namespace afr {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kYT = 8;  // streamed items per shared-memory tile (even)
+constexpr int kMaxChunks = 8;  // cp.async granules of the W tile per thread
 
 struct DftParams {
     const double *xc;      // (nx,3) owner coordinates
     const double *yc;      // (ny,3) streamed coordinates
-    const double *w;       // (ny,nchan,wstride) real or complex
-    const uint8_t *flags;  // (ny,nchan,wstride) or nullptr
+    const void *w;         // (ny,nchan,wstride) real or complex, in the accumulator precision
+    const uint8_t *anyflag;  // (ny,nchan) 1 = drop the sample, or nullptr
     const double *freq;    // (nchan,)
     void *out;             // (nsplit,nx,nchan,wstride) in the accumulator type
     double cst;
     long long nx, ny;
-    long long ysplit;            // y items per grid.z slice (multiple of kYT)
-    long long out_split_stride;  // elements (of the output scalar type) between slices
+    long long ysplit;            // y items per grid.z slice (multiple of yt)
+    long long out_split_stride;  // scalars between slices
     int nchan;
     int wstride;  // correlations in W / out
     int coff;     // first correlation handled by this launch
-    int nck;      // channel runs per CTA: 1, 2, 4 or 8
+    int nck;      // channel runs per CTA (power of two <= NW)
+    int yt;       // y items per tile (even, <= 8)
     int f32dot;
+    int fast;         // 1: W rows are contiguous and copied by cp.async granules
+    int granule;      // 4, 8 or 16 bytes
+    int row_chunks_log2;  // log2(granules per W tile row)
 };
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp_async(unsigned dst, const void *src, int granule, int src_bytes) {
+    if (granule == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+    else if (granule == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <int N>
 __device__ __forceinline__ void load_vec(const double *src, double (&dst)[N]) {
@@ -101,29 +121,35 @@ __device__ __forceinline__ void accumulate(ACC (&are)[NCORR], ACC (&aim)[ADJ ? 1
     }
 }
 
-template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, bool EXACT>
-__global__ void __launch_bounds__(kThreads) phasor_stream_kernel(const DftParams p) {
+template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NW, bool EXACT>
+__global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftParams p) {
+    constexpr int NT = NW * 32;
     constexpr int NV = NCORR * (WC ? 2 : 1);  // W scalars per channel
-    constexpr int G = 4;                      // channels per 16-byte-aligned W group
-    static_assert(CH % G == 0 && kYT % 2 == 0, "tiling");
+    constexpr int G = (NV >= 4) ? 2 : 4;      // channels per register group of W values
+    constexpr int SZ = (int)sizeof(ACC);
+    static_assert(CH % G == 0 && (G * NV * SZ) % 16 == 0, "tiling");
+    static_assert((CH & (CH - 1)) == 0, "CH must be a power of two");
     using CA = C2<ACC>;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nck = p.nck;
-    const int xgw = (kWarps / nck) * 32;  // owners per CTA
-    const int ft = nck * CH;              // channels per CTA
+    const int nck = p.nck, yt = p.yt;
+    const int xgw = (NW / nck) * 32;  // owners per CTA
+    const int ft = nck * CH;          // channels per CTA
     const int cta_f0 = blockIdx.y * ft;
     const long long cta_x0 = (long long)blockIdx.x * xgw;
 
-    // shared-memory carve-up
-    CA *anch = reinterpret_cast<CA *>(smem_raw);              // [kYT][nck][xgw]
-    CA *dstp = anch + (size_t)kYT * nck * xgw;                // [kYT][xgw]
-    ACC *wt = reinterpret_cast<ACC *>(dstp + (size_t)kYT * xgw);  // [kYT][ft][NV]
-    // exact mode re-uses the anchor region: double phi[kYT][xgw], double fq[ft]
-    double *phis = reinterpret_cast<double *>(smem_raw);
-    double *fq = phis + (size_t)kYT * xgw;
+    // ---- shared-memory carve-up: two {anchor, step, W} buffers + 3 y-coordinate slots
+    const size_t anch_elems = (size_t)yt * nck * xgw;  // CA, or double phi[yt][xgw] (exact)
+    const size_t dstp_elems = (size_t)yt * xgw;
+    const size_t w_elems = (size_t)yt * ft * NV;
+    const size_t buf_bytes = (anch_elems + dstp_elems) * sizeof(CA) + w_elems * SZ;
+    double *ycs = reinterpret_cast<double *>(smem_raw + 2 * buf_bytes);  // [3][yt*3]
+    double *fq = ycs + 3 * (size_t)yt * 3;                               // [ft] (exact mode)
+    auto anch_of = [&](int b) { return reinterpret_cast<CA *>(smem_raw + (size_t)b * buf_bytes); };
+    auto dstp_of = [&](int b) { return anch_of(b) + anch_elems; };
+    auto w_of = [&](int b) { return reinterpret_cast<ACC *>(dstp_of(b) + dstp_elems); };
 
     // consumer role: lane -> owner, warp -> (owner group, channel run)
     const int ck = warp % nck;
@@ -134,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) phasor_stream_kernel(const DftParams
     // producer role: fixed owner per thread, y strided
     const int px_local = tid % xgw;
     const int py0 = tid / xgw;
-    const int pystep = kThreads / xgw;
+    const int pystep = NT / xgw > 0 ? NT / xgw : 1;
     double px0, px1, px2;
     {
         long long pxi = cta_x0 + px_local;
@@ -144,14 +170,12 @@ __global__ void __launch_bounds__(kThreads) phasor_stream_kernel(const DftParams
         px2 = p.xc[3 * pxi + 2];
     }
 
-    // channel spacing for the recurrence
     double dnu = 0.0, nu0 = 0.0;
     if (!EXACT) {
         if (p.nchan > 1) dnu = (p.freq[p.nchan - 1] - p.freq[0]) / (double)(p.nchan - 1);
         nu0 = p.freq[cta_f0];
     } else {
-        for (int i = tid; i < ft; i += kThreads)
-            fq[i] = p.freq[min(cta_f0 + i, p.nchan - 1)];
+        for (int i = tid; i < ft; i += NT) fq[i] = p.freq[min(cta_f0 + i, p.nchan - 1)];
     }
 
     ACC are[CH][NCORR];
@@ -166,87 +190,152 @@ __global__ void __launch_bounds__(kThreads) phasor_stream_kernel(const DftParams
 
     const long long ys = (long long)blockIdx.z * p.ysplit;
     const long long ye = min(p.ny, ys + p.ysplit);
+    const int ntiles = (int)((ye - ys + yt - 1) / yt);
     const bool f32dot = p.f32dot != 0;
+    const int valid_ch = min(ft, p.nchan - cta_f0);  // channels of this CTA inside the array
 
-    for (long long y0 = ys; y0 < ye; y0 += kYT) {
-        __syncthreads();  // previous tile fully consumed
-
-        // ---- stage the W tile (flag-masked), zero-padded at the edges
-        {
-            const int per_y = ft * NV;
-            const int total = kYT * per_y;
-            for (int idx = tid; idx < total; idx += kThreads) {
-                const int yl = idx / per_y;
-                const int rem = idx - yl * per_y;
-                const int fl = rem / NV;
-                const int e = rem - fl * NV;
+    // ---- asynchronous staging: y coordinates of tile t -> ycs[t%3], W(t) -> w_of(t&1)
+    unsigned flagbits = 0;  // drop-mask of this thread's granules of the W tile in flight
+    auto issue_yc = [&](int t) {  // 8-byte copies, zero-filled past the end of the slice
+        if (tid < yt * 3) {
+            const long long gi = (ys + (long long)t * yt) * 3 + tid;
+            const bool ok = gi < ye * 3;
+            cp_async(smem_addr(ycs + (size_t)(t % 3) * yt * 3 + tid), p.yc + (ok ? gi : 0), 8,
+                     ok ? 8 : 0);
+        }
+    };
+    auto issue_w = [&](int t) {
+        if (t >= ntiles || !p.fast) return;
+        const long long y0 = ys + (long long)t * yt;
+        ACC *wt = w_of(t & 1);
+        const int g = p.granule;
+        const int rcl = p.row_chunks_log2;
+        const int total = yt << rcl;
+        const int valid_bytes = valid_ch * NV * SZ;
+        const char *wbase = reinterpret_cast<const char *>(p.w);
+        unsigned bits = 0;
+#pragma unroll
+        for (int k = 0; k < kMaxChunks; ++k) {
+            const int c = tid + k * NT;
+            if (c < total) {
+                const int yl = c >> rcl;
+                const int off = (c - (yl << rcl)) * g;  // byte offset in the tile row
                 const long long y = y0 + yl;
-                const int f = cta_f0 + fl;
-                double val = 0.0;
-                if (y < ye && f < p.nchan) {
-                    const long long base = (y * p.nchan + f) * p.wstride;
-                    bool flagged = false;
-                    if (p.flags != nullptr) {
-                        for (int k = 0; k < p.wstride; ++k) flagged |= (p.flags[base + k] != 0);
-                    }
-                    if (!flagged) {
-                        if (WC)
-                            val = p.w[2 * (base + p.coff + (e >> 1)) + (e & 1)];
-                        else
-                            val = p.w[base + p.coff + e];
+                const bool ok = (y < ye) && (off < valid_bytes);
+                const long long gbyte = ((y * p.nchan + cta_f0) * (long long)NV) * SZ + off;
+                cp_async(smem_addr(reinterpret_cast<char *>(wt) + (size_t)yl * ft * NV * SZ + off),
+                         wbase + (ok ? gbyte : 0), g, ok ? g : 0);
+                if (ADJ && p.anyflag != nullptr && ok) {
+                    // scalars of this granule -> samples -> drop bits
+                    const int s0 = off / SZ;
+                    for (int e = 0; e < g / SZ; ++e) {
+                        const int fl = (s0 + e) / NV;
+                        if (p.anyflag[y * p.nchan + cta_f0 + fl]) bits |= 1u << (k * 4 + e);
                     }
                 }
-                wt[idx] = (ACC)val;
             }
         }
-
-        // ---- anchors for this tile's (x, y) pairs
-        for (int yl = py0; yl < kYT; yl += pystep) {
+        flagbits = bits;
+    };
+    // generic (synchronous) staging: correlation sub-blocks of a wider W
+    auto stage_tile_slow = [&](int t) {
+        const long long y0 = ys + (long long)t * yt;
+        ACC *wt = w_of(t & 1);
+        const ACC *wsrc = reinterpret_cast<const ACC *>(p.w);
+        const int per_y = ft * NV;
+        const int total = yt * per_y;
+        for (int idx = tid; idx < total; idx += NT) {
+            const int yl = idx / per_y;
+            const int rem = idx - yl * per_y;
+            const int fl = rem / NV;
+            const int e = rem - fl * NV;
             const long long y = y0 + yl;
-            if (EXACT) {
-                double phi = 0.0;
-                if (y < ye) {
-                    const double y0c = p.yc[3 * y], y1c = p.yc[3 * y + 1], y2c = p.yc[3 * y + 2];
-                    phi = __dmul_rn(p.cst, phase_dot(px0, px1, px2, y0c, y1c, y2c, f32dot));
+            const int f = cta_f0 + fl;
+            ACC val = ACC(0);
+            if (y < ye && f < p.nchan) {
+                const long long sample = y * p.nchan + f;
+                const bool drop = ADJ && p.anyflag != nullptr && p.anyflag[sample] != 0;
+                if (!drop) {
+                    const long long base = sample * p.wstride + p.coff;
+                    val = WC ? wsrc[2 * (base + (e >> 1)) + (e & 1)] : wsrc[base + e];
                 }
+            }
+            wt[idx] = val;
+        }
+    };
+    auto apply_flags = [&](int t) {
+        if (!(ADJ && p.fast) || flagbits == 0) return;
+        ACC *wt = w_of(t & 1);
+        const int g = p.granule, rcl = p.row_chunks_log2;
+#pragma unroll
+        for (int k = 0; k < kMaxChunks; ++k) {
+            const unsigned b = (flagbits >> (k * 4)) & 0xFu;
+            if (b) {
+                const int c = tid + k * NT;
+                const int yl = c >> rcl;
+                const int off = (c - (yl << rcl)) * g;
+                ACC *dst = reinterpret_cast<ACC *>(reinterpret_cast<char *>(wt) + (size_t)yl * ft * NV * SZ + off);
+                for (int e = 0; e < g / SZ; ++e)
+                    if (b & (1u << e)) dst[e] = ACC(0);
+            }
+        }
+    };
+
+    // ---- anchors of tile `t` into buffer t&1 (y coordinates already in shared memory)
+    auto produce_tile = [&](int t) {
+        if (t >= ntiles) return;
+        const long long y0 = ys + (long long)t * yt;
+        const double *yct = ycs + (size_t)(t % 3) * yt * 3;
+        CA *anch = anch_of(t & 1);
+        CA *dstp = dstp_of(t & 1);
+        double *phis = reinterpret_cast<double *>(anch);
+        for (int yl = py0; yl < yt; yl += pystep) {
+            const long long y = y0 + yl;
+            const bool live = y < ye;
+            double phi = 0.0;
+            if (live)
+                phi = __dmul_rn(p.cst, phase_dot(px0, px1, px2, yct[3 * yl], yct[3 * yl + 1],
+                                                 yct[3 * yl + 2], f32dot));
+            if (EXACT) {
                 phis[yl * xgw + px_local] = phi;
             } else {
-                CA zero;
-                zero.re = ACC(0);
-                zero.im = ACC(0);
-                if (y < ye) {
-                    const double y0c = p.yc[3 * y], y1c = p.yc[3 * y + 1], y2c = p.yc[3 * y + 2];
-                    const double phi =
-                        __dmul_rn(p.cst, phase_dot(px0, px1, px2, y0c, y1c, y2c, f32dot));
-                    C2<double> a = cis(__dmul_rn(phi, nu0));
-                    const C2<double> d = cis(__dmul_rn(phi, dnu));
-                    CA dd;
-                    dd.re = (ACC)d.re;
-                    dd.im = (ACC)d.im;
-                    dstp[yl * xgw + px_local] = dd;
-                    C2<double> D;
-                    D.re = 1.0;
-                    D.im = 0.0;
-                    if (nck > 1) D = cis(__dmul_rn(phi, (double)CH * dnu));
-                    for (int k = 0; k < nck; ++k) {
-                        CA aa;
-                        aa.re = (ACC)a.re;
-                        aa.im = (ACC)a.im;
-                        anch[(yl * nck + k) * xgw + px_local] = aa;
-                        a = cmul(a, D);
+                C2<double> a = {0.0, 0.0}, d = {0.0, 0.0}, D = {1.0, 0.0};
+                if (live) {
+                    a = cis(__dmul_rn(phi, nu0));
+                    d = cis(__dmul_rn(phi, dnu));
+                    if (nck > 1) {  // D = d^CH by repeated squaring
+                        D = d;
+#pragma unroll
+                        for (int q = 1; q < CH; q *= 2) {
+                            const double re = D.re * D.re - D.im * D.im;
+                            D.im = 2.0 * D.re * D.im;
+                            D.re = re;
+                        }
                     }
-                } else {
-                    dstp[yl * xgw + px_local] = zero;
-                    for (int k = 0; k < nck; ++k) anch[(yl * nck + k) * xgw + px_local] = zero;
+                }
+                CA dd;
+                dd.re = (ACC)d.re;
+                dd.im = (ACC)d.im;
+                dstp[yl * xgw + px_local] = dd;
+                for (int k = 0; k < nck; ++k) {
+                    CA aa;
+                    aa.re = (ACC)a.re;
+                    aa.im = (ACC)a.im;
+                    anch[(yl * nck + k) * xgw + px_local] = aa;
+                    a = cmul(a, D);
                 }
             }
         }
-        __syncthreads();  // tile ready
+    };
 
-        // ---- consume: rotate + accumulate
+    auto consume_tile = [&](int t) {
+        const CA *anch = anch_of(t & 1);
+        const CA *dstp = dstp_of(t & 1);
+        const ACC *wt = w_of(t & 1);
         if (EXACT) {
+            const double *phis = reinterpret_cast<const double *>(anch);
 #pragma unroll 1
-            for (int yl = 0; yl < kYT; ++yl) {
+            for (int yl = 0; yl < yt; ++yl) {
                 const double phi = phis[yl * xgw + x_local];
                 const ACC *wrow = wt + (size_t)(yl * ft + fo) * NV;
 #pragma unroll
@@ -265,7 +354,7 @@ __global__ void __launch_bounds__(kThreads) phasor_stream_kernel(const DftParams
             }
         } else {
 #pragma unroll 1
-            for (int yl = 0; yl < kYT; yl += 2) {
+            for (int yl = 0; yl < yt; yl += 2) {
                 CA za = anch[(yl * nck + ck) * xgw + x_local];
                 CA zb = anch[((yl + 1) * nck + ck) * xgw + x_local];
                 const CA da = dstp[yl * xgw + x_local];
@@ -288,6 +377,30 @@ __global__ void __launch_bounds__(kThreads) phasor_stream_kernel(const DftParams
                     }
                 }
             }
+        }
+    };
+
+    // ---- software pipeline, one barrier per tile
+    if (ntiles > 0) {
+        issue_yc(0);
+        issue_yc(1);
+        issue_w(0);
+        cp_async_commit();
+        if (!p.fast) stage_tile_slow(0);
+        cp_async_wait_all();
+        apply_flags(0);
+        __syncthreads();
+        produce_tile(0);
+        for (int t = 0; t < ntiles; ++t) {
+            cp_async_wait_all();  // this thread's granules of W(t) and y(t+1) have landed
+            if (t > 0) apply_flags(t);
+            __syncthreads();  // W(t), y(t+1), anchors(t) visible; buffers of tile t-1 free
+            issue_yc(t + 2);
+            issue_w(t + 1);
+            cp_async_commit();
+            if (!p.fast && t + 1 < ntiles) stage_tile_slow(t + 1);
+            consume_tile(t);
+            produce_tile(t + 1);
         }
     }
 
@@ -315,8 +428,8 @@ __global__ void __launch_bounds__(kThreads) phasor_stream_kernel(const DftParams
     }
 }
 
-// out[i] = sum_k partial[k][i] in fixed k order (deterministic), correlations
-// [coff, coff+ncorr) of every (x, f)
+// out[i] = sum_k partial[k][i] in fixed k order (deterministic), scalars [coff, coff+nc)
+// of every (x, f)
 template <typename T>
 __global__ void reduce_partials_kernel(const T *partial, T *out, long long n_xf, int wstride,
                                        int coff, int nc, int nsplit, long long split_stride) {
@@ -329,6 +442,17 @@ __global__ void reduce_partials_kernel(const T *partial, T *out, long long n_xf,
         T s = partial[idx];
         for (int k = 1; k < nsplit; ++k) s += partial[(size_t)k * split_stride + idx];
         out[idx] = s;
+    }
+}
+
+// any-correlation flag per (y, f) sample (dft/kernels.py:136-137)
+__global__ void any_flag_kernel(const uint8_t *flags, long long n_samples, int ncorr,
+                                uint8_t *any) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_samples;
+         i += (long long)gridDim.x * blockDim.x) {
+        uint8_t a = 0;
+        for (int c = 0; c < ncorr; ++c) a |= flags[i * ncorr + c];
+        any[i] = a ? 1 : 0;
     }
 }
 
@@ -365,35 +489,74 @@ __global__ void lm_to_lmn_kernel(const double *lm, long long nsrc, int mode, int
     lmn[3 * s + 2] = n;
 }
 
-template <int NCORR, bool WC, bool ADJ, typename ACC, int CH>
+int ilog2(long long v) {
+    int r = 0;
+    while ((1LL << (r + 1)) <= v) ++r;
+    return r;
+}
+
+template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NW>
 int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     constexpr int NV = NCORR * (WC ? 2 : 1);
+    constexpr int SZ = (int)sizeof(ACC);
+    constexpr int NT = NW * 32;
     // channel runs per CTA
     const int runs = (p.nchan + CH - 1) / CH;
     int nck = 1;
-    while (nck < runs && nck < kWarps) nck *= 2;
+    while (nck < runs && nck < NW) nck *= 2;
     p.nck = nck;
-    const int xgw = (kWarps / nck) * 32;
+    const int xgw = (NW / nck) * 32;
     const int ft = nck * CH;
     const long long gx = (p.nx + xgw - 1) / xgw;
     const int gy = (p.nchan + ft - 1) / ft;
     AFR_REQUIRE(gx <= 2147483647LL && gy <= 65535, "phasor_stream: grid too large");
 
-    // split the streamed axis when owners alone cannot fill the machine
+    // W staging mode: cp.async granules when this launch covers every correlation of W
+    p.fast = (p.wstride == NCORR && p.coff == 0) ? 1 : 0;
+    const long long row_bytes_global = (long long)p.nchan * NV * SZ;
+    int granule = 16;
+    while (granule > SZ && ((row_bytes_global % granule) != 0 ||
+                            (reinterpret_cast<uintptr_t>(p.w) % granule) != 0))
+        granule /= 2;
+    p.granule = granule;
+    const int row_chunks = ft * NV * SZ / granule;
+    p.row_chunks_log2 = ilog2(row_chunks);
+
+    // y items per tile: as many (even, <= 8) as fit double-buffered in shared memory and in
+    // kMaxChunks cp.async granules per thread
+    const size_t per_y = (size_t)(nck + 1) * xgw * sizeof(C2<ACC>) + (size_t)ft * NV * SZ;
+    int yt = 8;
+    while (yt > 2 && (2 * yt * per_y > 200 * 1024 ||
+                      (long long)yt * row_chunks > (long long)kMaxChunks * NT))
+        yt -= 2;
+    if ((long long)yt * row_chunks > (long long)kMaxChunks * NT) p.fast = 0;
+    p.yt = yt;
+    const size_t smem = 2 * yt * per_y + 3 * (size_t)yt * 3 * sizeof(double) + (size_t)ft * sizeof(double);
+
+    // split the streamed axis when the owners alone cannot fill the machine; pick the
+    // split count whose CTA total wastes the least of the last wave (1 CTA per SM)
     const int sms = sm_count();
     long long nsplit = 1;
     const long long ctas = gx * gy;
-    if (ctas < 4LL * sms) {
-        nsplit = (4LL * sms + ctas - 1) / ctas;
-        const long long max_split = (p.ny + 4 * kYT - 1) / (4 * kYT);
+    const long long max_split = std::max(1LL, (p.ny + 4LL * yt - 1) / (4LL * yt));
+    if (ctas < 6LL * sms && max_split > 1) {
+        const long long lo = std::max(1LL, (3LL * sms + ctas - 1) / ctas);
+        double best = -1.0;
+        for (long long ns = lo; ns <= std::min(max_split, lo + 24); ++ns) {
+            const long long tot = ctas * ns;
+            const long long waves = (tot + sms - 1) / sms;
+            const double eff = (double)tot / (double)(waves * sms);
+            if (eff > best + 1e-9) {
+                best = eff;
+                nsplit = ns;
+            }
+        }
         if (nsplit > max_split) nsplit = max_split;
-        if (nsplit > 1024) nsplit = 1024;
-        if (nsplit < 1) nsplit = 1;
     }
     long long ysplit = (p.ny + nsplit - 1) / nsplit;
-    ysplit = ((ysplit + kYT - 1) / kYT) * kYT;
-    if (ysplit < kYT) ysplit = kYT;
-    nsplit = p.ny > 0 ? (p.ny + ysplit - 1) / ysplit : 1;
+    ysplit = ((ysplit + yt - 1) / yt) * yt;
+    nsplit = (p.ny + ysplit - 1) / ysplit;
+    AFR_REQUIRE(nsplit <= 65535, "phasor_stream: too many y slices");
     p.ysplit = ysplit;
 
     const size_t out_scalars = (size_t)p.nx * p.nchan * p.wstride * (ADJ ? 1 : 2);
@@ -407,27 +570,17 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
         p.out_split_stride = 0;
     }
 
-    size_t smem;
-    if (exact)
-        smem = (size_t)kYT * xgw * sizeof(double) + (size_t)ft * sizeof(double);
-    else
-        smem = (size_t)kYT * (nck + 1) * xgw * sizeof(C2<ACC>);
-    // the W tile starts after the (non-exact) anchor region in both modes
-    const size_t anchor_bytes = (size_t)kYT * (nck + 1) * xgw * sizeof(C2<ACC>);
-    if (smem < anchor_bytes) smem = anchor_bytes;
-    smem += (size_t)kYT * ft * NV * sizeof(ACC);
-
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nsplit);
     if (exact) {
-        auto kern = phasor_stream_kernel<NCORR, WC, ADJ, ACC, CH, true>;
+        auto kern = phasor_stream_kernel<NCORR, WC, ADJ, ACC, CH, NW, true>;
         AFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-        kern<<<grid, kThreads, smem, stream>>>(p);
+        kern<<<grid, NT, smem, stream>>>(p);
     } else {
-        auto kern = phasor_stream_kernel<NCORR, WC, ADJ, ACC, CH, false>;
+        auto kern = phasor_stream_kernel<NCORR, WC, ADJ, ACC, CH, NW, false>;
         AFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-        kern<<<grid, kThreads, smem, stream>>>(p);
+        kern<<<grid, NT, smem, stream>>>(p);
     }
     AFR_CUDA_OK(cudaGetLastError());
 
@@ -435,8 +588,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
         const long long n_xf = p.nx * p.nchan;
         const int sc = ADJ ? 1 : 2;  // scalars per correlation
         const long long total = n_xf * NCORR * sc;
-        int blocks = (int)((total + 255) / 256);
-        if (blocks > 8 * sms) blocks = 8 * sms;
+        int blocks = (int)std::min<long long>((total + 255) / 256, 8LL * sms);
         if (blocks < 1) blocks = 1;
         reduce_partials_kernel<ACC><<<blocks, 256, 0, stream>>>(
             reinterpret_cast<const ACC *>(partial.ptr), reinterpret_cast<ACC *>(final_out), n_xf,
@@ -446,8 +598,11 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     return 0;
 }
 
+// Tile shapes per variant: (CH channels per run, NW warps per CTA) chosen so the
+// accumulators fit the register budget of NW*32 threads on one SM.
 template <bool WC, bool ADJ, typename ACC>
 int launch_corr_blocks(DftParams p, bool exact, cudaStream_t stream) {
+    constexpr bool F32 = sizeof(ACC) == 4;
     // correlations are handled in blocks of 4, 2, 1 (ncorr = 3 -> 2 + 1, etc.)
     int c = 0;
     const int ncorr = p.wstride;
@@ -455,13 +610,16 @@ int launch_corr_blocks(DftParams p, bool exact, cudaStream_t stream) {
         p.coff = c;
         int rc;
         if (ncorr - c >= 4) {
-            rc = launch_one<4, WC, ADJ, ACC, ADJ ? 16 : 8>(p, exact, stream);
+            constexpr int CH = ADJ ? (F32 ? 16 : 8) : (F32 ? 8 : 4);
+            rc = launch_one<4, WC, ADJ, ACC, CH, 16>(p, exact, stream);
             c += 4;
         } else if (ncorr - c >= 2) {
-            rc = launch_one<2, WC, ADJ, ACC, ADJ ? 32 : 16>(p, exact, stream);
+            constexpr int CH = ADJ ? (F32 ? 32 : 16) : (F32 ? 16 : 8);
+            rc = launch_one<2, WC, ADJ, ACC, CH, 16>(p, exact, stream);
             c += 2;
         } else {
-            rc = launch_one<1, WC, ADJ, ACC, 32>(p, exact, stream);
+            constexpr int CH = ADJ ? 32 : (F32 ? 32 : 16);
+            rc = launch_one<1, WC, ADJ, ACC, CH, 16>(p, exact, stream);
             c += 1;
         }
         if (rc) return rc;
@@ -480,10 +638,10 @@ int launch_lm_to_lmn(const double *lm, int64_t nsrc, int mode, bool lm_f32, doub
     return 0;
 }
 
-int run_phasor_stream(const double *xc, int64_t nx, const double *yc, int64_t ny,
-                      const double *w, bool w_complex, const uint8_t *flags, const double *freq,
-                      int64_t nchan, int64_t ncorr, double cst, bool f32dot, bool adjoint,
-                      bool exact, bool acc32, void *out, cudaStream_t stream) {
+int run_phasor_stream(const double *xc, int64_t nx, const double *yc, int64_t ny, const void *w,
+                      bool w_complex, const uint8_t *flags, const double *freq, int64_t nchan,
+                      int64_t ncorr, double cst, bool f32dot, bool adjoint, bool exact,
+                      bool acc32, void *out, cudaStream_t stream) {
     AFR_REQUIRE(nchan <= 2147483647LL / 64 && ncorr <= 64, "phasor_stream: nchan/ncorr too large");
     const size_t out_bytes = (size_t)nx * nchan * ncorr * (adjoint ? 1 : 2) * (acc32 ? 4 : 8);
     if (nx <= 0 || nchan <= 0 || ncorr <= 0) return 0;
@@ -491,11 +649,19 @@ int run_phasor_stream(const double *xc, int64_t nx, const double *yc, int64_t ny
         AFR_CUDA_OK(cudaMemsetAsync(out, 0, out_bytes, stream));
         return 0;
     }
+    Scratch anyflag;
+    if (flags != nullptr) {
+        const long long n = ny * nchan;
+        AFR_CUDA_OK(anyflag.alloc((size_t)n, stream));
+        const int blocks = (int)std::min<long long>((n + 255) / 256, 16LL * sm_count());
+        any_flag_kernel<<<blocks, 256, 0, stream>>>(flags, n, (int)ncorr, (uint8_t *)anyflag.ptr);
+        AFR_CUDA_OK(cudaGetLastError());
+    }
     DftParams p{};
     p.xc = xc;
     p.yc = yc;
     p.w = w;
-    p.flags = flags;
+    p.anyflag = (const uint8_t *)anyflag.ptr;
     p.freq = freq;
     p.out = out;
     p.cst = cst;
@@ -541,10 +707,9 @@ extern "C" int afr_im_to_vis(const void *image, int image_complex, const double 
                               (double *)lmn.ptr, stream);
     if (rc) return rc;
     const bool f32dot = (f32_flags & AFR_F32_LM) && (f32_flags & AFR_F32_UVW);
-    return run_phasor_stream(uvw, nrow, (const double *)lmn.ptr, nsrc, (const double *)image,
-                             image_complex != 0, nullptr, freq, nchan, ncorr, cst, f32dot,
-                             /*adjoint=*/false, chan_mode == AFR_CHAN_EXACT, out_c64 != 0, out,
-                             stream);
+    return run_phasor_stream(uvw, nrow, (const double *)lmn.ptr, nsrc, image, image_complex != 0,
+                             nullptr, freq, nchan, ncorr, cst, f32dot, /*adjoint=*/false,
+                             chan_mode == AFR_CHAN_EXACT, out_c64 != 0, out, stream);
 }
 
 extern "C" int afr_vis_to_im(const void *vis, int vis_complex, const double *uvw,
@@ -564,8 +729,7 @@ extern "C" int afr_vis_to_im(const void *vis, int vis_complex, const double *uvw
                               (double *)lmn.ptr, stream);
     if (rc) return rc;
     const bool f32dot = (f32_flags & AFR_F32_LM) && (f32_flags & AFR_F32_UVW);
-    return run_phasor_stream((const double *)lmn.ptr, nsrc, uvw, nrow, (const double *)vis,
-                             vis_complex != 0, flags, freq, nchan, ncorr, cst, f32dot,
-                             /*adjoint=*/true, chan_mode == AFR_CHAN_EXACT, out_f32 != 0, out,
-                             stream);
+    return run_phasor_stream((const double *)lmn.ptr, nsrc, uvw, nrow, vis, vis_complex != 0,
+                             flags, freq, nchan, ncorr, cst, f32dot, /*adjoint=*/true,
+                             chan_mode == AFR_CHAN_EXACT, out_f32 != 0, out, stream);
 }

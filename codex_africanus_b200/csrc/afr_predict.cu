@@ -277,13 +277,6 @@ __global__ void __launch_bounds__(128) fused_dde_kernel(const FusedParams p) {
     }
 }
 
-template <typename TO>
-__global__ void convert_c64_to_c128_kernel(const float *in, double *out, long long n) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x)
-        out[i] = (double)in[i];
-}
-
 int grid_for(long long total, int threads) {
     long long blocks = (total + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
@@ -409,17 +402,8 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
         AFR_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)nrow * nchan * ncorr * elem, stream));
     } else if (dde1 == nullptr) {
         // point-source sum: phasor-stream kernel with the brightness as complex "image"
-        Scratch b128;
-        const double *bright = (const double *)brightness;
-        if (out_c64) {
-            const long long n = nsrc * nchan * ncorr * 2;
-            AFR_CUDA_OK(b128.alloc(sizeof(double) * (size_t)n, stream));
-            convert_c64_to_c128_kernel<double><<<grid_for(n, 256), 256, 0, stream>>>(
-                (const float *)brightness, (double *)b128.ptr, n);
-            AFR_CUDA_OK(cudaGetLastError());
-            bright = (const double *)b128.ptr;
-        }
-        rc = run_phasor_stream(uvw, nrow, (const double *)lmn.ptr, nsrc, bright, true, nullptr,
+        // (complex64 brightness feeds the FP32 accumulator variant directly)
+        rc = run_phasor_stream(uvw, nrow, (const double *)lmn.ptr, nsrc, brightness, true, nullptr,
                                freq, nchan, ncorr, cst, false, /*adjoint=*/false, exact,
                                out_c64 != 0, out, stream);
         if (rc) return rc;

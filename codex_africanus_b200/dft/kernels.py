@@ -52,7 +52,10 @@ def im_to_vis(image, uvw, lm, frequency, convention="fourier", dtype=None):
     out_c64 = int(out_dtype == np.complex64)
 
     with torch.cuda.device(device):
-        d_img = pl.to_device(image, np.complex128 if img_complex else np.float64, device)
+        if out_c64:  # FP32 accumulator variant takes the image in single precision
+            d_img = pl.to_device(image, np.complex64 if img_complex else np.float32, device)
+        else:
+            d_img = pl.to_device(image, np.complex128 if img_complex else np.float64, device)
         d_uvw = pl.to_device(uvw, np.float64, device)
         d_lm = pl.to_device(lm, np.float64, device)
         d_freq = pl.to_device(frequency, np.float64, device)
@@ -128,7 +131,10 @@ def vis_to_im(vis, uvw, lm, frequency, flags, convention="fourier", dtype=None):
     vis_complex = vdt.kind == "c"
 
     with torch.cuda.device(device):
-        d_vis = pl.to_device(vis, np.complex128 if vis_complex else np.float64, device)
+        if out_dtype == np.float32:  # FP32 accumulator variant takes vis in single precision
+            d_vis = pl.to_device(vis, np.complex64 if vis_complex else np.float32, device)
+        else:
+            d_vis = pl.to_device(vis, np.complex128 if vis_complex else np.float64, device)
         d_uvw = pl.to_device(uvw, np.float64, device)
         d_lm = pl.to_device(lm, np.float64, device)
         d_freq = pl.to_device(frequency, np.float64, device)

@@ -74,8 +74,9 @@ int afr_measure_fma_peak(int fp64, int iters, double *flops_per_s, void *stream)
 
 /* ---- africanus.dft.im_to_vis  (africanus/dft/kernels.py:14-69) --------- */
 /* image (nsrc,nchan,ncorr) float64 or complex128 (image_complex);
- * uvw (nrow,3); lm (nsrc,2); freq (nchan,);
- * out (nrow,nchan,ncorr) complex128, or complex64 when out_c64. */
+ * uvw (nrow,3); lm (nsrc,2); freq (nchan,); out (nrow,nchan,ncorr) complex128.
+ * out_c64: out is complex64, image is float32 / complex64, and the rotation and
+ * accumulation run in FP32 (phase argument and anchors stay FP64). */
 int afr_im_to_vis(const void *image, int image_complex, const double *uvw, const double *lm,
                   const double *freq, int64_t nsrc, int64_t nrow, int64_t nchan, int64_t ncorr,
                   int convention, int f32_flags, int chan_mode, int out_c64, void *out,
@@ -83,7 +84,8 @@ int afr_im_to_vis(const void *image, int image_complex, const double *uvw, const
 
 /* ---- africanus.dft.vis_to_im  (africanus/dft/kernels.py:72-148) -------- */
 /* vis (nrow,nchan,ncorr) float64 or complex128 (vis_complex); flags uint8 same shape
- * (NULL = nothing flagged); out (nsrc,nchan,ncorr) float64, or float32 when out_f32. */
+ * (NULL = nothing flagged); out (nsrc,nchan,ncorr) float64.
+ * out_f32: out is float32 and vis is float32 / complex64 (FP32 rotation/accumulation). */
 int afr_vis_to_im(const void *vis, int vis_complex, const double *uvw, const double *lm,
                   const double *freq, const uint8_t *flags, int64_t nsrc, int64_t nrow,
                   int64_t nchan, int64_t ncorr, int convention, int f32_flags, int chan_mode,
