@@ -94,4 +94,42 @@ __device__ __forceinline__ C2<double> cis(double p) {
     return r;
 }
 
+// exp(i p) for |p| <= 1e6 rad in ~22 FP64 instructions and no branches: Cody-Waite
+// reduction by pi/2 in three 33-bit pieces (exact products for |k| < 2^20), then the
+// classic minimax kernels on [-pi/4, pi/4] (coefficients of Sun's fdlibm k_sin.c /
+// k_cos.c), quadrant fix-up on the integer pipe.  Absolute error ~1e-16.  Larger
+// arguments take CUDA's sincos (Payne-Hanek).
+__device__ __forceinline__ C2<double> cis_fast(double p) {
+    if (!(fabs(p) <= 1.0e6)) return cis(p);
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+    double kd = fma(p, 6.36619772367581382433e-01, kMagic);
+    const int k = __double2loint(kd);
+    kd -= kMagic;
+    double r = fma(-kd, 1.57079632673412561417e+00, p);  // pio2_1 (33 bits)
+    r = fma(-kd, 6.07710050630396597660e-11, r);          // pio2_2 (33 bits)
+    r = fma(-kd, 2.02226624879595063154e-21, r);          // pio2_2t
+    const double z = r * r;
+    // sin(r)
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sn = fma(z * r, ps, r);
+    // cos(r)
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+    // quadrant: k&1 swaps, sign bits from k
+    const double a = (k & 1) ? cs : sn;  // |sin p|
+    const double b = (k & 1) ? sn : cs;  // |cos p|
+    C2<double> out;
+    out.im = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));
+    out.re = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
+    return out;
+}
+
 }  // namespace afr

@@ -49,7 +49,7 @@ struct DftParams {
     int nchan;
     int wstride;  // correlations in W / out
     int coff;     // first correlation handled by this launch
-    int nck;      // channel runs per CTA (power of two <= NW)
+    int nck;      // channel runs per CTA (power of two <= NW/2)
     int yt;       // y items per tile (even, <= 8)
     int f32dot;
     int fast;         // 1: W rows are contiguous and copied by cp.async granules
@@ -97,7 +97,7 @@ __device__ __forceinline__ void load_vec(const float *src, float (&dst)[N]) {
     }
 }
 
-__device__ __noinline__ C2<double> cis_noinline(double p) { return cis(p); }
+__device__ __noinline__ C2<double> cis_noinline(double p) { return cis_fast(p); }
 
 // acc (+)= z * w for the NCORR correlations of one channel
 template <int NCORR, bool WC, bool ADJ, typename ACC>
@@ -195,7 +195,14 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
     const int valid_ch = min(ft, p.nchan - cta_f0);  // channels of this CTA inside the array
 
     // ---- asynchronous staging: y coordinates of tile t -> ycs[t%3], W(t) -> w_of(t&1)
+    // Tile rows are contiguous in shared memory, so granule c of the tile lands at byte
+    // c*g; its source is row (c >> rcl) of the tile at byte offset (c & mask)*g.
     unsigned flagbits = 0;  // drop-mask of this thread's granules of the W tile in flight
+    const int g = p.granule, rcl = p.row_chunks_log2;
+    const int total_chunks = yt << rcl;
+    const int valid_bytes = valid_ch * NV * SZ;
+    const long long row_pitch = (long long)p.nchan * NV * SZ;  // bytes between W rows
+    const char *w_cta = reinterpret_cast<const char *>(p.w) + (long long)cta_f0 * NV * SZ;
     auto issue_yc = [&](int t) {  // 8-byte copies, zero-filled past the end of the slice
         if (tid < yt * 3) {
             const long long gi = (ys + (long long)t * yt) * 3 + tid;
@@ -207,32 +214,23 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
     auto issue_w = [&](int t) {
         if (t >= ntiles || !p.fast) return;
         const long long y0 = ys + (long long)t * yt;
-        ACC *wt = w_of(t & 1);
-        const int g = p.granule;
-        const int rcl = p.row_chunks_log2;
-        const int total = yt << rcl;
-        const int valid_bytes = valid_ch * NV * SZ;
-        const char *wbase = reinterpret_cast<const char *>(p.w);
+        const int rows_valid = (int)min((long long)yt, ye - y0);
+        const char *src_tile = w_cta + y0 * row_pitch;
+        const unsigned dst_tile = smem_addr(w_of(t & 1));
         unsigned bits = 0;
-#pragma unroll
-        for (int k = 0; k < kMaxChunks; ++k) {
-            const int c = tid + k * NT;
-            if (c < total) {
-                const int yl = c >> rcl;
-                const int off = (c - (yl << rcl)) * g;  // byte offset in the tile row
-                const long long y = y0 + yl;
-                const bool ok = (y < ye) && (off < valid_bytes);
-                const long long gbyte = ((y * p.nchan + cta_f0) * (long long)NV) * SZ + off;
-                cp_async(smem_addr(reinterpret_cast<char *>(wt) + (size_t)yl * ft * NV * SZ + off),
-                         wbase + (ok ? gbyte : 0), g, ok ? g : 0);
-                if (ADJ && p.anyflag != nullptr && ok) {
-                    // scalars of this granule -> samples -> drop bits
-                    const int s0 = off / SZ;
-                    for (int e = 0; e < g / SZ; ++e) {
-                        const int fl = (s0 + e) / NV;
-                        if (p.anyflag[y * p.nchan + cta_f0 + fl]) bits |= 1u << (k * 4 + e);
-                    }
-                }
+        int k = 0;
+#pragma unroll 2
+        for (int c = tid; c < total_chunks; c += NT, ++k) {
+            const int yl = c >> rcl;
+            const int off = (c - (yl << rcl)) * g;
+            const bool ok = (yl < rows_valid) && (off < valid_bytes);
+            cp_async(dst_tile + c * g, src_tile + (ok ? yl * row_pitch + off : 0), g, ok ? g : 0);
+            if (ADJ && p.anyflag != nullptr && ok) {
+                // scalars of this granule -> samples -> drop bits
+                const uint8_t *af = p.anyflag + (y0 + yl) * p.nchan + cta_f0;
+                const int s0 = off / SZ;
+                for (int e = 0; e < g / SZ; ++e)
+                    if (af[(s0 + e) / NV]) bits |= 1u << (k * 4 + e);
             }
         }
         flagbits = bits;
@@ -265,18 +263,14 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
     };
     auto apply_flags = [&](int t) {
         if (!(ADJ && p.fast) || flagbits == 0) return;
-        ACC *wt = w_of(t & 1);
-        const int g = p.granule, rcl = p.row_chunks_log2;
-#pragma unroll
-        for (int k = 0; k < kMaxChunks; ++k) {
-            const unsigned b = (flagbits >> (k * 4)) & 0xFu;
-            if (b) {
-                const int c = tid + k * NT;
-                const int yl = c >> rcl;
-                const int off = (c - (yl << rcl)) * g;
-                ACC *dst = reinterpret_cast<ACC *>(reinterpret_cast<char *>(wt) + (size_t)yl * ft * NV * SZ + off);
+        char *wt = reinterpret_cast<char *>(w_of(t & 1));
+        int k = 0;
+        for (int c = tid; c < total_chunks; c += NT, ++k) {
+            const unsigned bsel = (flagbits >> (k * 4)) & 0xFu;
+            if (bsel) {
+                ACC *dst = reinterpret_cast<ACC *>(wt + (size_t)c * g);
                 for (int e = 0; e < g / SZ; ++e)
-                    if (b & (1u << e)) dst[e] = ACC(0);
+                    if (bsel & (1u << e)) dst[e] = ACC(0);
             }
         }
     };
@@ -301,8 +295,8 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
             } else {
                 C2<double> a = {0.0, 0.0}, d = {0.0, 0.0}, D = {1.0, 0.0};
                 if (live) {
-                    a = cis(__dmul_rn(phi, nu0));
-                    d = cis(__dmul_rn(phi, dnu));
+                    a = cis_fast(__dmul_rn(phi, nu0));
+                    d = cis_fast(__dmul_rn(phi, dnu));
                     if (nck > 1) {  // D = d^CH by repeated squaring
                         D = d;
 #pragma unroll
@@ -353,27 +347,24 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
                 }
             }
         } else {
+            // ONE rotation chain per thread: with >= 4 warps per scheduler the 8-cycle DFMA
+            // latency is hidden by the other warps, and the single chain lets ptxas pair
+            // instructions that share a register operand (.reuse).  A DFMA with three
+            // distinct 64-bit register operands issues every 3 cycles on sm_100a (register
+            // file bandwidth), one with a reused operand every 2 -- measured, see DESIGN.md.
 #pragma unroll 1
-            for (int yl = 0; yl < yt; yl += 2) {
-                CA za = anch[(yl * nck + ck) * xgw + x_local];
-                CA zb = anch[((yl + 1) * nck + ck) * xgw + x_local];
-                const CA da = dstp[yl * xgw + x_local];
-                const CA db = dstp[(yl + 1) * xgw + x_local];
-                const ACC *wa = wt + (size_t)(yl * ft + fo) * NV;
-                const ACC *wb = wa + (size_t)ft * NV;
+            for (int yl = 0; yl < yt; ++yl) {
+                CA z = anch[(yl * nck + ck) * xgw + x_local];
+                const CA d = dstp[yl * xgw + x_local];
+                const ACC *wrow = wt + (size_t)(yl * ft + fo) * NV;
 #pragma unroll
                 for (int j = 0; j < CH; j += G) {
-                    ACC wva[G * NV], wvb[G * NV];
-                    load_vec<G * NV>(wa + j * NV, wva);
-                    load_vec<G * NV>(wb + j * NV, wvb);
+                    ACC wv[G * NV];
+                    load_vec<G * NV>(wrow + j * NV, wv);
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
-                        accumulate<NCORR, WC, ADJ, ACC>(are[j + g], aim[j + g], za, wva + g * NV);
-                        accumulate<NCORR, WC, ADJ, ACC>(are[j + g], aim[j + g], zb, wvb + g * NV);
-                        if (j + g + 1 < CH) {
-                            za = cmul(za, da);
-                            zb = cmul(zb, db);
-                        }
+                        accumulate<NCORR, WC, ADJ, ACC>(are[j + g], aim[j + g], z, wv + g * NV);
+                        if (j + g + 1 < CH) z = cmul(z, d);
                     }
                 }
             }
@@ -399,8 +390,16 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
             issue_w(t + 1);
             cp_async_commit();
             if (!p.fast && t + 1 < ntiles) stage_tile_slow(t + 1);
-            consume_tile(t);
-            produce_tile(t + 1);
+            // consume(t) and produce(t+1) are independent: alternate their order between the
+            // warps of a scheduler so the latency-bound anchor math of one warp overlaps the
+            // FP64-dense rotation loop of its neighbours
+            if ((warp >> 2) & 1) {
+                produce_tile(t + 1);
+                consume_tile(t);
+            } else {
+                consume_tile(t);
+                produce_tile(t + 1);
+            }
         }
     }
 
@@ -503,7 +502,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     // channel runs per CTA
     const int runs = (p.nchan + CH - 1) / CH;
     int nck = 1;
-    while (nck < runs && nck < NW) nck *= 2;
+    while (nck < runs && nck < NW / 2) nck *= 2;
     p.nck = nck;
     const int xgw = (NW / nck) * 32;
     const int ft = nck * CH;

@@ -54,13 +54,13 @@ __global__ void __launch_bounds__(256) phase_delay_f64_kernel(const PhaseParams 
 #pragma unroll
             for (int j = 0; j < kRun; ++j) {
                 if (f0 + j < p.nchan) {
-                    const C2<double> z = cis(__dmul_rn(phi, p.freq[f0 + j]));
+                    const C2<double> z = cis_fast(__dmul_rn(phi, p.freq[f0 + j]));
                     o[j] = make_double2(z.re, z.im);
                 }
             }
         } else {
-            C2<double> z = cis(__dmul_rn(phi, p.freq[f0]));
-            const C2<double> d = cis(__dmul_rn(phi, dnu));
+            C2<double> z = cis_fast(__dmul_rn(phi, p.freq[f0]));
+            const C2<double> d = cis_fast(__dmul_rn(phi, dnu));
 #pragma unroll
             for (int j = 0; j < kRun; ++j) {
                 if (f0 + j < p.nchan) o[j] = make_double2(z.re, z.im);

@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(128) fused_dde_kernel(const FusedParams p) {
                 p.cst, phase_dot(p.lmn[3 * s], p.lmn[3 * s + 1], p.lmn[3 * s + 2], u, v, w, false));
             C2<double> z = {1.0, 0.0}, d = {1.0, 0.0};
             if (!EXACT) {
-                z = cis(__dmul_rn(phi, p.freq[min(fbase, p.nchan - 1)]));
-                d = cis(__dmul_rn(phi, 32.0 * dnu));
+                z = cis_fast(__dmul_rn(phi, p.freq[min(fbase, p.nchan - 1)]));
+                d = cis_fast(__dmul_rn(phi, 32.0 * dnu));
             }
             const C *e1p = dde1 + (((s * p.ntime + ti) * p.nant + a1) * p.nchan) * N;
             const C *e2p = dde2 + (((s * p.ntime + ti) * p.nant + a2) * p.nchan) * N;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(128) fused_dde_kernel(const FusedParams p) {
             for (int k = 0; k < kK; ++k) {
                 const int f = fbase + 32 * k;
                 if (f < p.nchan) {
-                    if (EXACT) z = cis(__dmul_rn(phi, p.freq[f]));
+                    if (EXACT) z = cis_fast(__dmul_rn(phi, p.freq[f]));
                     const C zz = {(T)z.re, (T)z.im};
                     C b[N], e1[N], e2[N], x[N];
                     load_n<T, N>(bp + (long long)f * N, b);
