@@ -82,6 +82,8 @@ def to_device(a, np_dtype, device):
     if not arr.flags.writeable:
         arr = arr.copy()
     host = torch.from_numpy(arr)
+    if host.is_pinned():  # caller-provided page-locked memory: DMA straight from it
+        return host.to(device, non_blocking=True)
     if arr.nbytes >= (1 << 20):
         # stage through (cached) pinned memory so the copy is a real async DMA
         pinned = torch.empty(host.shape, dtype=tdt, pin_memory=True)

@@ -166,7 +166,7 @@ int launch_beam(BeamParams p, cudaStream_t stream) {
             beam_cube_dde_kernel<T, 1><<<grid, 256, 0, stream>>>(p);
             c += 1;
         }
-        AFR_CUDA_OK(cudaGetLastError());
+        AFR_LAUNCH_OK();
     }
     return 0;
 }
@@ -184,7 +184,7 @@ extern "C" int afr_freq_grid_interp(const double *freq, const double *beam_freq_
     if (nchan == 0) return 0;
     freq_grid_interp_kernel<<<(int)((nchan + 255) / 256), 256, 0, stream>>>(freq, beam_freq_map,
                                                                           nchan, nud, freq_data);
-    AFR_CUDA_OK(cudaGetLastError());
+    AFR_LAUNCH_OK();
     return 0;
 }
 

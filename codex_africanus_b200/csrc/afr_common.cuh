@@ -23,6 +23,17 @@ constexpr double kTwoPiOverC = 2.0 * 3.141592653589793 / kLightSpeed;
 // --------------------------------------------------------------------------
 void set_error(const std::string &msg);
 int fail(const std::string &msg);
+// every kernel launch of the library is counted (afr_kernel_launches())
+void note_launch(int n = 1);
+
+// call right after a <<<...>>> launch: counts it and checks the launch status
+#define AFR_LAUNCH_OK()                                                                \
+    do {                                                                               \
+        ::afr::note_launch();                                                          \
+        cudaError_t _e = cudaGetLastError();                                           \
+        if (_e != cudaSuccess)                                                         \
+            return ::afr::fail(std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+    } while (0)
 
 #define AFR_CUDA_OK(expr)                                                              \
     do {                                                                               \

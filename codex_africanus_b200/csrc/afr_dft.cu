@@ -581,7 +581,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
                                          (int)smem));
         kern<<<grid, NT, smem, stream>>>(p);
     }
-    AFR_CUDA_OK(cudaGetLastError());
+    AFR_LAUNCH_OK();
 
     if (nsplit > 1) {
         const long long n_xf = p.nx * p.nchan;
@@ -592,7 +592,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
         reduce_partials_kernel<ACC><<<blocks, 256, 0, stream>>>(
             reinterpret_cast<const ACC *>(partial.ptr), reinterpret_cast<ACC *>(final_out), n_xf,
             p.wstride * sc, p.coff * sc, NCORR * sc, (int)nsplit, (long long)out_scalars);
-        AFR_CUDA_OK(cudaGetLastError());
+        AFR_LAUNCH_OK();
     }
     return 0;
 }
@@ -633,7 +633,7 @@ int launch_lm_to_lmn(const double *lm, int64_t nsrc, int mode, bool lm_f32, doub
     if (nsrc <= 0) return 0;
     const int blocks = (int)((nsrc + 255) / 256);
     lm_to_lmn_kernel<<<blocks, 256, 0, stream>>>(lm, nsrc, mode, lm_f32 ? 1 : 0, lmn);
-    AFR_CUDA_OK(cudaGetLastError());
+    AFR_LAUNCH_OK();
     return 0;
 }
 
@@ -654,7 +654,7 @@ int run_phasor_stream(const double *xc, int64_t nx, const double *yc, int64_t ny
         AFR_CUDA_OK(anyflag.alloc((size_t)n, stream));
         const int blocks = (int)std::min<long long>((n + 255) / 256, 16LL * sm_count());
         any_flag_kernel<<<blocks, 256, 0, stream>>>(flags, n, (int)ncorr, (uint8_t *)anyflag.ptr);
-        AFR_CUDA_OK(cudaGetLastError());
+        AFR_LAUNCH_OK();
     }
     DftParams p{};
     p.xc = xc;

@@ -150,7 +150,7 @@ extern "C" int afr_phase_delay_f64(const double *lm, const double *uvw, const do
         phase_delay_f64_kernel<true><<<grid_for(total), 256, 0, stream>>>(p);
     else
         phase_delay_f64_kernel<false><<<grid_for(total), 256, 0, stream>>>(p);
-    AFR_CUDA_OK(cudaGetLastError());
+    AFR_LAUNCH_OK();
     return 0;
 }
 
@@ -167,6 +167,6 @@ extern "C" int afr_phase_delay_f32(const float *lm, const float *uvw, const floa
     const long long total = nsrc * nrow * ((nchan + kRun - 1) / kRun);
     phase_delay_f32_kernel<<<grid_for(total), 256, 0, stream>>>(lm, uvw, freq, (float2 *)out, cst,
                                                                nsrc, nrow, (int)nchan);
-    AFR_CUDA_OK(cudaGetLastError());
+    AFR_LAUNCH_OK();
     return 0;
 }

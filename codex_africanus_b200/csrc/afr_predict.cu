@@ -293,7 +293,7 @@ int launch_predict(const PredictParams &p, int jones_mode, cudaStream_t stream) 
         predict_vis_kernel<T, 4><<<grid_for(total, 256), 256, 0, stream>>>(p);
     else
         predict_vis_kernel<T, 1><<<grid_for(total, 256), 256, 0, stream>>>(p);
-    AFR_CUDA_OK(cudaGetLastError());
+    AFR_LAUNCH_OK();
     return 0;
 }
 
@@ -322,7 +322,7 @@ int launch_fused_dde(const FusedParams &p, int jones_mode, bool exact, cudaStrea
         return fail("afr_predict_fused: diagonal Jones with DDEs supports ncorr in (1, 2, 4)");
     }
 #undef AFR_LAUNCH_FUSED
-    AFR_CUDA_OK(cudaGetLastError());
+    AFR_LAUNCH_OK();
     return 0;
 }
 

@@ -1,5 +1,6 @@
 // Library plumbing: error text, device queries, frequency-grid check and the
 // FMA pipe peak measurement used as the roofline denominator.
+#include <atomic>
 #include <cmath>
 
 #include "afr_common.cuh"
@@ -7,6 +8,9 @@
 namespace afr {
 
 static thread_local std::string g_last_error;
+static std::atomic<unsigned long long> g_launches{0};
+
+void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 void set_error(const std::string &msg) { g_last_error = msg; }
 
@@ -40,6 +44,10 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T *sink, int iters, T a, 
 using namespace afr;
 
 extern "C" int afr_version(void) { return AFR_VERSION; }
+
+extern "C" unsigned long long afr_kernel_launches(void) {
+    return g_launches.load(std::memory_order_relaxed);
+}
 
 extern "C" const char *afr_last_error(void) { return g_last_error.c_str(); }
 

@@ -1,0 +1,140 @@
+"""
+Multi-GPU drivers: one process per GPU (``torch.distributed``, NCCL over NVLink), rows
+sharded in whole-timestep blocks.
+
+* predict / ``im_to_vis`` / ``phase_delay``: rows are independent (the reference's dask
+  ``row`` chunking, africanus/rime/dask.py:41-52, africanus/dft/dask.py:29-51) -- each rank
+  computes its own row block, no collective on the data path; an optional final gather
+  assembles the (row, chan, corr) blocks.
+* ``vis_to_im``: each rank reduces its row shard into a full (source, chan, corr) partial
+  image and the partials are summed -- the reference's ``ims.sum(axis=0)`` over row chunks
+  (africanus/dft/dask.py:71-90) -- with ONE ``all_reduce(SUM)``.
+
+``local_fn`` lets the CPU (gloo) tests substitute the oracle for the CUDA entry point; the
+default is always the CUDA path.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def row_shards(time_index, world_size):
+    """Contiguous row ranges [(start, stop), ...] -- one per rank -- cut at timestep
+    boundaries so that every rank needs only its own (time, ...) slices of the DDE/DIE
+    arrays and ``time_index - min`` stays local (the rule the reference's dask wrapper
+    imposes, africanus/rime/dask_predict.py:667-726).  Rows must be ordered by time."""
+    ti = np.asarray(time_index)
+    nrow = ti.shape[0]
+    if nrow == 0:
+        return [(0, 0)] * world_size
+    if np.any(np.diff(ti) < 0):
+        raise ValueError("row_shards: time_index must be non-decreasing")
+    starts = np.flatnonzero(np.concatenate(([True], ti[1:] != ti[:-1])))  # first row of each step
+    bounds = np.concatenate((starts, [nrow]))
+    ntime = starts.shape[0]
+    shards = []
+    for r in range(world_size):
+        t0 = (ntime * r) // world_size
+        t1 = (ntime * (r + 1)) // world_size
+        shards.append((int(bounds[t0]), int(bounds[t1])))
+    return shards
+
+
+def _rank_world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def _to_tensor(a, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+def sharded_im_to_vis(image, uvw, lm, frequency, time_index, convention="fourier", dtype=None,
+                      gather=False, group=None, local_fn=None):
+    """Row-sharded ``im_to_vis``: returns this rank's (rows, chan, corr) block and its
+    (start, stop) row range; with ``gather=True`` every rank returns the full array."""
+    if local_fn is None:
+        from .dft import im_to_vis as local_fn
+    rank, world = _rank_world(group)
+    r0, r1 = row_shards(time_index, world)[rank]
+    vis = local_fn(image, uvw[r0:r1], lm, frequency, convention=convention, dtype=dtype)
+    if not gather or world == 1:
+        return vis, (r0, r1)
+    return _gather_rows(vis, row_shards(time_index, world), group), (0, len(time_index))
+
+
+def sharded_fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
+                              dde1_jones=None, dde2_jones=None, die1_jones=None, base_vis=None,
+                              die2_jones=None, convention="fourier", gather=False, group=None,
+                              local_fn=None):
+    """Row-sharded fused predict.  DDE / DIE arrays are sliced to the rank's own timesteps."""
+    if local_fn is None:
+        from .rime import fused_predict_vis as local_fn
+    rank, world = _rank_world(group)
+    shards = row_shards(time_index, world)
+    r0, r1 = shards[rank]
+    ti = np.asarray(time_index)
+    tmin = int(ti.min()) if ti.size else 0
+    if r1 > r0:
+        t_lo, t_hi = int(ti[r0]) - tmin, int(ti[r1 - 1]) - tmin + 1
+    else:
+        t_lo, t_hi = 0, 0
+
+    def tslice(a, axis):
+        if a is None:
+            return None
+        idx = [slice(None)] * a.ndim
+        idx[axis] = slice(t_lo, t_hi)
+        return a[tuple(idx)]
+
+    vis = local_fn(lm, uvw[r0:r1], frequency, brightness, ti[r0:r1], antenna1[r0:r1],
+                   antenna2[r0:r1], tslice(dde1_jones, 1), tslice(dde2_jones, 1),
+                   tslice(die1_jones, 0), None if base_vis is None else base_vis[r0:r1],
+                   tslice(die2_jones, 0), convention=convention)
+    if not gather or world == 1:
+        return vis, (r0, r1)
+    return _gather_rows(vis, shards, group), (0, len(time_index))
+
+
+def _gather_rows(block, shards, group):
+    """Final gather of the per-rank row blocks (the only collective of the predict path)."""
+    as_numpy = not isinstance(block, torch.Tensor)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = _to_tensor(block, dev)
+    complex_in = t.is_complex()
+    if complex_in:
+        t = torch.view_as_real(t)
+    # shards may differ by a timestep: pad to the longest block, gather once, trim
+    nmax = max(s1 - s0 for s0, s1 in shards)
+    padded = torch.zeros((nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+    padded[: t.shape[0]] = t
+    outs = [torch.empty_like(padded) for _ in shards]
+    dist.all_gather(outs, padded, group=group)
+    full = torch.cat([o[: s1 - s0] for o, (s0, s1) in zip(outs, shards)], dim=0)
+    if complex_in:
+        full = torch.view_as_complex(full)
+    return full.cpu().numpy() if as_numpy else full
+
+
+def sharded_vis_to_im(vis, uvw, lm, frequency, flags, time_index, convention="fourier",
+                      dtype=None, group=None, local_fn=None):
+    """Row-sharded ``vis_to_im``: per-rank partial image + one all_reduce(SUM).  Every rank
+    returns the full (source, chan, corr) image."""
+    if local_fn is None:
+        from .dft import vis_to_im as local_fn
+    rank, world = _rank_world(group)
+    r0, r1 = row_shards(time_index, world)[rank]
+    partial = local_fn(vis[r0:r1], uvw[r0:r1], lm, frequency, flags[r0:r1],
+                       convention=convention, dtype=dtype)
+    if world == 1:
+        return partial
+    as_numpy = not isinstance(partial, torch.Tensor)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = _to_tensor(partial, dev).contiguous()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy() if as_numpy else t

@@ -57,6 +57,8 @@ extern "C" {
 int afr_version(void);
 const char *afr_last_error(void);
 int afr_device_count(void);
+/* number of CUDA kernels this library has launched in this process so far */
+unsigned long long afr_kernel_launches(void);
 /* Select the CUDA device used by subsequent calls on this host thread.  The library
  * links its own (static) CUDA runtime, whose current-device state is separate from any
  * other runtime in the process (e.g. PyTorch's): bindings call this before each entry

@@ -1,0 +1,185 @@
+"""
+Secondary timings reported under "extra" in bench.py's JSON line: every other entry of the
+hot path on device-resident synthetic inputs, CUDA-event timed
+(1 warm-up + best of 2).  Kept short so the default bench finishes in a few minutes.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import synth  # noqa: E402
+from codex_africanus_b200 import dft, rime  # noqa: E402
+from codex_africanus_b200 import distributed as D  # noqa: E402
+
+
+def _timed(fn, reps=2):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+        del out
+    return best
+
+
+def run(dev, fp64_peak):
+    rng = np.random.default_rng(3)
+    res = {}
+
+    def T(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    def compute_entry(name, seconds, terms, flop_per_term, peak=None, note=None):
+        e = {"Gterms_per_s": terms / seconds / 1e9, "ms": 1e3 * seconds, "terms": terms,
+             "flop_per_term": flop_per_term}
+        if peak:
+            e["frac_of_fp64_fma_peak"] = flop_per_term * terms / seconds / peak
+        if note:
+            e["note"] = note
+        res[name] = e
+
+    def bw_entry(name, seconds, nbytes, terms=None, note=None):
+        e = {"GB_per_s": nbytes / seconds / 1e9, "ms": 1e3 * seconds, "algorithmic_bytes": nbytes}
+        if terms:
+            e["Gterms_per_s"] = terms / seconds / 1e9
+        if note:
+            e["note"] = note
+        res[name] = e
+
+    # ---- configs[1] (100-timestep slice): adjoint and FP32 variants
+    na, ntime, nchan, nsrc = 64, 100, 256, 10000
+    uvw, tidx, a1, a2 = synth.uvw_tracks(na, ntime, rng, ntime_total=1000)
+    freq = synth.frequencies(nchan)
+    lm = synth.sky_lm(nsrc, rng)
+    image = synth.stokes_image(nsrc, nchan, 1, rng, freq)
+    d_uvw, d_lm, d_freq, d_img = T(uvw), T(lm), T(freq), T(image)
+    terms = float(nsrc) * uvw.shape[0] * nchan
+    vis = dft.im_to_vis(d_img, d_uvw, d_lm, d_freq)
+    flags = (torch.rand(vis.shape, device=dev) < 0.05)
+    t = _timed(lambda: dft.vis_to_im(vis, d_uvw, d_lm, d_freq, flags))
+    compute_entry("vis_to_im_f64_cfg2_100steps", t, terms, 11, fp64_peak, "5% flags")
+    t = _timed(lambda: dft.im_to_vis(d_img, d_uvw, d_lm, d_freq, dtype=np.complex64))
+    compute_entry("im_to_vis_c64_cfg2_100steps", t, terms, 11,
+                  note="FP32 rotation/accumulate, FP64 phase + anchors")
+    t = _timed(lambda: dft.vis_to_im(vis, d_uvw, d_lm, d_freq, flags, dtype=np.float32))
+    compute_entry("vis_to_im_f32_cfg2_100steps", t, terms, 11)
+    image4 = synth.stokes_image(nsrc, nchan, 4, rng, freq)
+    d_img4 = T(image4)
+    t = _timed(lambda: dft.im_to_vis(d_img4, d_uvw[: uvw.shape[0] // 4], d_lm, d_freq))
+    compute_entry("im_to_vis_c128_ncorr4_cfg2_25steps", t, terms / 4, 23, fp64_peak)
+    del vis, flags, d_img4, d_img
+
+    # ---- configs[0]: fused point-source predict, 64 ant x 100 times, 64 chan, 100 src, 2x2
+    nchan1, nsrc1 = 64, 100
+    freq1 = synth.frequencies(nchan1)
+    lm1 = synth.sky_lm(nsrc1, rng)
+    bright = synth.brightness_2x2(nsrc1, nchan1, rng, freq1)
+    d_b, d_f1, d_lm1 = T(bright), T(freq1), T(lm1)
+    d_t, d_a1, d_a2 = T(tidx), T(a1), T(a2)
+    terms1 = float(nsrc1) * uvw.shape[0] * nchan1
+    t = _timed(lambda: rime.fused_predict_vis(d_lm1, d_uvw, d_f1, d_b, d_t, d_a1, d_a2))
+    compute_entry("fused_point_predict_c128_cfg1", t, terms1, 39, fp64_peak)
+    die = synth.gains(ntime, na, nchan1, rng)
+    d_die = T(die)
+    t = _timed(lambda: rime.fused_predict_vis(d_lm1, d_uvw, d_f1, d_b, d_t, d_a1, d_a2,
+                                              die1_jones=d_die, die2_jones=d_die))
+    compute_entry("fused_point_predict_die_c128_cfg1", t, terms1, 39, fp64_peak)
+
+    # ---- un-fused building blocks on a 10-timestep slice (memory-bound by construction)
+    rows10 = 10 * (uvw.shape[0] // ntime)
+    K = rime.phase_delay(d_lm1, d_uvw[:rows10], d_f1)
+    t = _timed(lambda: rime.phase_delay(d_lm1, d_uvw[:rows10], d_f1))
+    bw_entry("phase_delay_c128_store", t, K.numel() * 16, terms=float(K.numel()),
+             note="16 B/term store-bound")
+    coh = torch.einsum("srf,sfij->srfij", K, d_b).contiguous()
+    del K
+    t = _timed(lambda: rime.predict_vis(d_t[:rows10], d_a1[:rows10], d_a2[:rows10], None, coh,
+                                        None, d_die[:10], None, d_die[:10]))
+    bw_entry("predict_vis_c128_2x2_materialised_coh", t, coh.numel() * 16, terms=float(coh.numel() // 4),
+             note="64 B/term load-bound")
+    del coh
+
+    # ---- configs[2] slice: beam_cube_dde -> fused DIE+DDE predict, 4096 chan, 1 timestep
+    nchan3, nsrc3 = 4096, 96
+    freq3 = synth.frequencies(nchan3)
+    lm3 = synth.sky_lm(nsrc3, rng)
+    beam, ext, bfreq = synth.beam_cube(257, 64, rng)
+    d_beam = T(beam)
+    pa = rng.uniform(-0.3, 0.3, (1, na))
+    perr = np.zeros((1, na, nchan3, 2))
+    ascale = np.ones((na, nchan3, 2))
+    d_pa, d_pe, d_as, d_f3, d_lm3 = T(pa), T(perr), T(ascale), T(freq3), T(lm3)
+    dde = rime.beam_cube_dde(d_beam, ext, bfreq, d_lm3, d_pa, d_pe, d_as, d_f3)
+    t = _timed(lambda: rime.beam_cube_dde(d_beam, ext, bfreq, d_lm3, d_pa, d_pe, d_as, d_f3))
+    bw_entry("beam_cube_dde_c128_257x257x64", t, dde.numel() * 16,
+             note="bytes = output only; 8 corner gathers/elem from a 270 MB cube")
+    rows3 = uvw.shape[0] // ntime
+    bright3 = synth.brightness_2x2(nsrc3, nchan3, rng, freq3)
+    die3 = synth.gains(1, na, nchan3, rng)
+    d_b3, d_die3 = T(bright3), T(die3)
+    tz = torch.zeros(rows3, dtype=torch.int32, device=dev)
+    terms3 = float(nsrc3) * rows3 * nchan3
+    t = _timed(lambda: rime.fused_predict_vis(d_lm3, d_uvw[:rows3], d_f3, d_b3, tz, d_a1[:rows3],
+                                              d_a2[:rows3], dde, dde, d_die3, None, d_die3))
+    e = {"Gterms_per_s": terms3 / t / 1e9, "ms": 1e3 * t, "terms": terms3, "flop_per_term": 95,
+         "frac_of_fp64_fma_peak": 95 * terms3 / t / fp64_peak,
+         "dde_GB_per_s_if_read_once": dde.numel() * 16 / t / 1e9,
+         "dde_GB_per_s_gathered": 128 * terms3 / t / 1e9,
+         "note": "configs[2] slice: 64 ant, 1 timestep, 4096 chan, %d src; DDE %.2f GB" % (
+             nsrc3, dde.numel() * 16 / 1e9)}
+    res["fused_dde_predict_c128_cfg3_slice"] = e
+    return res
+
+
+def run_distributed(dev, rank, world):
+    """configs[4]-shaped vis_to_im: per-rank partial dirty image + one NCCL all_reduce."""
+    import torch.distributed as dist
+
+    rng = np.random.default_rng(5)
+    na, ntime, nchan, npix = 64, 40, 64, 256
+    uvw, tidx, a1, a2 = synth.uvw_tracks(na, ntime * world, rng, ntime_total=ntime * world)
+    cell = np.deg2rad(4.0 / 3600.0)
+    x = (np.arange(npix) - npix // 2) * cell
+    ll, mm = np.meshgrid(x, x)
+    lm = np.stack([ll.ravel(), mm.ravel()], axis=1)
+    freq = synth.frequencies(nchan)
+
+    def T(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    r0, r1 = D.row_shards(tidx, world)[rank]
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    vis = torch.randn((r1 - r0, nchan, 1), dtype=torch.complex128, device=dev, generator=g)
+    flags = torch.rand((r1 - r0, nchan, 1), device=dev, generator=g) < 0.05
+    d_uvw, d_lm, d_freq = T(uvw[r0:r1]), T(lm), T(freq)
+    out = {}
+    for _ in range(2):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        part = dft.vis_to_im(vis, d_uvw, d_lm, d_freq, flags)
+        e1.record()
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        e2.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, ar_ms = float(tt[0]), float(tt[1])
+    terms = float(lm.shape[0]) * uvw.shape[0] * nchan
+    out["vis_to_im_f64_allreduce"] = {
+        "Gterms_per_s": terms / (total_ms * 1e-3) / 1e9, "ms": total_ms, "allreduce_ms": ar_ms,
+        "image_bytes": int(lm.shape[0] * nchan * 8), "terms": terms,
+        "note": "%dx%d pixels, %d chan, %d rows over %d ranks; NCCL all_reduce(SUM) of the "
+                "per-rank partial image" % (npix, npix, nchan, uvw.shape[0], world)}
+    return out
