@@ -26,6 +26,7 @@
 //  * two y's are processed per inner iteration so each thread has two independent
 //    rotation chains in flight (measured DFMA latency 8.4 cycles, issue 1 per 2 cycles/SMSP).
 #include <algorithm>
+#include <cstdlib>
 
 #include "afr_dft.cuh"
 
@@ -55,6 +56,7 @@ struct DftParams {
     int fast;         // 1: W rows are contiguous and copied by cp.async granules
     int granule;      // 4, 8 or 16 bytes
     int row_chunks_log2;  // log2(granules per W tile row)
+    int debug;            // development only (AFR_DEBUG): 1 skip produce after tile 0, 2 skip staging
 };
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) {
@@ -125,7 +127,7 @@ template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NW, bool EXACT
 __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftParams p) {
     constexpr int NT = NW * 32;
     constexpr int NV = NCORR * (WC ? 2 : 1);  // W scalars per channel
-    constexpr int G = (NV >= 4) ? 2 : 4;      // channels per register group of W values
+    constexpr int G = (NV * (int)sizeof(ACC) >= 16) ? 1 : 16 / (NV * (int)sizeof(ACC));  // channels per 16-byte W load
     constexpr int SZ = (int)sizeof(ACC);
     static_assert(CH % G == 0 && (G * NV * SZ) % 16 == 0, "tiling");
     static_assert((CH & (CH - 1)) == 0, "CH must be a power of two");
@@ -387,13 +389,15 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
             if (t > 0) apply_flags(t);
             __syncthreads();  // W(t), y(t+1), anchors(t) visible; buffers of tile t-1 free
             issue_yc(t + 2);
-            issue_w(t + 1);
+            if (!(p.debug & 2)) issue_w(t + 1);
             cp_async_commit();
             if (!p.fast && t + 1 < ntiles) stage_tile_slow(t + 1);
             // consume(t) and produce(t+1) are independent: alternate their order between the
             // warps of a scheduler so the latency-bound anchor math of one warp overlaps the
             // FP64-dense rotation loop of its neighbours
-            if ((warp >> 2) & 1) {
+            if (p.debug & 1) {
+                consume_tile(t);
+            } else if ((warp >> 2) & 1) {
                 produce_tile(t + 1);
                 consume_tile(t);
             } else {
@@ -404,6 +408,302 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
     }
 
     // ---- write the owner's channel run
+    if (x < p.nx) {
+        ACC *o = reinterpret_cast<ACC *>(p.out) + (size_t)blockIdx.z * p.out_split_stride;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int f = cta_f0 + fo + j;
+            if (f < p.nchan) {
+                const long long base = (x * p.nchan + f) * p.wstride + p.coff;
+#pragma unroll
+                for (int c = 0; c < NCORR; ++c) {
+                    if (ADJ) {
+                        o[base + c] = are[j][c];
+                    } else {
+                        C2<ACC> v;
+                        v.re = are[j][c];
+                        v.im = aim[j][c];
+                        reinterpret_cast<C2<ACC> *>(o)[base + c] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Warp-specialised variant (EXPERIMENTAL, opt-in with AFR_WS=1).
+//
+// Same tiling, anchors and rotation loop as phasor_stream_kernel, but the CTA is
+// NWC consumer warps + 4 producer warps.  Producers run up to two tiles ahead: they wait
+// for a buffer to be released (mbarrier "empty"), cp.async the W tile into it, compute the
+// tile's anchors and publish it (mbarrier "full").  A consumer warp waits for "full", runs
+// the FP64 rotation loop, and releases the buffer with ONE arrive per warp -- consumer
+// warps never synchronise with each other, so a late warp stalls nobody and the integer /
+// sincos-heavy producer instructions fill the issue slots the FP64 pipe leaves empty.
+// (setmaxnreg rebalancing is available through CREGS/PREGS but not needed: 96 regs suffice.)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n\t}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr int kProducerWarps = 4;
+
+template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NWC, bool EXACT, int CREGS, int PREGS>
+__global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
+    phasor_stream_ws_kernel(const DftParams p) {
+    constexpr int NTP = kProducerWarps * 32;  // producer threads
+    constexpr int NV = NCORR * (WC ? 2 : 1);
+    constexpr int G = (NV * (int)sizeof(ACC) >= 16) ? 1 : 16 / (NV * (int)sizeof(ACC));
+    constexpr int SZ = (int)sizeof(ACC);
+    static_assert(CH % G == 0 && (G * NV * SZ) % 16 == 0, "tiling");
+    static_assert((CH & (CH - 1)) == 0 && NWC % 4 == 0, "shape");
+    using CA = C2<ACC>;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nck = p.nck, yt = p.yt;
+    const int xgw = (NWC / nck) * 32;
+    const int ft = nck * CH;
+    const int cta_f0 = blockIdx.y * ft;
+    const long long cta_x0 = (long long)blockIdx.x * xgw;
+
+    const size_t anch_elems = (size_t)yt * nck * xgw;
+    const size_t dstp_elems = (size_t)yt * xgw;
+    const size_t w_elems = (size_t)yt * ft * NV;
+    const size_t buf_bytes = (anch_elems + dstp_elems) * sizeof(CA) + w_elems * SZ;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * buf_bytes);  // full[2], empty[2]
+    double *fq = reinterpret_cast<double *>(bars + 4);                        // [ft] (exact)
+    auto anch_of = [&](int b) { return reinterpret_cast<CA *>(smem_raw + (size_t)b * buf_bytes); };
+    auto dstp_of = [&](int b) { return anch_of(b) + anch_elems; };
+    auto w_of = [&](int b) { return reinterpret_cast<ACC *>(dstp_of(b) + dstp_elems); };
+
+    const long long ys = (long long)blockIdx.z * p.ysplit;
+    const long long ye = min(p.ny, ys + p.ysplit);
+    const int ntiles = (int)((ye - ys + yt - 1) / yt);
+
+    if (tid == 0) {
+        mbar_init(&bars[0], NTP);
+        mbar_init(&bars[1], NTP);
+        mbar_init(&bars[2], NWC);
+        mbar_init(&bars[3], NWC);
+    }
+    if (EXACT)
+        for (int i = tid; i < ft; i += blockDim.x) fq[i] = p.freq[min(cta_f0 + i, p.nchan - 1)];
+    __syncthreads();
+
+    if (warp >= NWC) {
+        // =============================== PRODUCERS ===============================
+        if (PREGS > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PREGS > 0 ? PREGS : 24));
+        const int ptid = tid - NWC * 32;
+        const bool f32dot = p.f32dot != 0;
+        const int valid_ch = min(ft, p.nchan - cta_f0);
+        const int px_local = ptid % xgw;
+        const int py0 = ptid / xgw;
+        const int pystep = NTP / xgw > 0 ? NTP / xgw : 1;
+        // owners handled by this thread: px_local, px_local + NTP, ... (when xgw > NTP)
+        double dnu = 0.0, nu0 = 0.0;
+        if (!EXACT) {
+            if (p.nchan > 1) dnu = (p.freq[p.nchan - 1] - p.freq[0]) / (double)(p.nchan - 1);
+            nu0 = p.freq[cta_f0];
+        }
+        const int g = p.granule, rcl = p.row_chunks_log2;
+        const int total_chunks = yt << rcl;
+        const int valid_bytes = valid_ch * NV * SZ;
+        const long long row_pitch = (long long)p.nchan * NV * SZ;
+        const char *w_cta = reinterpret_cast<const char *>(p.w) + (long long)cta_f0 * NV * SZ;
+
+        for (int t = 0; t < ntiles; ++t) {
+            const int b = t & 1;
+            mbar_wait(&bars[2 + b], ((t >> 1) & 1) ^ 1);  // buffer released by every consumer warp
+            const long long y0 = ys + (long long)t * yt;
+            ACC *wt = w_of(b);
+            unsigned long long bits = 0;  // 4 drop bits per granule, <= 16 granules per thread
+            if (p.fast) {
+                const int rows_valid = (int)min((long long)yt, ye - y0);
+                const char *src_tile = w_cta + y0 * row_pitch;
+                const unsigned dst_tile = smem_addr(wt);
+                int k = 0;
+                for (int c = ptid; c < total_chunks; c += NTP, ++k) {
+                    const int yl = c >> rcl;
+                    const int off = (c - (yl << rcl)) * g;
+                    const bool ok = (yl < rows_valid) && (off < valid_bytes);
+                    cp_async(dst_tile + c * g, src_tile + (ok ? yl * row_pitch + off : 0), g, ok ? g : 0);
+                    if (ADJ && p.anyflag != nullptr && ok) {
+                        const uint8_t *af = p.anyflag + (y0 + yl) * p.nchan + cta_f0;
+                        const int s0 = off / SZ;
+                        for (int e = 0; e < g / SZ; ++e)
+                            if (af[(s0 + e) / NV]) bits |= 1ull << (k * 4 + e);
+                    }
+                }
+                cp_async_commit();
+            } else {
+                const ACC *wsrc = reinterpret_cast<const ACC *>(p.w);
+                const int per_y = ft * NV;
+                for (int idx = ptid; idx < yt * per_y; idx += NTP) {
+                    const int yl = idx / per_y;
+                    const int rem = idx - yl * per_y;
+                    const int fl = rem / NV;
+                    const int e = rem - fl * NV;
+                    const long long y = y0 + yl;
+                    const int f = cta_f0 + fl;
+                    ACC val = ACC(0);
+                    if (y < ye && f < p.nchan) {
+                        const long long sample = y * p.nchan + f;
+                        const bool drop = ADJ && p.anyflag != nullptr && p.anyflag[sample] != 0;
+                        if (!drop) {
+                            const long long base = sample * p.wstride + p.coff;
+                            val = WC ? wsrc[2 * (base + (e >> 1)) + (e & 1)] : wsrc[base + e];
+                        }
+                    }
+                    wt[idx] = val;
+                }
+            }
+            // ---- anchors of tile t
+            CA *anch = anch_of(b);
+            CA *dstp = dstp_of(b);
+            double *phis = reinterpret_cast<double *>(anch);
+            for (int xo = px_local; xo < xgw; xo += NTP) {
+                long long pxi = cta_x0 + xo;
+                if (pxi >= p.nx) pxi = p.nx - 1;
+                const double px0 = p.xc[3 * pxi], px1 = p.xc[3 * pxi + 1], px2 = p.xc[3 * pxi + 2];
+                for (int yl = py0; yl < yt; yl += pystep) {
+                    const long long y = y0 + yl;
+                    const bool live = y < ye;
+                    double phi = 0.0;
+                    if (live)
+                        phi = __dmul_rn(p.cst, phase_dot(px0, px1, px2, p.yc[3 * y], p.yc[3 * y + 1],
+                                                         p.yc[3 * y + 2], f32dot));
+                    if (EXACT) {
+                        phis[yl * xgw + xo] = phi;
+                    } else {
+                        C2<double> a = {0.0, 0.0}, d = {0.0, 0.0}, D = {1.0, 0.0};
+                        if (live) {
+                            a = cis_fast(__dmul_rn(phi, nu0));
+                            d = cis_fast(__dmul_rn(phi, dnu));
+                            if (nck > 1) {
+                                D = d;
+#pragma unroll
+                                for (int q = 1; q < CH; q *= 2) {
+                                    const double re = D.re * D.re - D.im * D.im;
+                                    D.im = 2.0 * D.re * D.im;
+                                    D.re = re;
+                                }
+                            }
+                        }
+                        CA dd;
+                        dd.re = (ACC)d.re;
+                        dd.im = (ACC)d.im;
+                        dstp[yl * xgw + xo] = dd;
+                        for (int k = 0; k < nck; ++k) {
+                            CA aa;
+                            aa.re = (ACC)a.re;
+                            aa.im = (ACC)a.im;
+                            anch[(yl * nck + k) * xgw + xo] = aa;
+                            a = cmul(a, D);
+                        }
+                    }
+                }
+            }
+            if (p.fast) {
+                cp_async_wait_all();
+                if (ADJ && bits) {  // zero this thread's flagged scalars
+                    char *wtb = reinterpret_cast<char *>(wt);
+                    int k = 0;
+                    for (int c = ptid; c < total_chunks; c += NTP, ++k) {
+                        const unsigned bsel = (unsigned)(bits >> (k * 4)) & 0xFu;
+                        if (bsel) {
+                            ACC *dst = reinterpret_cast<ACC *>(wtb + (size_t)c * g);
+                            for (int e = 0; e < g / SZ; ++e)
+                                if (bsel & (1u << e)) dst[e] = ACC(0);
+                        }
+                    }
+                }
+            }
+            mbar_arrive(&bars[b]);  // release: anchors, W tile and flag zeroing are visible
+        }
+        return;
+    }
+
+    // ================================= CONSUMERS =================================
+    if (CREGS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(CREGS > 0 ? CREGS : 24));
+    const int ck = warp % nck;
+    const int x_local = (warp / nck) * 32 + lane;
+    const long long x = cta_x0 + x_local;
+    const int fo = ck * CH;
+
+    ACC are[CH][NCORR];
+    ACC aim[CH][ADJ ? 1 : NCORR];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+#pragma unroll
+        for (int c = 0; c < NCORR; ++c) are[j][c] = ACC(0);
+#pragma unroll
+        for (int c = 0; c < (ADJ ? 1 : NCORR); ++c) aim[j][c] = ACC(0);
+    }
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int b = t & 1;
+        mbar_wait(&bars[b], (t >> 1) & 1);
+        const CA *anch = anch_of(b);
+        const CA *dstp = dstp_of(b);
+        const ACC *wt = w_of(b);
+        if (EXACT) {
+            const double *phis = reinterpret_cast<const double *>(anch);
+#pragma unroll 1
+            for (int yl = 0; yl < yt; ++yl) {
+                const double phi = phis[yl * xgw + x_local];
+                const ACC *wrow = wt + (size_t)(yl * ft + fo) * NV;
+#pragma unroll
+                for (int j = 0; j < CH; j += G) {
+                    ACC wv[G * NV];
+                    load_vec<G * NV>(wrow + j * NV, wv);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const C2<double> zd = cis_fast(__dmul_rn(phi, fq[fo + j + g]));
+                        CA z;
+                        z.re = (ACC)zd.re;
+                        z.im = (ACC)zd.im;
+                        accumulate<NCORR, WC, ADJ, ACC>(are[j + g], aim[j + g], z, wv + g * NV);
+                    }
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int yl = 0; yl < yt; ++yl) {
+                CA z = anch[(yl * nck + ck) * xgw + x_local];
+                const CA d = dstp[yl * xgw + x_local];
+                const ACC *wrow = wt + (size_t)(yl * ft + fo) * NV;
+#pragma unroll
+                for (int j = 0; j < CH; j += G) {
+                    ACC wv[G * NV];
+                    load_vec<G * NV>(wrow + j * NV, wv);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        accumulate<NCORR, WC, ADJ, ACC>(are[j + g], aim[j + g], z, wv + g * NV);
+                        if (j + g + 1 < CH) z = cmul(z, d);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[2 + b]);  // this warp is done with buffer b
+    }
+
     if (x < p.nx) {
         ACC *o = reinterpret_cast<ACC *>(p.out) + (size_t)blockIdx.z * p.out_split_stride;
 #pragma unroll
@@ -504,6 +804,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     int nck = 1;
     while (nck < runs && nck < NW / 2) nck *= 2;
     p.nck = nck;
+    p.debug = getenv("AFR_DEBUG") ? atoi(getenv("AFR_DEBUG")) : 0;
     const int xgw = (NW / nck) * 32;
     const int ft = nck * CH;
     const long long gx = (p.nx + xgw - 1) / xgw;
@@ -524,11 +825,19 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     // y items per tile: as many (even, <= 8) as fit double-buffered in shared memory and in
     // kMaxChunks cp.async granules per thread
     const size_t per_y = (size_t)(nck + 1) * xgw * sizeof(C2<ACC>) + (size_t)ft * NV * SZ;
+    const char *ws_env = getenv("AFR_WS");
+    // experimental, off by default (AFR_WS=1 enables it for the ncorr=1 real-image forward
+    // kernel): see DESIGN.md 4.1 -- the 640-thread CTA caps consumers at 96 registers, which
+    // costs more in the rotation loop than the removed barrier gains
+    const bool use_ws = (sizeof(ACC) == 8 && NCORR == 1 && !WC && !ADJ && !exact) &&
+                        (ws_env && atoi(ws_env) == 1);
+    // granules one thread may have in flight: 8 per thread of the whole CTA, or 16 per
+    // producer thread of the warp-specialised kernel
+    const long long max_chunks = use_ws ? 16LL * kProducerWarps * 32 : (long long)kMaxChunks * NT;
     int yt = 8;
-    while (yt > 2 && (2 * yt * per_y > 200 * 1024 ||
-                      (long long)yt * row_chunks > (long long)kMaxChunks * NT))
+    while (yt > 2 && (2 * yt * per_y > 200 * 1024 || (long long)yt * row_chunks > max_chunks))
         yt -= 2;
-    if ((long long)yt * row_chunks > (long long)kMaxChunks * NT) p.fast = 0;
+    if ((long long)yt * row_chunks > max_chunks) p.fast = 0;
     p.yt = yt;
     const size_t smem = 2 * yt * per_y + 3 * (size_t)yt * 3 * sizeof(double) + (size_t)ft * sizeof(double);
 
@@ -570,7 +879,24 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     }
 
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nsplit);
-    if (exact) {
+    if constexpr (sizeof(ACC) == 8 && NCORR == 1 && !WC && !ADJ) {
+      if (use_ws && !exact) {
+        // setmaxnreg can only move registers inside the CTA's launch-time pool (640 x 96);
+        // the consumer loop fits 96 registers without spills, so no rebalancing is done (0 = off)
+        constexpr int CREGS = 0, PREGS = 0;
+        const size_t smem_ws = 2 * yt * per_y + 4 * sizeof(uint64_t) + (size_t)ft * sizeof(double);
+        const int threads = (NW + kProducerWarps) * 32;
+        {
+            auto kern = phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS>;
+            AFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem_ws));
+            kern<<<grid, threads, smem_ws, stream>>>(p);
+        }
+      }
+    }
+    if (use_ws) {
+        // launched above
+    } else if (exact) {
         auto kern = phasor_stream_kernel<NCORR, WC, ADJ, ACC, CH, NW, true>;
         AFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));

@@ -2,17 +2,15 @@
 //
 // Stand-alone, the K term is bound by the HBM store of its (source,row,chan) output
 // (16 B/term complex128, 8 B/term complex64), so the kernel is organised around the
-// store: one thread produces a run of kRun consecutive channels (kRun * 16 B contiguous,
-// 128-bit stores), consecutive threads produce consecutive runs, and the phasor inside a
-// run advances by a complex rotation from a sincos anchor (equispaced channels) or by one
-// sincos per channel (arbitrary channels / float32 inputs, where the reference's per-channel
-// rounding of the phase must be reproduced).
+// store: one thread produces ONE 16-byte store (one complex128 element, or two complex64
+// elements) and consecutive lanes write consecutive 16-byte slots, i.e. every warp store
+// is a fully coalesced 512-byte segment.  At 16 B/term the FP64 pipe has room for one
+// branch-free sincos (cis_fast, 22 FP64 instructions) per element, so each element's
+// phase is fl(fl(phi)*nu_f) exactly as the reference rounds it -- no recurrence here.
 #include "afr_dft.cuh"
 
 namespace afr {
 namespace {
-
-constexpr int kRun = 8;  // channels per thread
 
 struct PhaseParams {
     const double *lmn;   // (nsrc,3), n already clamped (rime/phase.py:42-43)
@@ -36,37 +34,16 @@ __device__ __forceinline__ double real_phase(const PhaseParams &p, long long s, 
     return __dmul_rn(p.cst, phase_dot(l, m, n, u, v, w, false));
 }
 
-template <bool EXACT>
 __global__ void __launch_bounds__(256) phase_delay_f64_kernel(const PhaseParams p) {
-    const int runs = (p.nchan + kRun - 1) / kRun;
-    const long long total = p.nsrc * p.nrow * runs;
-    double dnu = 0.0;
-    if (!EXACT && p.nchan > 1) dnu = (p.freq[p.nchan - 1] - p.freq[0]) / (double)(p.nchan - 1);
+    const long long total = p.nsrc * p.nrow * p.nchan;
+    double2 *out = reinterpret_cast<double2 *>(p.out);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long sr = i / runs;
-        const int k = (int)(i - sr * runs);
+        const long long sr = i / p.nchan;
+        const int f = (int)(i - sr * p.nchan);
         const long long s = sr / p.nrow, r = sr - s * p.nrow;
-        const double phi = real_phase(p, s, r);
-        const int f0 = k * kRun;
-        double2 *o = reinterpret_cast<double2 *>(p.out) + (sr * p.nchan + f0);
-        if (EXACT) {
-#pragma unroll
-            for (int j = 0; j < kRun; ++j) {
-                if (f0 + j < p.nchan) {
-                    const C2<double> z = cis_fast(__dmul_rn(phi, p.freq[f0 + j]));
-                    o[j] = make_double2(z.re, z.im);
-                }
-            }
-        } else {
-            C2<double> z = cis_fast(__dmul_rn(phi, p.freq[f0]));
-            const C2<double> d = cis_fast(__dmul_rn(phi, dnu));
-#pragma unroll
-            for (int j = 0; j < kRun; ++j) {
-                if (f0 + j < p.nchan) o[j] = make_double2(z.re, z.im);
-                z = cmul(z, d);
-            }
-        }
+        const C2<double> z = cis_fast(__dmul_rn(real_phase(p, s, r), p.freq[f]));
+        out[i] = make_double2(z.re, z.im);
     }
 }
 
@@ -75,12 +52,14 @@ __global__ void __launch_bounds__(256) phase_delay_f64_kernel(const PhaseParams 
 __global__ void __launch_bounds__(256)
     phase_delay_f32_kernel(const float *lm, const float *uvw, const float *freq, float2 *out,
                            float cst, long long nsrc, long long nrow, int nchan) {
-    const int runs = (nchan + kRun - 1) / kRun;
-    const long long total = nsrc * nrow * runs;
+    // two consecutive elements (16 bytes) per thread when nchan is even, else one
+    const int per = (nchan % 2 == 0) ? 2 : 1;
+    const long long total = nsrc * nrow * nchan / per;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long sr = i / runs;
-        const int k = (int)(i - sr * runs);
+        const long long e0 = i * per;
+        const long long sr = e0 / nchan;
+        const int f0 = (int)(e0 - sr * nchan);
         const long long s = sr / nrow, r = sr - s * nrow;
         const float l = lm[2 * s], m = lm[2 * s + 1];
         float n = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(l, l)), __fmul_rn(m, m));
@@ -88,16 +67,14 @@ __global__ void __launch_bounds__(256)
         const float u = uvw[3 * r], v = uvw[3 * r + 1], w = uvw[3 * r + 2];
         const float rp = __fmul_rn(
             cst, __fadd_rn(__fadd_rn(__fmul_rn(l, u), __fmul_rn(m, v)), __fmul_rn(n, w)));
-        const int f0 = k * kRun;
-        float2 *o = out + (sr * nchan + f0);
-#pragma unroll
-        for (int j = 0; j < kRun; ++j) {
-            if (f0 + j < nchan) {
-                const float ph = __fmul_rn(rp, freq[f0 + j]);
-                float sn, cs;
-                sincosf(ph, &sn, &cs);
-                o[j] = make_float2(cs, sn);
-            }
+        float sn0, cs0;
+        sincosf(__fmul_rn(rp, freq[f0]), &sn0, &cs0);
+        if (per == 2) {
+            float sn1, cs1;
+            sincosf(__fmul_rn(rp, freq[f0 + 1]), &sn1, &cs1);
+            reinterpret_cast<float4 *>(out)[i] = make_float4(cs0, sn0, cs1, sn1);
+        } else {
+            out[e0] = make_float2(cs0, sn0);
         }
     }
 }
@@ -142,14 +119,9 @@ extern "C" int afr_phase_delay_f64(const double *lm, const double *uvw, const do
     p.nrow = nrow;
     p.nchan = (int)nchan;
     p.all_f32_coords = (lm_f32 && uvw_f32) ? 1 : 0;
-    const long long total = nsrc * nrow * ((nchan + kRun - 1) / kRun);
-    // float32 coordinates or frequencies: the reference's per-channel rounding is
-    // reproduced by the exact path only
-    const bool exact = chan_mode == AFR_CHAN_EXACT || f32_flags != 0;
-    if (exact)
-        phase_delay_f64_kernel<true><<<grid_for(total), 256, 0, stream>>>(p);
-    else
-        phase_delay_f64_kernel<false><<<grid_for(total), 256, 0, stream>>>(p);
+    (void)chan_mode;  // every element takes its own sincos: both modes are exact
+    const long long total = nsrc * nrow * nchan;
+    phase_delay_f64_kernel<<<grid_for(total), 256, 0, stream>>>(p);
     AFR_LAUNCH_OK();
     return 0;
 }
@@ -164,7 +136,7 @@ extern "C" int afr_phase_delay_f32(const float *lm, const float *uvw, const floa
     if (nsrc == 0 || nrow == 0 || nchan == 0) return 0;
     float cst = (float)(-kTwoPiOverC);
     if (convention == AFR_CASA) cst = -cst;
-    const long long total = nsrc * nrow * ((nchan + kRun - 1) / kRun);
+    const long long total = nsrc * nrow * nchan;
     phase_delay_f32_kernel<<<grid_for(total), 256, 0, stream>>>(lm, uvw, freq, (float2 *)out, cst,
                                                                nsrc, nrow, (int)nchan);
     AFR_LAUNCH_OK();
