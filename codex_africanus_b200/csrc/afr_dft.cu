@@ -432,7 +432,8 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
 }
 
 // ---------------------------------------------------------------------------
-// Warp-specialised variant (EXPERIMENTAL, opt-in with AFR_WS=1).
+// Warp-specialised variant: the default for the FP64 kernels (AFR_WS=0 selects the
+// single-role kernel above, which the FP32 variants always use).
 //
 // Same tiling, anchors and rotation loop as phasor_stream_kernel, but the CTA is
 // NWC consumer warps + 4 producer warps.  Producers run up to two tiles ahead: they wait
@@ -441,7 +442,9 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
 // the FP64 rotation loop, and releases the buffer with ONE arrive per warp -- consumer
 // warps never synchronise with each other, so a late warp stalls nobody and the integer /
 // sincos-heavy producer instructions fill the issue slots the FP64 pipe leaves empty.
-// (setmaxnreg rebalancing is available through CREGS/PREGS but not needed: 96 regs suffice.)
+// Registers are rebalanced with setmaxnreg inside the CTA's launch-time pool (640 x 96 =
+// 512 x 104 + 128 x 64): the extra 8 registers let ptxas keep the operand-reuse-friendly
+// schedule of the rotation loop (tools/sass_dp_model.py: 14.2 vs 16.0 cycles per term).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count));
@@ -826,11 +829,11 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     // kMaxChunks cp.async granules per thread
     const size_t per_y = (size_t)(nck + 1) * xgw * sizeof(C2<ACC>) + (size_t)ft * NV * SZ;
     const char *ws_env = getenv("AFR_WS");
-    // experimental, off by default (AFR_WS=1 enables it for the ncorr=1 real-image forward
-    // kernel): see DESIGN.md 4.1 -- the 640-thread CTA caps consumers at 96 registers, which
-    // costs more in the rotation loop than the removed barrier gains
-    const bool use_ws = (sizeof(ACC) == 8 && NCORR == 1 && !WC && !ADJ && !exact) &&
-                        (ws_env && atoi(ws_env) == 1);
+    // Which FP64 variants run warp-specialised (16 consumer + 4 producer warps) was decided
+    // by measurement (tools/ws_sweep.py, B200): the forward kernels with one correlation or a
+    // complex W, and the 4-correlation real adjoint.  AFR_WS=0 / 1 forces the choice.
+    constexpr bool kPreferWS = (!ADJ && (NCORR == 1 || WC)) || (ADJ && !WC && NCORR == 4);
+    const bool use_ws = (sizeof(ACC) == 8) && (ws_env ? atoi(ws_env) != 0 : kPreferWS);
     // granules one thread may have in flight: 8 per thread of the whole CTA, or 16 per
     // producer thread of the warp-specialised kernel
     const long long max_chunks = use_ws ? 16LL * kProducerWarps * 32 : (long long)kMaxChunks * NT;
@@ -879,19 +882,27 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     }
 
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nsplit);
-    if constexpr (sizeof(ACC) == 8 && NCORR == 1 && !WC && !ADJ) {
-      if (use_ws && !exact) {
-        // setmaxnreg can only move registers inside the CTA's launch-time pool (640 x 96);
-        // the consumer loop fits 96 registers without spills, so no rebalancing is done (0 = off)
-        constexpr int CREGS = 0, PREGS = 0;
+    if constexpr (sizeof(ACC) == 8) {
+      if (use_ws) {
+        // setmaxnreg can only move registers inside the CTA's launch-time pool: 640 threads
+        // x 96 registers = 512 x 104 (consumers) + 128 x 64 (producers)
+        constexpr int CREGS = 104, PREGS = 64;
         const size_t smem_ws = 2 * yt * per_y + 4 * sizeof(uint64_t) + (size_t)ft * sizeof(double);
         const int threads = (NW + kProducerWarps) * 32;
-        {
-            auto kern = phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS>;
+        auto launch_ws = [&](auto kern) -> int {
+            cudaFuncAttributes attr;
+            AFR_CUDA_OK(cudaFuncGetAttributes(&attr, kern));
+            // the register move must balance exactly, otherwise setmaxnreg.inc never returns
+            AFR_REQUIRE(threads * attr.numRegs >= NW * 32 * CREGS + kProducerWarps * 32 * PREGS,
+                        "phasor_stream_ws: launch-time register pool too small for setmaxnreg");
             AFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem_ws));
             kern<<<grid, threads, smem_ws, stream>>>(p);
-        }
+            return 0;
+        };
+        int rc = exact ? launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, true, CREGS, PREGS>)
+                       : launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS>);
+        if (rc) return rc;
       }
     }
     if (use_ws) {

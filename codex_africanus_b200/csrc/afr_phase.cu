@@ -2,9 +2,8 @@
 //
 // Stand-alone, the K term is bound by the HBM store of its (source,row,chan) output
 // (16 B/term complex128, 8 B/term complex64), so the kernel is organised around the
-// store: one thread produces ONE 16-byte store (one complex128 element, or two complex64
-// elements) and consecutive lanes write consecutive 16-byte slots, i.e. every warp store
-// is a fully coalesced 512-byte segment.  At 16 B/term the FP64 pipe has room for one
+// store: a warp walks one (source,row) line of the output with lane <-> channel, so every
+// warp store is a fully coalesced 512-byte (256-byte for complex64) segment.  At 16 B/term the FP64 pipe has room for one
 // branch-free sincos (cis_fast, 22 FP64 instructions) per element, so each element's
 // phase is fl(fl(phi)*nu_f) exactly as the reference rounds it -- no recurrence here.
 #include "afr_dft.cuh"
@@ -34,16 +33,26 @@ __device__ __forceinline__ double real_phase(const PhaseParams &p, long long s, 
     return __dmul_rn(p.cst, phase_dot(l, m, n, u, v, w, false));
 }
 
+constexpr int kRowsPerBlock = 64;  // rows of one source handled by a 256-thread block
+
+// block <-> (source, block of kRowsPerBlock rows); warp <-> one row at a time; lane <-> channel
+// (f = lane, lane+32, ...), so a warp store is 512 contiguous bytes and no thread divides.
 __global__ void __launch_bounds__(256) phase_delay_f64_kernel(const PhaseParams p) {
-    const long long total = p.nsrc * p.nrow * p.nchan;
+    const long long row_blocks = (p.nrow + kRowsPerBlock - 1) / kRowsPerBlock;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double2 *out = reinterpret_cast<double2 *>(p.out);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long sr = i / p.nchan;
-        const int f = (int)(i - sr * p.nchan);
-        const long long s = sr / p.nrow, r = sr - s * p.nrow;
-        const C2<double> z = cis_fast(__dmul_rn(real_phase(p, s, r), p.freq[f]));
-        out[i] = make_double2(z.re, z.im);
+    for (long long blk = blockIdx.x; blk < p.nsrc * row_blocks; blk += gridDim.x) {
+        const long long s = blk / row_blocks;
+        const long long r0 = (blk - s * row_blocks) * kRowsPerBlock;
+        const long long r1 = min(p.nrow, r0 + kRowsPerBlock);
+        for (long long r = r0 + warp; r < r1; r += 8) {
+            const double phi = real_phase(p, s, r);
+            double2 *o = out + (s * p.nrow + r) * p.nchan;
+            for (int f = lane; f < p.nchan; f += 32) {
+                const C2<double> z = cis_fast(__dmul_rn(phi, p.freq[f]));
+                o[f] = make_double2(z.re, z.im);
+            }
+        }
     }
 }
 
@@ -52,29 +61,25 @@ __global__ void __launch_bounds__(256) phase_delay_f64_kernel(const PhaseParams 
 __global__ void __launch_bounds__(256)
     phase_delay_f32_kernel(const float *lm, const float *uvw, const float *freq, float2 *out,
                            float cst, long long nsrc, long long nrow, int nchan) {
-    // two consecutive elements (16 bytes) per thread when nchan is even, else one
-    const int per = (nchan % 2 == 0) ? 2 : 1;
-    const long long total = nsrc * nrow * nchan / per;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long e0 = i * per;
-        const long long sr = e0 / nchan;
-        const int f0 = (int)(e0 - sr * nchan);
-        const long long s = sr / nrow, r = sr - s * nrow;
+    const long long row_blocks = (nrow + kRowsPerBlock - 1) / kRowsPerBlock;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long blk = blockIdx.x; blk < nsrc * row_blocks; blk += gridDim.x) {
+        const long long s = blk / row_blocks;
+        const long long r0 = (blk - s * row_blocks) * kRowsPerBlock;
+        const long long r1 = min(nrow, r0 + kRowsPerBlock);
         const float l = lm[2 * s], m = lm[2 * s + 1];
         float n = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(l, l)), __fmul_rn(m, m));
         n = __fsub_rn(__fsqrt_rn(n < 0.0f ? 0.0f : n), 1.0f);
-        const float u = uvw[3 * r], v = uvw[3 * r + 1], w = uvw[3 * r + 2];
-        const float rp = __fmul_rn(
-            cst, __fadd_rn(__fadd_rn(__fmul_rn(l, u), __fmul_rn(m, v)), __fmul_rn(n, w)));
-        float sn0, cs0;
-        sincosf(__fmul_rn(rp, freq[f0]), &sn0, &cs0);
-        if (per == 2) {
-            float sn1, cs1;
-            sincosf(__fmul_rn(rp, freq[f0 + 1]), &sn1, &cs1);
-            reinterpret_cast<float4 *>(out)[i] = make_float4(cs0, sn0, cs1, sn1);
-        } else {
-            out[e0] = make_float2(cs0, sn0);
+        for (long long r = r0 + warp; r < r1; r += 8) {
+            const float u = uvw[3 * r], v = uvw[3 * r + 1], w = uvw[3 * r + 2];
+            const float rp = __fmul_rn(
+                cst, __fadd_rn(__fadd_rn(__fmul_rn(l, u), __fmul_rn(m, v)), __fmul_rn(n, w)));
+            float2 *o = out + (s * nrow + r) * nchan;
+            for (int f = lane; f < nchan; f += 32) {
+                float sn, cs;
+                sincosf(__fmul_rn(rp, freq[f]), &sn, &cs);
+                o[f] = make_float2(cs, sn);
+            }
         }
     }
 }
@@ -120,8 +125,8 @@ extern "C" int afr_phase_delay_f64(const double *lm, const double *uvw, const do
     p.nchan = (int)nchan;
     p.all_f32_coords = (lm_f32 && uvw_f32) ? 1 : 0;
     (void)chan_mode;  // every element takes its own sincos: both modes are exact
-    const long long total = nsrc * nrow * nchan;
-    phase_delay_f64_kernel<<<grid_for(total), 256, 0, stream>>>(p);
+    const long long blocks = nsrc * ((nrow + kRowsPerBlock - 1) / kRowsPerBlock);
+    phase_delay_f64_kernel<<<grid_for(blocks * 256), 256, 0, stream>>>(p);
     AFR_LAUNCH_OK();
     return 0;
 }
@@ -136,8 +141,8 @@ extern "C" int afr_phase_delay_f32(const float *lm, const float *uvw, const floa
     if (nsrc == 0 || nrow == 0 || nchan == 0) return 0;
     float cst = (float)(-kTwoPiOverC);
     if (convention == AFR_CASA) cst = -cst;
-    const long long total = nsrc * nrow * nchan;
-    phase_delay_f32_kernel<<<grid_for(total), 256, 0, stream>>>(lm, uvw, freq, (float2 *)out, cst,
+    const long long blocks = nsrc * ((nrow + kRowsPerBlock - 1) / kRowsPerBlock);
+    phase_delay_f32_kernel<<<grid_for(blocks * 256), 256, 0, stream>>>(lm, uvw, freq, (float2 *)out, cst,
                                                                nsrc, nrow, (int)nchan);
     AFR_LAUNCH_OK();
     return 0;

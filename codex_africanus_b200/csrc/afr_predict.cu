@@ -15,6 +15,8 @@
 //       f0+L, f0+L+32, ... so DDE gathers stay coalesced along chan, and the phasor
 //       advances by exp(i*phi*32*dnu) between a lane's channels.
 //   base_vis and the DIE product are applied by the same epilogue as predict_vis.
+#include <algorithm>
+
 #include "afr_dft.cuh"
 
 namespace afr {
@@ -277,6 +279,268 @@ __global__ void __launch_bounds__(128) fused_dde_kernel(const FusedParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// fused predict with DDEs, antenna-tiled (2x2 Jones, complex128, rows ordered by time)
+// ---------------------------------------------------------------------------
+// The gather kernel above re-reads two 64-byte Jones matrices per term (128 B/term of L2
+// traffic).  Here a CTA owns (one timestep, up to 256 rows of it, FT channels); per source it
+// stages E[s,t,:,f-tile] for ALL antennas once in shared memory (cp.async, one source ahead),
+// precombines A_p = E_p * B_s (africanus/rime/predict.py:103-117 re-associated:
+// E1 (K B) E2^H = K (E1 B) E2^H since K is a scalar), and every row then reads A_a1 and E_a2
+// from shared memory: each DDE element is fetched from L2/HBM once per ~256 rows instead of
+// once per row.  lane <-> row (so the phasor advances by a rotation along the thread's own
+// channel run), warp <-> (row group, run of 4 channels); shared-memory matrices are stored
+// [chan][antenna][64 B] with the 16-byte chunks XOR-swizzled by antenna so that lanes reading
+// consecutive antennas hit distinct banks.
+constexpr int kTileRowsMax = 512;  // rows per CTA = (16 / nck) * 32
+constexpr int kTileCHD = 4;      // channels per thread
+constexpr int kTileThreads = 512;
+
+struct TiledParams {
+    const double *lmn, *uvw, *freq;
+    const double *bright;  // (nsrc,nchan,4) complex
+    const int32_t *ant1, *ant2;
+    const int32_t *row_start;  // (ntime+1) first row of each timestep
+    const double *dde1, *dde2;
+    double *out;
+    double cst;
+    long long nsrc, nrow, ntime, nant;
+    int nchan;
+    int nck;      // channel runs per CTA (1 or 2): FT = nck * 4
+    int same_dde; // dde1 == dde2: stage one copy
+};
+
+__device__ __forceinline__ unsigned sw_off(int fl, int a, int na, int c) {
+    // byte offset of 16-byte chunk c of the matrix of (channel fl, antenna a)
+    return (unsigned)(((fl * na + a) << 6) + ((c ^ ((a >> 1) & 3)) << 4));
+}
+
+__device__ __forceinline__ void lds_mat(const unsigned char *base, int fl, int a, int na,
+                                        Cx<double> (&m)[4]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double2 v = *reinterpret_cast<const double2 *>(base + sw_off(fl, a, na, c));
+        m[c].re = v.x;
+        m[c].im = v.y;
+    }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kTileThreads, 1) fused_dde_tiled_kernel(const TiledParams p) {
+    using C = Cx<double>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nck = p.nck, ft = nck * kTileCHD;
+    const int na = (int)p.nant;
+    const int t = blockIdx.y;
+    const int f0 = blockIdx.z * ft;
+    const int tile_rows = (16 / p.nck) * 32;
+    const long long rbeg = p.row_start[t] + (long long)blockIdx.x * tile_rows;
+    const long long rend = min((long long)p.row_start[t + 1], rbeg + tile_rows);
+    if (rbeg >= rend) return;
+
+    // shared memory: E1 slots [2], (E2 slots [2] unless same), A, B slots [2], anchors, steps
+    const size_t mat_bytes = (size_t)ft * na * 64;
+    unsigned char *e1s = smem;                                   // [2][mat_bytes]
+    unsigned char *e2s = p.same_dde ? e1s : e1s + 2 * mat_bytes;  // [2][mat_bytes]
+    unsigned char *as = e2s + 2 * mat_bytes;                      // [mat_bytes]
+    unsigned char *bs = as + mat_bytes;                           // [2][ft*64]
+    C2<double> *anch = reinterpret_cast<C2<double> *>(bs + 2 * (size_t)ft * 64);  // [nck][tile_rows]
+    C2<double> *dstp = anch + kTileRowsMax;                                       // [tile_rows]
+    double *fq = reinterpret_cast<double *>(dstp + kTileRowsMax);                 // [ft]
+
+    // consumer role
+    const int ck = warp % nck;
+    const int row_local = (warp / nck) * 32 + lane;  // 16 warps / nck groups of 32 rows
+    const long long r = rbeg + row_local;
+    const bool row_ok = r < rend;
+    int a1 = 0, a2 = 0;
+    if (row_ok) {
+        a1 = p.ant1[r];
+        a2 = p.ant2[r];
+    }
+    // anchor role: thread tid < tile_rows owns row rbeg + tid
+    double pu = 0, pv = 0, pw = 0;
+    {
+        const int arow = tid < tile_rows ? tid : tid - tile_rows;
+        if (arow < tile_rows && rbeg + arow < rend) {
+            pu = p.uvw[3 * (rbeg + arow)];
+            pv = p.uvw[3 * (rbeg + arow) + 1];
+            pw = p.uvw[3 * (rbeg + arow) + 2];
+        }
+    }
+    double sl = p.lmn[0], sm = p.lmn[1], sn = p.lmn[2];  // coordinates of the current source
+    double dnu = 0.0;
+    if (p.nchan > 1) dnu = (p.freq[p.nchan - 1] - p.freq[0]) / (double)(p.nchan - 1);
+    const double nu0 = p.freq[min(f0, p.nchan - 1)];
+    if (EXACT)
+        for (int i = tid; i < ft; i += kTileThreads) fq[i] = p.freq[min(f0 + i, p.nchan - 1)];
+
+    C acc[kTileCHD][4];
+#pragma unroll
+    for (int j = 0; j < kTileCHD; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[j][c] = {0.0, 0.0};
+
+    const int items = na * ft;  // (antenna, channel) matrices per source
+    auto issue = [&](long long s) {
+        if (s < p.nsrc) {
+            const int slot = (int)(s & 1);
+            for (int idx = tid; idx < items; idx += kTileThreads) {
+                const int fl = idx / na, a = idx - fl * na;  // antenna fastest: conflict-free smem
+                const int f = f0 + fl;
+                const bool ok = f < p.nchan;
+                const long long g = (((s * p.ntime + t) * p.nant + a) * p.nchan + (ok ? f : 0)) * 8;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(
+                                     (unsigned)__cvta_generic_to_shared(e1s + slot * mat_bytes) +
+                                     sw_off(fl, a, na, c)),
+                                 "l"(p.dde1 + g + 2 * c), "r"(ok ? 16 : 0));
+                    if (!p.same_dde)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(
+                                         (unsigned)__cvta_generic_to_shared(e2s + slot * mat_bytes) +
+                                         sw_off(fl, a, na, c)),
+                                     "l"(p.dde2 + g + 2 * c), "r"(ok ? 16 : 0));
+                }
+            }
+            if (tid < ft * 4) {  // brightness of this source: ft matrices of 4 chunks
+                const int fl = tid >> 2, c = tid & 3;
+                const int f = f0 + fl;
+                const bool ok = f < p.nchan;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(
+                                 (unsigned)__cvta_generic_to_shared(bs + slot * (size_t)ft * 64 + tid * 16)),
+                             "l"(p.bright + ((s * p.nchan + (ok ? f : 0)) * 4 + c) * 2), "r"(ok ? 16 : 0));
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    issue(0);
+    for (long long s = 0; s < p.nsrc; ++s) {
+        const int slot = (int)(s & 1);
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();  // consume(s-1) finished everywhere; E(s), B(s) landed
+        issue(s + 1);
+        // ---- A_p = E1_p * B_s for every (antenna, channel) of the tile
+        const unsigned char *e1 = e1s + slot * mat_bytes;
+        const unsigned char *e2 = e2s + slot * mat_bytes;
+        for (int idx = tid; idx < items; idx += kTileThreads) {
+            const int fl = idx / na, a = idx - fl * na;
+            C b[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double2 v = *reinterpret_cast<const double2 *>(bs + slot * (size_t)ft * 64 + (fl * 4 + c) * 16);
+                b[c] = {v.x, v.y};
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // one output row of E*B at a time (register pressure)
+                const double2 v0 = *reinterpret_cast<const double2 *>(e1 + sw_off(fl, a, na, 2 * h));
+                const double2 v1 = *reinterpret_cast<const double2 *>(e1 + sw_off(fl, a, na, 2 * h + 1));
+                const C e0 = {v0.x, v0.y}, e1m = {v1.x, v1.y};
+                const C m0 = add(mul(e0, b[0]), mul(e1m, b[2]));
+                const C m1 = add(mul(e0, b[1]), mul(e1m, b[3]));
+                *reinterpret_cast<double2 *>(as + sw_off(fl, a, na, 2 * h)) = make_double2(m0.re, m0.im);
+                *reinterpret_cast<double2 *>(as + sw_off(fl, a, na, 2 * h + 1)) = make_double2(m1.re, m1.im);
+            }
+        }
+        // ---- phasor anchors for the rows of this CTA: thread tid < tile_rows computes the
+        // first-run anchor of row tid, thread tile_rows <= tid < 2*tile_rows its channel step
+        // (when the CTA has fewer than 2*tile_rows threads the first half does both)
+        {
+            const bool two_halves = 2 * tile_rows <= kTileThreads;
+            const int arow = tid < tile_rows ? tid : tid - tile_rows;
+            const bool do_z = tid < tile_rows;
+            const bool do_d = two_halves ? (tid >= tile_rows && tid < 2 * tile_rows) : do_z;
+            if (do_z || do_d) {
+                double phi = 0.0;
+                const bool live = rbeg + arow < rend;
+                if (live)
+                    phi = __dmul_rn(p.cst, phase_dot(sl, sm, sn, pu, pv, pw, false));
+                if (EXACT) {
+                    if (do_z) dstp[arow].re = phi;  // exact mode: one sincos per channel later
+                } else {
+                    if (do_z) anch[arow] = live ? cis_fast(__dmul_rn(phi, nu0)) : C2<double>{0.0, 0.0};
+                    if (do_d) dstp[arow] = live ? cis_fast(__dmul_rn(phi, dnu)) : C2<double>{0.0, 0.0};
+                }
+            }
+        }
+        // source coordinates for the next iteration (latency hidden behind consume)
+        if (s + 1 < p.nsrc) {
+            sl = p.lmn[3 * (s + 1)];
+            sm = p.lmn[3 * (s + 1) + 1];
+            sn = p.lmn[3 * (s + 1) + 2];
+        }
+        __syncthreads();  // A(s), anchors(s) visible
+        // ---- consume: V[r,f] += K * (A_a1 * E_a2^H)
+        if (row_ok) {
+            C2<double> z = anch[row_local];
+            const C2<double> d = dstp[row_local];
+            if (!EXACT && ck > 0) {  // run ck starts at z0 * d^(4*ck)
+                C2<double> D = d;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const double re = D.re * D.re - D.im * D.im;
+                    D.im = 2.0 * D.re * D.im;
+                    D.re = re;
+                }
+                for (int q = 0; q < ck; ++q) z = cmul(z, D);
+            }
+#pragma unroll
+            for (int j = 0; j < kTileCHD; ++j) {
+                const int fl = ck * kTileCHD + j;
+                if (EXACT) z = cis_fast(__dmul_rn(d.re, fq[fl]));
+                C em[4];
+                lds_mat(e2, fl, a2, na, em);
+                const C zz = {z.re, z.im};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {  // output rows of the 2x2 product, one at a time
+                    C a0, a1m;
+                    {
+                        const double2 v0 = *reinterpret_cast<const double2 *>(as + sw_off(fl, a1, na, 2 * h));
+                        const double2 v1 = *reinterpret_cast<const double2 *>(as + sw_off(fl, a1, na, 2 * h + 1));
+                        a0 = {v0.x, v0.y};
+                        a1m = {v1.x, v1.y};
+                    }
+                    const C m0 = add(mulc(a0, em[0]), mulc(a1m, em[1]));
+                    const C m1 = add(mulc(a0, em[2]), mulc(a1m, em[3]));
+                    acc[j][2 * h] = add(acc[j][2 * h], mul(zz, m0));
+                    acc[j][2 * h + 1] = add(acc[j][2 * h + 1], mul(zz, m1));
+                }
+                if (!EXACT) z = cmul(z, d);
+            }
+        }
+    }
+    if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < kTileCHD; ++j) {
+            const int f = f0 + ck * kTileCHD + j;
+            if (f < p.nchan) store_n<double, 4>(reinterpret_cast<C *>(p.out) + (r * p.nchan + f) * 4, acc[j]);
+        }
+    }
+}
+
+// row_start[t] = first row with time_index >= t (rows sorted by time); flags[0] |= 1 when
+// the rows are not sorted; flags[1] = max rows in one timestep
+__global__ void time_ranges_kernel(const int32_t *time_index, long long nrow, long long ntime,
+                                   int32_t *row_start, int *flags) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i + 1 < nrow && time_index[i + 1] < time_index[i]) atomicOr(&flags[0], 1);
+    if (i < nrow && (time_index[i] < 0 || time_index[i] >= ntime)) atomicOr(&flags[0], 2);
+    if (i <= ntime) {
+        long long lo = 0, hi = nrow;  // lower_bound(time_index, i)
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (time_index[mid] < i) lo = mid + 1; else hi = mid;
+        }
+        row_start[i] = (int32_t)lo;
+    }
+}
+__global__ void max_rows_kernel(const int32_t *row_start, long long ntime, int *flags) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < ntime) atomicMax(&flags[1], row_start[t + 1] - row_start[t]);
+}
+
 int grid_for(long long total, int threads) {
     long long blocks = (total + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
@@ -426,8 +690,74 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
         f.nant = nant;
         f.nchan = (int)nchan;
         f.ncorr = (int)ncorr;
-        rc = out_c64 ? launch_fused_dde<float>(f, jones_mode, exact, stream)
-                     : launch_fused_dde<double>(f, jones_mode, exact, stream);
+        bool done = false;
+        if (!out_c64 && jones_mode == AFR_JONES_2X2 && nsrc > 0) {
+            // antenna-tiled kernel: needs rows ordered by time and the tile in shared memory
+            Scratch rs, fl;
+            AFR_CUDA_OK(rs.alloc(sizeof(int32_t) * (size_t)(ntime + 1), stream));
+            AFR_CUDA_OK(fl.alloc(sizeof(int) * 2, stream));
+            AFR_CUDA_OK(cudaMemsetAsync(fl.ptr, 0, sizeof(int) * 2, stream));
+            const long long n = std::max<long long>(nrow, ntime + 1);
+            time_ranges_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(
+                time_index, nrow, ntime, (int32_t *)rs.ptr, (int *)fl.ptr);
+            AFR_LAUNCH_OK();
+            max_rows_kernel<<<(int)((ntime + 255) / 256), 256, 0, stream>>>((const int32_t *)rs.ptr,
+                                                                            ntime, (int *)fl.ptr);
+            AFR_LAUNCH_OK();
+            int hflags[2] = {0, 0};
+            AFR_CUDA_OK(cudaMemcpyAsync(hflags, fl.ptr, sizeof(hflags), cudaMemcpyDeviceToHost, stream));
+            AFR_CUDA_OK(cudaStreamSynchronize(stream));
+            const bool same = dde1 == dde2;
+            int nck = 2;
+            auto smem_for = [&](int k) {
+                const size_t mat = (size_t)k * kTileCHD * nant * 64;
+                return (same ? 3 : 5) * mat + 2 * (size_t)k * kTileCHD * 64 +
+                       2 * (size_t)kTileRowsMax * 16 + (size_t)k * kTileCHD * 8;
+            };
+            if (smem_for(nck) > 200 * 1024) nck = 1;
+            if (hflags[0] == 0 && hflags[1] > 0 && smem_for(nck) <= 200 * 1024) {
+                TiledParams tp{};
+                tp.lmn = (const double *)lmn.ptr;
+                tp.uvw = uvw;
+                tp.freq = freq;
+                tp.bright = (const double *)brightness;
+                tp.ant1 = antenna1;
+                tp.ant2 = antenna2;
+                tp.row_start = (const int32_t *)rs.ptr;
+                tp.dde1 = (const double *)dde1;
+                tp.dde2 = (const double *)dde2;
+                tp.out = (double *)out;
+                tp.cst = cst;
+                tp.nsrc = nsrc;
+                tp.nrow = nrow;
+                tp.ntime = ntime;
+                tp.nant = nant;
+                tp.nchan = (int)nchan;
+                tp.nck = nck;
+                tp.same_dde = same ? 1 : 0;
+                const int tile_rows = (16 / nck) * 32;
+                const int ft = nck * kTileCHD;
+                dim3 grid((unsigned)((hflags[1] + tile_rows - 1) / tile_rows), (unsigned)ntime,
+                          (unsigned)((nchan + ft - 1) / ft));
+                AFR_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "afr_predict_fused: grid too large");
+                const size_t smem = smem_for(nck);
+                // rows not covered by any timestep range cannot exist once the order check passed
+                if (exact) {
+                    AFR_CUDA_OK(cudaFuncSetAttribute(fused_dde_tiled_kernel<true>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    fused_dde_tiled_kernel<true><<<grid, kTileThreads, smem, stream>>>(tp);
+                } else {
+                    AFR_CUDA_OK(cudaFuncSetAttribute(fused_dde_tiled_kernel<false>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    fused_dde_tiled_kernel<false><<<grid, kTileThreads, smem, stream>>>(tp);
+                }
+                AFR_LAUNCH_OK();
+                done = true;
+            }
+        }
+        if (!done)
+            rc = out_c64 ? launch_fused_dde<float>(f, jones_mode, exact, stream)
+                         : launch_fused_dde<double>(f, jones_mode, exact, stream);
         if (rc) return rc;
     }
 
