@@ -405,3 +405,66 @@ def test_fused_predict_vs_oracle(b200, oracle):
                                               bvis.astype(c64), die.astype(c64))
             assert got.dtype == c64
             assert rel_l2(got.astype(np.complex128), ref) < 1e-5
+
+
+# ----------------------------------------------------------------------------- cross-kernel
+def test_fused_equals_unfused_composition_on_gpu(b200):
+    """Size-independent property at a size the CPU oracle cannot reach: the fused kernel must
+    equal the reference's own three-step composition (rime/examples/predict.py:107-134,490,
+    522-527) built from the OTHER kernels of this library: phase_delay -> einsum -> predict_vis.
+    64 antennas x 6 times (12096 rows), 128 channels, 40 sources, 2x2, DIE + DDE."""
+    import torch
+
+    rng = np.random.default_rng(123)
+    na, ntime, nchan, nsrc = 64, 6, 128, 40
+    a1, a2 = np.triu_indices(na, 1)
+    ant1, ant2 = np.tile(a1, ntime), np.tile(a2, ntime)
+    ti = np.repeat(np.arange(ntime), a1.size)
+    nrow = ti.size
+    dev = torch.device("cuda:0")
+
+    def T(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    def rc(shape, scale=1.0):
+        return scale * (rng.standard_normal(shape) + 1j * rng.standard_normal(shape))
+
+    uvw = T(rng.standard_normal((nrow, 3)) * 3000.0)
+    lm = T(rng.uniform(-0.02, 0.02, (nsrc, 2)))
+    freq = T(np.linspace(0.856e9, 1.712e9, nchan))
+    bright = T(rc((nsrc, nchan, 2, 2)))
+    dde = T(1.0 + rc((nsrc, ntime, na, nchan, 2, 2), 0.2))
+    dde_b = T(1.0 + rc((nsrc, ntime, na, nchan, 2, 2), 0.2))
+    die = T(1.0 + rc((ntime, na, nchan, 2, 2), 0.1))
+    bvis = T(rc((nrow, nchan, 2, 2)))
+    tiT, a1T, a2T = T(ti), T(ant1), T(ant2)
+    K = b200.rime.phase_delay(lm, uvw, freq)
+    coh = torch.einsum("srf,sfij->srfij", K, bright).contiguous()
+    for d1, d2 in ((None, None), (dde, dde), (dde, dde_b)):
+        ref = b200.rime.predict_vis(tiT, a1T, a2T, d1, coh, d2, die, bvis, die)
+        got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, tiT, a1T, a2T, d1, d2, die, bvis, die)
+        assert_c128_close(got.cpu().numpy(), ref.cpu().numpy())
+    # rows not ordered by time take the gather kernel; same answer
+    perm = torch.from_numpy(rng.permutation(nrow)).to(dev)
+    ref = b200.rime.predict_vis(tiT, a1T, a2T, dde, coh, dde_b, die, bvis, die)
+    got = b200.rime.fused_predict_vis(lm, uvw[perm], freq, bright, tiT[perm], a1T[perm], a2T[perm],
+                                      dde, dde_b, die, bvis[perm], die)
+    assert_c128_close(got.cpu().numpy(), ref[perm].cpu().numpy())
+
+
+def test_phasor_stream_kernel_variants_agree(b200, monkeypatch):
+    """The warp-specialised and the single-role phasor-stream kernels are two schedules of
+    the same arithmetic: forcing either one (AFR_WS) must give the same visibilities."""
+    rng = np.random.default_rng(77)
+    nsrc, nrow, nchan = 300, 1000, 96
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    uvw = rng.standard_normal((nrow, 3)) * 3000.0
+    freq = np.linspace(0.856e9, 1.712e9, nchan)
+    for ncorr in (1, 2, 4):
+        image = rng.standard_normal((nsrc, nchan, ncorr)) + 1j * rng.standard_normal((nsrc, nchan, ncorr))
+        out = {}
+        for ws in ("0", "1"):
+            monkeypatch.setenv("AFR_WS", ws)
+            out[ws] = b200.dft.im_to_vis(image, uvw, lm, freq)
+        monkeypatch.delenv("AFR_WS")
+        assert_c128_close(out["1"], out["0"], rtol=1e-12)

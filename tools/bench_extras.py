@@ -95,6 +95,27 @@ def run(dev, fp64_peak):
                                               die1_jones=d_die, die2_jones=d_die))
     compute_entry("fused_point_predict_die_c128_cfg1", t, terms1, 39, fp64_peak)
 
+    # ---- configs[3] block: SKA-Mid 197 antennas (19306 rows = one timestep), 4096 chan, 500 src
+    na4, nchan4, nsrc4 = 197, 4096, 500
+    uvw4, tidx4, a14, a24 = synth.uvw_tracks(na4, 1, rng, ntime_total=1000, max_radius=150e3)
+    freq4 = synth.frequencies(nchan4)
+    lm4 = synth.sky_lm(nsrc4, rng)
+    b4 = synth.brightness_2x2(nsrc4, nchan4, rng, freq4)
+    d_uvw4, d_f4, d_lm4, d_b4 = T(uvw4), T(freq4), T(lm4), T(b4)
+    d_t4, d_a14, d_a24 = T(tidx4), T(a14), T(a24)
+    terms4 = float(nsrc4) * uvw4.shape[0] * nchan4
+    t = _timed(lambda: rime.fused_predict_vis(d_lm4, d_uvw4, d_f4, d_b4, d_t4, d_a14, d_a24))
+    compute_entry("fused_point_predict_c128_cfg4_block", t, terms4, 39, fp64_peak,
+                  "one row block (1 timestep, 19306 rows) x 4096 chan x 500 sources of configs[3]")
+    del d_b4
+
+    # ---- pure store reference for the phase_delay number: torch fill of the same bytes
+    fill = torch.empty(2 << 30, dtype=torch.uint8, device=dev)
+    t = _timed(lambda: fill.fill_(1))
+    res["device_fill_reference"] = {"GB_per_s": fill.numel() / t / 1e9, "ms": 1e3 * t,
+                                    "note": "torch fill_ of 2 GiB: write-only HBM rate on this GPU"}
+    del fill
+
     # ---- un-fused building blocks on a 10-timestep slice (memory-bound by construction)
     rows10 = 10 * (uvw.shape[0] // ntime)
     K = rime.phase_delay(d_lm1, d_uvw[:rows10], d_f1)
