@@ -54,12 +54,17 @@ inline int sm_count() {
     return n > 0 ? n : 148;
 }
 
+// keep freed scratch in the device's default memory pool instead of returning it to the
+// driver at every synchronisation (the default release threshold is 0)
+void retain_pool_memory();
+
 // stream-ordered scratch allocation
 struct Scratch {
     void *ptr = nullptr;
     cudaStream_t stream = nullptr;
     cudaError_t alloc(size_t bytes, cudaStream_t s) {
         stream = s;
+        retain_pool_memory();
         return cudaMallocAsync(&ptr, bytes ? bytes : 16, s);
     }
     ~Scratch() {

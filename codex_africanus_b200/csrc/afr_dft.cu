@@ -802,10 +802,20 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     constexpr int NV = NCORR * (WC ? 2 : 1);
     constexpr int SZ = (int)sizeof(ACC);
     constexpr int NT = NW * 32;
-    // channel runs per CTA
+    const char *ws_env = getenv("AFR_WS");
+    // Which FP64 variants run warp-specialised (16 consumer + 4 producer warps) was decided
+    // by measurement (tools/ws_sweep.py, B200): the forward (complex-accumulator) kernels
+    // gain 5-10 %, the adjoint kernels (64 real accumulators per thread) lose.  AFR_WS=0 / 1
+    // forces the choice.
+    constexpr bool kPreferWS = !ADJ;
+    const bool use_ws = (sizeof(ACC) == 8) && (ws_env ? atoi(ws_env) != 0 : kPreferWS);
+    // channel runs per CTA: the single-role kernel keeps nck <= NW/2 so that every thread
+    // owns an (x,y) pair per tile; dedicated producers do not need that, and anchors are
+    // cheaper per term the more channels a CTA covers (measured +9 % at 16 runs vs 8)
     const int runs = (p.nchan + CH - 1) / CH;
+    const int nck_max = use_ws ? NW : NW / 2;
     int nck = 1;
-    while (nck < runs && nck < NW / 2) nck *= 2;
+    while (nck < runs && nck < nck_max) nck *= 2;
     p.nck = nck;
     p.debug = getenv("AFR_DEBUG") ? atoi(getenv("AFR_DEBUG")) : 0;
     const int xgw = (NW / nck) * 32;
@@ -828,12 +838,6 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     // y items per tile: as many (even, <= 8) as fit double-buffered in shared memory and in
     // kMaxChunks cp.async granules per thread
     const size_t per_y = (size_t)(nck + 1) * xgw * sizeof(C2<ACC>) + (size_t)ft * NV * SZ;
-    const char *ws_env = getenv("AFR_WS");
-    // Which FP64 variants run warp-specialised (16 consumer + 4 producer warps) was decided
-    // by measurement (tools/ws_sweep.py, B200): the forward kernels with one correlation or a
-    // complex W, and the 4-correlation real adjoint.  AFR_WS=0 / 1 forces the choice.
-    constexpr bool kPreferWS = (!ADJ && (NCORR == 1 || WC)) || (ADJ && !WC && NCORR == 4);
-    const bool use_ws = (sizeof(ACC) == 8) && (ws_env ? atoi(ws_env) != 0 : kPreferWS);
     // granules one thread may have in flight: 8 per thread of the whole CTA, or 16 per
     // producer thread of the warp-specialised kernel
     const long long max_chunks = use_ws ? 16LL * kProducerWarps * 32 : (long long)kMaxChunks * NT;

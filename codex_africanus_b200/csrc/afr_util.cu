@@ -10,6 +10,20 @@ namespace afr {
 static thread_local std::string g_last_error;
 static std::atomic<unsigned long long> g_launches{0};
 
+void retain_pool_memory() {
+    static std::atomic<unsigned> done_mask{0};  // one bit per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return;
+    const unsigned bit = 1u << dev;
+    if (done_mask.load(std::memory_order_relaxed) & bit) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    done_mask.fetch_or(bit, std::memory_order_relaxed);
+}
+
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 void set_error(const std::string &msg) { g_last_error = msg; }
