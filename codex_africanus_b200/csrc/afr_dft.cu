@@ -808,6 +808,8 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     // gain 5-10 %, the adjoint kernels (64 real accumulators per thread) lose.  AFR_WS=0 / 1
     // forces the choice.
     constexpr bool kPreferWS = !ADJ;
+    // FP32 variants gain nothing from it (measured 3.10 vs 3.07 Tterm/s): they are bound by
+    // the register-file bandwidth of three-operand FFMAs, not by the anchor work
     const bool use_ws = (sizeof(ACC) == 8) && (ws_env ? atoi(ws_env) != 0 : kPreferWS);
     // channel runs per CTA: the single-role kernel keeps nck <= NW/2 so that every thread
     // owns an (x,y) pair per tile; dedicated producers do not need that, and anchors are
