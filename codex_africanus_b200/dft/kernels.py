@@ -138,10 +138,13 @@ def vis_to_im(vis, uvw, lm, frequency, flags, convention="fourier", dtype=None):
         d_uvw = pl.to_device(uvw, np.float64, device)
         d_lm = pl.to_device(lm, np.float64, device)
         d_freq = pl.to_device(frequency, np.float64, device)
+        # nothing flagged (the common case for simulated data): skip the flag path entirely
         if pl.is_torch(flags):
-            d_flags = (flags != 0).to(device=device, dtype=torch.uint8).contiguous()
+            any_flag = bool((flags != 0).any().item()) if flags.numel() else False
+            d_flags = (flags != 0).to(device=device, dtype=torch.uint8).contiguous() if any_flag else None
         else:
-            d_flags = pl.to_device(np.asarray(flags) != 0, np.uint8, device)
+            fl = np.asarray(flags) != 0
+            d_flags = pl.to_device(fl, np.uint8, device) if fl.any() else None
         d_out = pl.empty_device((nsrc, nchan, ncorr), out_dtype, device)
         pl.call("afr_vis_to_im", device, pl.ptr(d_vis), int(vis_complex), pl.ptr(d_uvw),
                 pl.ptr(d_lm), pl.ptr(d_freq), pl.ptr(d_flags), nsrc, nrow, nchan, ncorr, sign,
