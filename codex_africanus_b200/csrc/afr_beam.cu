@@ -63,8 +63,19 @@ struct BeamParams {
     int ncorr, coff;
 };
 
-__device__ __forceinline__ double habs(double re, double im) { return hypot(re, im); }
-__device__ __forceinline__ float habs(float re, float im) { return hypotf(re, im); }
+// |re + i im| as the reference's np.abs (hypot).  hypot's overflow/underflow guards cost
+// ~10x a square root; they only matter when re^2 + im^2 leaves the normal range, so take the
+// direct sqrt (correctly rounded sqrt of a 1-ulp sum: within 1 ulp of hypot) inside it.
+__device__ __forceinline__ double habs(double re, double im) {
+    const double t = fma(re, re, im * im);
+    if (t > 1e-290 && t < 1e290) return sqrt(t);
+    return hypot(re, im);
+}
+__device__ __forceinline__ float habs(float re, float im) {
+    const float t = fmaf(re, re, im * im);
+    if (t > 1e-30f && t < 1e30f) return sqrtf(t);
+    return hypotf(re, im);
+}
 
 template <typename T, int NC>
 __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) {

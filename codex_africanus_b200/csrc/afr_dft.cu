@@ -56,7 +56,6 @@ struct DftParams {
     int fast;         // 1: W rows are contiguous and copied by cp.async granules
     int granule;      // 4, 8 or 16 bytes
     int row_chunks_log2;  // log2(granules per W tile row)
-    int debug;            // development only (AFR_DEBUG): 1 skip produce after tile 0, 2 skip staging
 };
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) {
@@ -389,15 +388,13 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
             if (t > 0) apply_flags(t);
             __syncthreads();  // W(t), y(t+1), anchors(t) visible; buffers of tile t-1 free
             issue_yc(t + 2);
-            if (!(p.debug & 2)) issue_w(t + 1);
+            issue_w(t + 1);
             cp_async_commit();
             if (!p.fast && t + 1 < ntiles) stage_tile_slow(t + 1);
             // consume(t) and produce(t+1) are independent: alternate their order between the
             // warps of a scheduler so the latency-bound anchor math of one warp overlaps the
             // FP64-dense rotation loop of its neighbours
-            if (p.debug & 1) {
-                consume_tile(t);
-            } else if ((warp >> 2) & 1) {
+            if ((warp >> 2) & 1) {
                 produce_tile(t + 1);
                 consume_tile(t);
             } else {
@@ -819,7 +816,6 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     int nck = 1;
     while (nck < runs && nck < nck_max) nck *= 2;
     p.nck = nck;
-    p.debug = getenv("AFR_DEBUG") ? atoi(getenv("AFR_DEBUG")) : 0;
     const int xgw = (NW / nck) * 32;
     const int ft = nck * CH;
     const long long gx = (p.nx + xgw - 1) / xgw;
