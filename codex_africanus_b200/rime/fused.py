@@ -19,6 +19,9 @@ from .. import _lib
 from .. import _plumbing as pl
 from .predict import normalise_indices, predict_checks
 
+# output bytes above which the numpy path streams row blocks back while computing
+_ROW_BLOCK_BYTES = 512 << 20
+
 
 def fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
                       dde1_jones=None, dde2_jones=None, die1_jones=None, base_vis=None,
@@ -61,16 +64,61 @@ def fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, ante
                   dde2_jones, die1_jones, base_vis, die2_jones)
     device = pl.pick_device(*everything)
     as_torch = pl.wants_torch(*everything)
+    chan_mode = pl.channel_mode(frequency)
+    c64 = int(out_dtype == np.complex64)
     with torch.cuda.device(device):
         f64 = np.float64
         d_lm, d_uvw, d_f = (pl.to_device(a, f64, device) for a in (lm, uvw, frequency))
         d_b = pl.to_device(brightness, out_dtype, device)
-        dj = [None if a is None else pl.to_device(a, out_dtype, device)
-              for a in (dde1_jones, dde2_jones, die1_jones, base_vis, die2_jones)]
+        d_dde1, d_dde2, d_die1, d_die2 = (
+            None if a is None else pl.to_device(a, out_dtype, device)
+            for a in (dde1_jones, dde2_jones, die1_jones, die2_jones))
+        if dde1_jones is dde2_jones:
+            d_dde2 = d_dde1  # one upload; also lets the kernel stage a single copy per tile
         ti, a1, a2 = normalise_indices(time_index, antenna1, antenna2, device)
-        d_out = pl.empty_device((nrow, nchan) + tuple(corr_shape), out_dtype, device)
-        pl.call("afr_predict_fused", device, pl.ptr(d_lm), pl.ptr(d_uvw), pl.ptr(d_f),
-                pl.ptr(d_b), pl.ptr(ti), pl.ptr(a1), pl.ptr(a2), *(pl.ptr(x) for x in dj),
-                nsrc, nrow, ntime, nant, nchan, ncorr, mode, sign, pl.channel_mode(frequency),
-                int(out_dtype == np.complex64), pl.ptr(d_out), pl.stream_ptr(device))
-        return d_out if as_torch else pl.to_host(d_out)
+        out_shape = (nrow, nchan) + tuple(corr_shape)
+
+        def launch(r0, r1, d_bvis, d_out):
+            pl.call("afr_predict_fused", device, pl.ptr(d_lm), pl.ptr(d_uvw[r0:r1]), pl.ptr(d_f),
+                    pl.ptr(d_b), pl.ptr(ti[r0:r1]), pl.ptr(a1[r0:r1]), pl.ptr(a2[r0:r1]),
+                    pl.ptr(d_dde1), pl.ptr(d_dde2), pl.ptr(d_die1), pl.ptr(d_bvis), pl.ptr(d_die2),
+                    nsrc, r1 - r0, ntime, nant, nchan, ncorr, mode, sign, chan_mode, c64,
+                    pl.ptr(d_out), pl.stream_ptr(device))
+
+        row_bytes = max(1, nchan * ncorr * out_dtype.itemsize)
+        if as_torch or nrow * row_bytes <= _ROW_BLOCK_BYTES or nrow == 0:
+            d_bvis = None if base_vis is None else pl.to_device(base_vis, out_dtype, device)
+            d_out = pl.empty_device(out_shape, out_dtype, device)
+            if nrow:
+                launch(0, nrow, d_bvis, d_out)
+            return d_out if as_torch else pl.to_host(d_out)
+
+        # numpy path, large output: rows are independent, so stream row blocks -- the block's
+        # base_vis goes up and its visibilities come back on a copy stream while the next
+        # block computes (the reference's own answer to configs-3-sized outputs is row
+        # chunking, africanus/rime/dask_predict.py:667-726)
+        block = max(1024, _ROW_BLOCK_BYTES // row_bytes)
+        h_out = pl.empty_pinned(out_shape, out_dtype)
+        compute = torch.cuda.current_stream(device)
+        copier = pl.side_stream(device)
+        bufs = [pl.empty_device((min(block, nrow), nchan) + tuple(corr_shape), out_dtype, device)
+                for _ in range(2)]
+        done = [None, None]
+        bv = None if base_vis is None else np.asarray(base_vis)
+        for i, r0 in enumerate(range(0, nrow, block)):
+            r1 = min(nrow, r0 + block)
+            buf = bufs[i & 1][: r1 - r0]
+            if done[i & 1] is not None:
+                compute.wait_event(done[i & 1])  # the copy out of this buffer has finished
+            d_bvis = None if bv is None else pl.to_device(bv[r0:r1], out_dtype, device)
+            launch(r0, r1, d_bvis, buf)
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            copier.wait_event(ev)
+            with torch.cuda.stream(copier):
+                h_out[r0:r1].copy_(buf, non_blocking=True)
+                done[i & 1] = torch.cuda.Event()
+                done[i & 1].record(copier)
+        copier.synchronize()
+        compute.synchronize()
+        return h_out.numpy()

@@ -468,3 +468,42 @@ def test_phasor_stream_kernel_variants_agree(b200, monkeypatch):
             out[ws] = b200.dft.im_to_vis(image, uvw, lm, freq)
         monkeypatch.delenv("AFR_WS")
         assert_c128_close(out["1"], out["0"], rtol=1e-12)
+
+
+def test_row_block_streaming_paths(b200, oracle, monkeypatch):
+    """numpy inputs with a large output are computed in row blocks whose results stream back
+    on a copy stream; force tiny blocks and compare with the oracle (rows are independent)."""
+    import codex_africanus_b200.dft.kernels as dk
+    import codex_africanus_b200.rime.fused as fu
+
+    rng = np.random.default_rng(19)
+    na, ntime, nchan, nsrc = 9, 11, 24, 7
+    a1, a2 = np.triu_indices(na, 1)
+    ant1, ant2 = np.tile(a1, ntime), np.tile(a2, ntime)
+    ti = np.repeat(np.arange(ntime), a1.size) + 2
+    nrow = ti.size
+    uvw = rng.standard_normal((nrow, 3)) * 2000.0
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    freq = np.linspace(0.856e9, 1.712e9, nchan)
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    image = rng.standard_normal((nsrc, nchan, 2))
+    bright = rc((nsrc, nchan, 2, 2))
+    dde = 1.0 + 0.2 * rc((nsrc, ntime, na, nchan, 2, 2))
+    die = 1.0 + 0.1 * rc((ntime, na, nchan, 2, 2))
+    bvis = rc((nrow, nchan, 2, 2))
+    monkeypatch.setattr(dk, "_ROW_BLOCK_BYTES", 1)   # -> minimum block of 4096 rows > nrow: 1 block
+    assert_c128_close(b200.dft.im_to_vis(image, uvw, lm, freq), oracle.im_to_vis(image, uvw, lm, freq))
+    monkeypatch.setattr(fu, "_ROW_BLOCK_BYTES", 100 * nchan * 4 * 16)  # 100-row blocks (min 1024)
+    ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die)
+    got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die)
+    assert_c128_close(got, ref)
+    # genuinely multi-block: shrink the floor as well
+    real_max = max
+    monkeypatch.setattr(fu, "max", lambda a, b: real_max(37, b) if a == 1024 else real_max(a, b), raising=False)
+    got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die)
+    assert_c128_close(got, ref)
+    got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2)
+    assert_c128_close(got, oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2))
