@@ -56,6 +56,7 @@ struct DftParams {
     int fast;         // 1: W rows are contiguous and copied by cp.async granules
     int granule;      // 4, 8 or 16 bytes
     int row_chunks_log2;  // log2(granules per W tile row)
+    int arrive_all;       // every consumer lane arrives on the "empty" mbarrier (AFR_SANITIZE=1)
 };
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) {
@@ -499,8 +500,11 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
     if (tid == 0) {
         mbar_init(&bars[0], NTP);
         mbar_init(&bars[1], NTP);
-        mbar_init(&bars[2], NWC);
-        mbar_init(&bars[3], NWC);
+        // one elected lane per consumer warp releases a buffer (after __syncwarp); with
+        // AFR_SANITIZE=1 every lane arrives instead, which compute-sanitizer's racecheck can
+        // follow (it does not model the warp-elected release and reports false hazards)
+        mbar_init(&bars[2], p.arrive_all ? NWC * 32 : NWC);
+        mbar_init(&bars[3], p.arrive_all ? NWC * 32 : NWC);
     }
     if (EXACT)
         for (int i = tid; i < ft; i += blockDim.x) fq[i] = p.freq[min(cta_f0 + i, p.nchan - 1)];
@@ -701,7 +705,7 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[2 + b]);  // this warp is done with buffer b
+        if (p.arrive_all || lane == 0) mbar_arrive(&bars[2 + b]);  // done with buffer b
     }
 
     if (x < p.nx) {
@@ -816,6 +820,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     int nck = 1;
     while (nck < runs && nck < nck_max) nck *= 2;
     p.nck = nck;
+    p.arrive_all = (getenv("AFR_SANITIZE") && atoi(getenv("AFR_SANITIZE")) != 0) ? 1 : 0;
     const int xgw = (NW / nck) * 32;
     const int ft = nck * CH;
     const long long gx = (p.nx + xgw - 1) / xgw;

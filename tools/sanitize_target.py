@@ -1,0 +1,34 @@
+"""Small end-to-end calls of every kernel for compute-sanitizer (memcheck / racecheck)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from codex_africanus_b200 import dft, rime
+rng = np.random.default_rng(1)
+na, ntime, nchan, nsrc = 6, 3, 40, 19
+a1, a2 = np.triu_indices(na, 1)
+ant1, ant2 = np.tile(a1, ntime), np.tile(a2, ntime)
+ti = np.repeat(np.arange(ntime), a1.size)
+nrow = ti.size
+uvw = rng.standard_normal((nrow, 3)) * 2000.0
+lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+freq = np.linspace(0.856e9, 1.712e9, nchan)
+rc = lambda shape: rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+for ncorr in (1, 2, 3):
+    img = rng.standard_normal((nsrc, nchan, ncorr))
+    v = dft.im_to_vis(img, uvw, lm, freq)
+    v = dft.im_to_vis(img + 1j * img, uvw, lm, freq)
+    fl = rng.random(v.shape) < 0.1
+    dft.vis_to_im(v, uvw, lm, freq, fl)
+    dft.vis_to_im(v, uvw, lm, freq, fl, dtype=np.float32)
+    dft.im_to_vis(img, uvw, lm, freq, dtype=np.complex64)
+dft.im_to_vis(img, uvw, lm, np.sort(rng.uniform(1e9, 2e9, nchan)))
+bright = rc((nsrc, nchan, 2, 2)); dde = rc((nsrc, ntime, na, nchan, 2, 2)); die = rc((ntime, na, nchan, 2, 2))
+rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2)
+rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, None, die)
+rime.fused_predict_vis(lm, uvw, freq, bright[..., 0], ti, ant1, ant2, dde[..., 0], dde[..., 0])
+K = rime.phase_delay(lm, uvw, freq)
+rime.predict_vis(ti, ant1, ant2, dde, np.einsum("srf,sfij->srfij", K, bright), dde, die, None, die)
+beam = rc((9, 9, 5, 2, 2))
+rime.beam_cube_dde(beam, np.array([[-0.03, 0.03], [-0.03, 0.03]]), np.linspace(0.8e9, 1.8e9, 5), lm,
+                   rng.uniform(-1, 1, (ntime, na)), np.zeros((ntime, na, nchan, 2)), np.ones((na, nchan, 2)), freq)
+print("sanitize target done")
