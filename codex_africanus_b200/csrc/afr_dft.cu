@@ -123,6 +123,98 @@ __device__ __forceinline__ void accumulate(ACC (&are)[NCORR], ACC (&aim)[ADJ ? 1
     }
 }
 
+// Anchors of the nck channel runs of one (x, y) pair: a_k = a * D^k, written to
+// anch[k * stride].  The chain across runs uses the same three-term form as the channels
+// inside a run (a_{k+1} = 2 Re(D) a_k - a_{k-1}): half the FP64 instructions and half the
+// dependent latency of a complex multiply per run; <= 16 steps, error < 3e-14.
+template <typename ACC>
+__device__ __forceinline__ void store_run_anchors(C2<ACC> *anch, int nck, int stride, C2<double> a,
+                                                  const C2<double> D) {
+    auto put = [&](const C2<double> v) {
+        C2<ACC> t;
+        t.re = (ACC)v.re;
+        t.im = (ACC)v.im;
+        *anch = t;
+        anch += stride;
+    };
+    put(a);
+    if (nck == 1) return;  // nck is a power of two
+    C2<double> a1 = cmul(a, D);
+    put(a1);
+    const double c2 = D.re + D.re;
+#pragma unroll 2
+    for (int k = 2; k < nck; k += 2) {
+        C2<double> a2, a3;
+        a2.re = fma(c2, a1.re, -a.re);
+        a2.im = fma(c2, a1.im, -a.im);
+        a3.re = fma(c2, a2.re, -a1.re);
+        a3.im = fma(c2, a2.im, -a1.im);
+        put(a2);
+        put(a3);
+        a = a2;
+        a1 = a3;
+    }
+}
+
+// exp(i*phi*nu0), exp(i*phi*dnu) and the run step D = d^CH (repeated squaring) of one pair
+template <int CH>
+__device__ __forceinline__ void pair_anchors(double phi, double nu0, double dnu, bool need_D,
+                                             C2<double> &a, C2<double> &d, C2<double> &D) {
+    a = cis_fast(__dmul_rn(phi, nu0));
+    d = cis_fast(__dmul_rn(phi, dnu));
+    D = d;
+    if (need_D) {
+#pragma unroll
+        for (int q = 1; q < CH; q *= 2) {
+            const double re = D.re * D.re - D.im * D.im;
+            D.im = 2.0 * D.re * D.im;
+            D.re = re;
+        }
+    }
+}
+
+// One channel run of one (x, y) pair: acc[j] (+)= z_j * W[j], z_j = z0 * d^j, j < CH.
+//
+// FP64: the phasor advances by the THREE-TERM form of the rotation recurrence,
+//     z_{j+1} = (2 Re d) z_j - z_{j-1}          (2 DFMA per channel instead of 2 DMUL + 2 DFMA),
+// started from the two anchors z_0 (exact sincos) and z_1 = z_0 * d, and restarted at every
+// run (CH <= 32 channels).  Rounding of the coefficient perturbs z_j by at most
+// eps * (|U'_{j-1}| + |U'_{j-2}|) <= (2/3) j^3 eps (U = Chebyshev polynomials of the 2nd
+// kind), injected roundings by j^2/2 eps; measured over 2e7 steps incl. d -> 0 and d -> pi
+// the worst error after 32 channels is 1.3e-13 (oracle/../tests: uniform-vs-exact goldens),
+// three orders below the 1e-10 gate.  FP32 keeps the plain rotation (k eps growth): the
+// three-term form costs ~1e3 eps_32 = 6e-5, above the 1e-5 gate.
+template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int G>
+__device__ __forceinline__ void consume_run(ACC (&are)[CH][NCORR], ACC (&aim)[CH][ADJ ? 1 : NCORR],
+                                            C2<ACC> z, const C2<ACC> d, const ACC *wrow) {
+    constexpr int NV = NCORR * (WC ? 2 : 1);
+    constexpr bool kThreeTerm = sizeof(ACC) == 8 && CH > 2;
+    C2<ACC> zp = z;  // z_{j-1}
+    const ACC c2 = d.re + d.re;
+#pragma unroll
+    for (int j = 0; j < CH; j += G) {
+        ACC wv[G * NV];
+        load_vec<G * NV>(wrow + j * NV, wv);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            accumulate<NCORR, WC, ADJ, ACC>(are[j + g], aim[j + g], z, wv + g * NV);
+            if (j + g + 1 < CH) {
+                if (!kThreeTerm || j + g == 0) {
+                    const C2<ACC> zn = cmul(z, d);
+                    zp = z;
+                    z = zn;
+                } else {
+                    C2<ACC> zn;
+                    zn.re = fma(c2, z.re, -zp.re);
+                    zn.im = fma(c2, z.im, -zp.im);
+                    zp = z;
+                    z = zn;
+                }
+            }
+        }
+    }
+}
+
 template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NW, bool EXACT>
 __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftParams p) {
     constexpr int NT = NW * 32;
@@ -296,30 +388,12 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
                 phis[yl * xgw + px_local] = phi;
             } else {
                 C2<double> a = {0.0, 0.0}, d = {0.0, 0.0}, D = {1.0, 0.0};
-                if (live) {
-                    a = cis_fast(__dmul_rn(phi, nu0));
-                    d = cis_fast(__dmul_rn(phi, dnu));
-                    if (nck > 1) {  // D = d^CH by repeated squaring
-                        D = d;
-#pragma unroll
-                        for (int q = 1; q < CH; q *= 2) {
-                            const double re = D.re * D.re - D.im * D.im;
-                            D.im = 2.0 * D.re * D.im;
-                            D.re = re;
-                        }
-                    }
-                }
+                if (live) pair_anchors<CH>(phi, nu0, dnu, nck > 1, a, d, D);
                 CA dd;
                 dd.re = (ACC)d.re;
                 dd.im = (ACC)d.im;
                 dstp[yl * xgw + px_local] = dd;
-                for (int k = 0; k < nck; ++k) {
-                    CA aa;
-                    aa.re = (ACC)a.re;
-                    aa.im = (ACC)a.im;
-                    anch[(yl * nck + k) * xgw + px_local] = aa;
-                    a = cmul(a, D);
-                }
+                store_run_anchors<ACC>(anch + (size_t)yl * nck * xgw + px_local, nck, xgw, a, D);
             }
         }
     };
@@ -356,19 +430,10 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
             // file bandwidth), one with a reused operand every 2 -- measured, see DESIGN.md.
 #pragma unroll 1
             for (int yl = 0; yl < yt; ++yl) {
-                CA z = anch[(yl * nck + ck) * xgw + x_local];
+                const CA z = anch[(yl * nck + ck) * xgw + x_local];
                 const CA d = dstp[yl * xgw + x_local];
-                const ACC *wrow = wt + (size_t)(yl * ft + fo) * NV;
-#pragma unroll
-                for (int j = 0; j < CH; j += G) {
-                    ACC wv[G * NV];
-                    load_vec<G * NV>(wrow + j * NV, wv);
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        accumulate<NCORR, WC, ADJ, ACC>(are[j + g], aim[j + g], z, wv + g * NV);
-                        if (j + g + 1 < CH) z = cmul(z, d);
-                    }
-                }
+                consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, z, d,
+                                                        wt + (size_t)(yl * ft + fo) * NV);
             }
         }
     };
@@ -512,19 +577,33 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
 
     if (warp >= NWC) {
         // =============================== PRODUCERS ===============================
+        // One producer warp per SM sub-partition shares the issue port with four consumer
+        // warps, and its work is a chain of dependent instructions: every instruction it does
+        // not execute is latency the consumers do not wait for (ncu: the first version spent
+        // 1300 warp-instructions per tile, 80 % of them integer, and the consumers idled 16 %
+        // of the time).  Hence: owner coordinates live in registers when a thread always
+        // serves the same owner, tile-pair indices are shifts (xgw is a power of two), shared
+        // memory addresses advance by a constant, and two pairs are in flight per iteration.
         if (PREGS > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PREGS > 0 ? PREGS : 24));
         const int ptid = tid - NWC * 32;
         const bool f32dot = p.f32dot != 0;
         const int valid_ch = min(ft, p.nchan - cta_f0);
-        const int px_local = ptid % xgw;
-        const int py0 = ptid / xgw;
-        const int pystep = NTP / xgw > 0 ? NTP / xgw : 1;
-        // owners handled by this thread: px_local, px_local + NTP, ... (when xgw > NTP)
+        const int lxgw = 31 - __clz(xgw);
+        const int npairs = yt << lxgw;  // (y, owner) pairs of a tile, y-major
+        const bool fixed_owner = xgw <= NTP;  // NTP % xgw == 0: pair q + NTP has the owner of q
+        auto load_owner = [&](int xo, double &x0, double &x1, double &x2) {
+            long long pxi = cta_x0 + xo;
+            if (pxi >= p.nx) pxi = p.nx - 1;
+            x0 = p.xc[3 * pxi], x1 = p.xc[3 * pxi + 1], x2 = p.xc[3 * pxi + 2];
+        };
+        double ox0, ox1, ox2;
+        load_owner(ptid & (xgw - 1), ox0, ox1, ox2);
         double dnu = 0.0, nu0 = 0.0;
         if (!EXACT) {
             if (p.nchan > 1) dnu = (p.freq[p.nchan - 1] - p.freq[0]) / (double)(p.nchan - 1);
             nu0 = p.freq[cta_f0];
         }
+        const bool need_D = nck > 1;
         const int g = p.granule, rcl = p.row_chunks_log2;
         const int total_chunks = yt << rcl;
         const int valid_bytes = valid_ch * NV * SZ;
@@ -533,8 +612,8 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
 
         for (int t = 0; t < ntiles; ++t) {
             const int b = t & 1;
-            mbar_wait(&bars[2 + b], ((t >> 1) & 1) ^ 1);  // buffer released by every consumer warp
             const long long y0 = ys + (long long)t * yt;
+            mbar_wait(&bars[2 + b], ((t >> 1) & 1) ^ 1);  // buffer released by every consumer warp
             ACC *wt = w_of(b);
             unsigned long long bits = 0;  // 4 drop bits per granule, <= 16 granules per thread
             if (p.fast) {
@@ -577,48 +656,47 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
                     wt[idx] = val;
                 }
             }
-            // ---- anchors of tile t
+            // ---- anchors of tile t: pairs q = ptid, ptid + NTP, ... two per iteration
             CA *anch = anch_of(b);
             CA *dstp = dstp_of(b);
             double *phis = reinterpret_cast<double *>(anch);
-            for (int xo = px_local; xo < xgw; xo += NTP) {
-                long long pxi = cta_x0 + xo;
-                if (pxi >= p.nx) pxi = p.nx - 1;
-                const double px0 = p.xc[3 * pxi], px1 = p.xc[3 * pxi + 1], px2 = p.xc[3 * pxi + 2];
-                for (int yl = py0; yl < yt; yl += pystep) {
-                    const long long y = y0 + yl;
-                    const bool live = y < ye;
-                    double phi = 0.0;
-                    if (live)
-                        phi = __dmul_rn(p.cst, phase_dot(px0, px1, px2, p.yc[3 * y], p.yc[3 * y + 1],
-                                                         p.yc[3 * y + 2], f32dot));
-                    if (EXACT) {
-                        phis[yl * xgw + xo] = phi;
-                    } else {
-                        C2<double> a = {0.0, 0.0}, d = {0.0, 0.0}, D = {1.0, 0.0};
-                        if (live) {
-                            a = cis_fast(__dmul_rn(phi, nu0));
-                            d = cis_fast(__dmul_rn(phi, dnu));
-                            if (nck > 1) {
-                                D = d;
+            for (int q0 = ptid; q0 < npairs; q0 += 2 * NTP) {
+                double phi[2];
+                bool live[2];
 #pragma unroll
-                                for (int q = 1; q < CH; q *= 2) {
-                                    const double re = D.re * D.re - D.im * D.im;
-                                    D.im = 2.0 * D.re * D.im;
-                                    D.re = re;
-                                }
-                            }
-                        }
-                        CA dd;
-                        dd.re = (ACC)d.re;
-                        dd.im = (ACC)d.im;
-                        dstp[yl * xgw + xo] = dd;
-                        for (int k = 0; k < nck; ++k) {
-                            CA aa;
-                            aa.re = (ACC)a.re;
-                            aa.im = (ACC)a.im;
-                            anch[(yl * nck + k) * xgw + xo] = aa;
-                            a = cmul(a, D);
+                for (int i = 0; i < 2; ++i) {
+                    const int q = q0 + i * NTP;
+                    const long long y = y0 + (q >> lxgw);
+                    live[i] = q < npairs && y < ye;
+                    phi[i] = 0.0;
+                    if (live[i]) {
+                        double x0 = ox0, x1 = ox1, x2 = ox2;
+                        if (!fixed_owner) load_owner(q & (xgw - 1), x0, x1, x2);
+                        phi[i] = __dmul_rn(p.cst, phase_dot(x0, x1, x2, p.yc[3 * y], p.yc[3 * y + 1],
+                                                            p.yc[3 * y + 2], f32dot));
+                    }
+                }
+                if (EXACT) {
+                    phis[q0] = phi[0];
+                    if (q0 + NTP < npairs) phis[q0 + NTP] = phi[1];
+                } else {
+                    C2<double> a[2], d[2], D[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        a[i] = {0.0, 0.0}, d[i] = {0.0, 0.0}, D[i] = {1.0, 0.0};
+                        if (live[i]) pair_anchors<CH>(phi[i], nu0, dnu, need_D, a[i], d[i], D[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int q = q0 + i * NTP;
+                        if (q < npairs) {
+                            CA dd;
+                            dd.re = (ACC)d[i].re;
+                            dd.im = (ACC)d[i].im;
+                            dstp[q] = dd;
+                            // anchors of pair (yl, xo) start at (yl * nck) * xgw + xo
+                            store_run_anchors<ACC>(anch + (((q >> lxgw) * nck) << lxgw) + (q & (xgw - 1)),
+                                                   nck, xgw, a[i], D[i]);
                         }
                     }
                 }
@@ -689,19 +767,10 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
         } else {
 #pragma unroll 1
             for (int yl = 0; yl < yt; ++yl) {
-                CA z = anch[(yl * nck + ck) * xgw + x_local];
+                const CA z = anch[(yl * nck + ck) * xgw + x_local];
                 const CA d = dstp[yl * xgw + x_local];
-                const ACC *wrow = wt + (size_t)(yl * ft + fo) * NV;
-#pragma unroll
-                for (int j = 0; j < CH; j += G) {
-                    ACC wv[G * NV];
-                    load_vec<G * NV>(wrow + j * NV, wv);
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        accumulate<NCORR, WC, ADJ, ACC>(are[j + g], aim[j + g], z, wv + g * NV);
-                        if (j + g + 1 < CH) z = cmul(z, d);
-                    }
-                }
+                consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, z, d,
+                                                        wt + (size_t)(yl * ft + fo) * NV);
             }
         }
         __syncwarp();

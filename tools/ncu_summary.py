@@ -71,6 +71,13 @@ def main():
         uniq.append(r)
     data = uniq
     S = idx["# Samples"]
+    if len(sys.argv) > 3:  # per-instruction table for offline analysis
+        with open(sys.argv[3], "w") as instr_csv:
+            w = csv.writer(instr_csv)
+            keep = ["Address", "Source", "# Samples", "Instructions Executed"] + ["stall_" + k for k in STALLS if "stall_" + k in idx]
+            w.writerow(keep)
+            for r in data:
+                w.writerow([r[idx[k]].strip() for k in keep])
     tot = sum(int(r[S]) for r in data) or 1
     bars = [i for i, r in enumerate(data) if "BAR.SYNC" in r[idx["Source"]]]
     bounds = [0] + bars + [len(data)]
