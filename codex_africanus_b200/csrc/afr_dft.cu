@@ -56,6 +56,7 @@ struct DftParams {
     int fast;         // 1: W rows are contiguous and copied by cp.async granules
     int granule;      // 4, 8 or 16 bytes
     int row_chunks_log2;  // log2(granules per W tile row)
+    int bulk;             // warp-specialised kernel: W tile by TMA bulk copies
     int arrive_all;       // every consumer lane arrives on the "empty" mbarrier (AFR_SANITIZE=1)
 };
 
@@ -527,6 +528,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         : "memory");
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+// TMA bulk copy global -> shared of `bytes` (multiple of 16, both addresses 16-byte aligned);
+// completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+            smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+
 constexpr int kProducerWarps = 4;
 
 template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NWC, bool EXACT, int CREGS, int PREGS>
@@ -616,7 +632,23 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
             mbar_wait(&bars[2 + b], ((t >> 1) & 1) ^ 1);  // buffer released by every consumer warp
             ACC *wt = w_of(b);
             unsigned long long bits = 0;  // 4 drop bits per granule, <= 16 granules per thread
-            if (p.fast) {
+            if (p.bulk) {
+                // W tile by TMA bulk copies, one per row, issued by one thread: the bytes are
+                // accounted on the tile's "full" barrier (expect_tx now, this thread's arrival
+                // after its anchors), so no producer thread spends instructions on the copy
+                const int rows_valid = (int)min((long long)yt, ye - y0);
+                const int row_smem = ft * NV * SZ;
+                if (ptid == 0) {
+                    mbar_expect_tx(&bars[b], (unsigned)(rows_valid * valid_bytes));
+                    const char *src = w_cta + y0 * row_pitch;
+                    char *dst = reinterpret_cast<char *>(wt);
+                    for (int yl = 0; yl < rows_valid; ++yl, src += row_pitch, dst += row_smem)
+                        bulk_g2s(dst, src, (unsigned)valid_bytes, &bars[b]);
+                }
+                // rows past the end of the slice must read as zero (their anchors are zero,
+                // but 0 * stale NaN would poison the sum)
+                for (int idx = rows_valid * ft * NV + ptid; idx < yt * ft * NV; idx += NTP) wt[idx] = ACC(0);
+            } else if (p.fast) {
                 const int rows_valid = (int)min((long long)yt, ye - y0);
                 const char *src_tile = w_cta + y0 * row_pitch;
                 const unsigned dst_tile = smem_addr(wt);
@@ -701,7 +733,7 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
                     }
                 }
             }
-            if (p.fast) {
+            if (p.fast && !p.bulk) {
                 cp_async_wait_all();
                 if (ADJ && bits) {  // zero this thread's flagged scalars
                     char *wtb = reinterpret_cast<char *>(wt);
@@ -918,6 +950,8 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
         yt -= 2;
     if ((long long)yt * row_chunks > max_chunks) p.fast = 0;
     p.yt = yt;
+    // TMA bulk copies need 16-byte aligned rows and no flag post-processing of the tile
+    p.bulk = (use_ws && p.fast && granule == 16 && p.anyflag == nullptr) ? 1 : 0;
     const size_t smem = 2 * yt * per_y + 3 * (size_t)yt * 3 * sizeof(double) + (size_t)ft * sizeof(double);
 
     // split the streamed axis when the owners alone cannot fill the machine; pick the
