@@ -568,8 +568,8 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
     const size_t dstp_elems = (size_t)yt * xgw;
     const size_t w_elems = (size_t)yt * ft * NV;
     const size_t buf_bytes = (anch_elems + dstp_elems) * sizeof(CA) + w_elems * SZ;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * buf_bytes);  // full[2], empty[2]
-    double *fq = reinterpret_cast<double *>(bars + 4);                        // [ft] (exact)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * buf_bytes);  // full[2], empty[2], wland[2]
+    double *fq = reinterpret_cast<double *>(bars + 6);                        // [ft] (exact)
     auto anch_of = [&](int b) { return reinterpret_cast<CA *>(smem_raw + (size_t)b * buf_bytes); };
     auto dstp_of = [&](int b) { return anch_of(b) + anch_elems; };
     auto w_of = [&](int b) { return reinterpret_cast<ACC *>(dstp_of(b) + dstp_elems); };
@@ -586,6 +586,9 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
         // follow (it does not model the warp-elected release and reports false hazards)
         mbar_init(&bars[2], p.arrive_all ? NWC * 32 : NWC);
         mbar_init(&bars[3], p.arrive_all ? NWC * 32 : NWC);
+        // "W tile landed" (flagged adjoint only: producers edit the tile before publishing it)
+        mbar_init(&bars[4], 1);
+        mbar_init(&bars[5], 1);
     }
     if (EXACT)
         for (int i = tid; i < ft; i += blockDim.x) fq[i] = p.freq[min(cta_f0 + i, p.nchan - 1)];
@@ -632,18 +635,42 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
             mbar_wait(&bars[2 + b], ((t >> 1) & 1) ^ 1);  // buffer released by every consumer warp
             ACC *wt = w_of(b);
             unsigned long long bits = 0;  // 4 drop bits per granule, <= 16 granules per thread
+            uint4 fl16[2];
             if (p.bulk) {
                 // W tile by TMA bulk copies, one per row, issued by one thread: the bytes are
                 // accounted on the tile's "full" barrier (expect_tx now, this thread's arrival
                 // after its anchors), so no producer thread spends instructions on the copy
                 const int rows_valid = (int)min((long long)yt, ye - y0);
                 const int row_smem = ft * NV * SZ;
+                const bool edit = ADJ && p.anyflag != nullptr;
                 if (ptid == 0) {
-                    mbar_expect_tx(&bars[b], (unsigned)(rows_valid * valid_bytes));
+                    uint64_t *landed = edit ? &bars[4 + b] : &bars[b];
+                    if (edit) {
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(
+                                         smem_addr(landed)),
+                                     "r"((unsigned)(rows_valid * valid_bytes))
+                                     : "memory");
+                    } else {
+                        mbar_expect_tx(landed, (unsigned)(rows_valid * valid_bytes));
+                    }
                     const char *src = w_cta + y0 * row_pitch;
                     char *dst = reinterpret_cast<char *>(wt);
                     for (int yl = 0; yl < rows_valid; ++yl, src += row_pitch, dst += row_smem)
-                        bulk_g2s(dst, src, (unsigned)valid_bytes, &bars[b]);
+                        bulk_g2s(dst, src, (unsigned)valid_bytes, landed);
+                }
+                if (edit) {
+                    // any-flag bytes of this thread's (<= 2) groups of 16 samples of the tile;
+                    // the loads fly while the anchors are computed
+                    const int lft = 31 - __clz(ft);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int s0 = (ptid + i * NTP) * 16;  // first sample of the group
+                        const int yl = s0 >> lft, fl = s0 & (ft - 1);
+                        fl16[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (yl < rows_valid && fl < valid_ch)
+                            fl16[i] = *reinterpret_cast<const uint4 *>(p.anyflag + (y0 + yl) * p.nchan +
+                                                                       cta_f0 + fl);
+                    }
                 }
                 // rows past the end of the slice must read as zero (their anchors are zero,
                 // but 0 * stale NaN would poison the sum)
@@ -730,6 +757,23 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
                             store_run_anchors<ACC>(anch + (((q >> lxgw) * nck) << lxgw) + (q & (xgw - 1)),
                                                    nck, xgw, a[i], D[i]);
                         }
+                    }
+                }
+            }
+            if (ADJ && p.bulk && p.anyflag != nullptr) {
+                mbar_wait(&bars[4 + b], (t >> 1) & 1);  // the TMA copies of this tile have landed
+                const int lft = 31 - __clz(ft);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if ((fl16[i].x | fl16[i].y | fl16[i].z | fl16[i].w) != 0u) {
+                        const unsigned wds[4] = {fl16[i].x, fl16[i].y, fl16[i].z, fl16[i].w};
+                        ACC *dst = wt + (size_t)(ptid + i * NTP) * 16 * NV;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            if ((wds[e >> 2] >> (8 * (e & 3))) & 0xFFu) {
+#pragma unroll
+                                for (int v = 0; v < NV; ++v) dst[e * NV + v] = ACC(0);
+                            }
                     }
                 }
             }
@@ -909,7 +953,17 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     // by measurement (tools/ws_sweep.py, B200): the forward (complex-accumulator) kernels
     // gain 5-10 %, the adjoint kernels (64 real accumulators per thread) lose.  AFR_WS=0 / 1
     // forces the choice.
-    constexpr bool kPreferWS = !ADJ;
+    // The adjoint kernels win too once the W tile arrives by TMA (ADJ c=1: 2.47 vs 2.01
+    // Tterm/s), which needs 16-byte rows and, with flags, 16-sample groups.
+    constexpr int CHV = (NV * SZ >= 16) ? 1 : 16 / (NV * SZ);
+    const bool rows16 = ((long long)p.nchan * NV * SZ) % 16 == 0 &&
+                        reinterpret_cast<uintptr_t>(p.w) % 16 == 0 && p.wstride == NCORR && p.coff == 0;
+    int nck_ws = 1;
+    while (nck_ws < (p.nchan + CH - 1) / CH && nck_ws < NW) nck_ws *= 2;
+    const bool flags16 = p.anyflag == nullptr || (p.nchan % 16 == 0 && (nck_ws * CH) % 16 == 0);
+    const bool bulk_ok = rows16 && flags16;
+    (void)CHV;
+    const bool kPreferWS = !ADJ || bulk_ok;
     // FP32 variants gain nothing from it (measured 3.10 vs 3.07 Tterm/s): they are bound by
     // the register-file bandwidth of three-operand FFMAs, not by the anchor work
     const bool use_ws = (sizeof(ACC) == 8) && (ws_env ? atoi(ws_env) != 0 : kPreferWS);
@@ -951,7 +1005,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     if ((long long)yt * row_chunks > max_chunks) p.fast = 0;
     p.yt = yt;
     // TMA bulk copies need 16-byte aligned rows and no flag post-processing of the tile
-    p.bulk = (use_ws && p.fast && granule == 16 && p.anyflag == nullptr) ? 1 : 0;
+    p.bulk = (use_ws && p.fast && granule == 16 && bulk_ok) ? 1 : 0;
     const size_t smem = 2 * yt * per_y + 3 * (size_t)yt * 3 * sizeof(double) + (size_t)ft * sizeof(double);
 
     // split the streamed axis when the owners alone cannot fill the machine; pick the
@@ -997,7 +1051,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
         // setmaxnreg can only move registers inside the CTA's launch-time pool: 640 threads
         // x 96 registers = 512 x 104 (consumers) + 128 x 64 (producers)
         constexpr int CREGS = 104, PREGS = 64;
-        const size_t smem_ws = 2 * yt * per_y + 4 * sizeof(uint64_t) + (size_t)ft * sizeof(double);
+        const size_t smem_ws = 2 * yt * per_y + 6 * sizeof(uint64_t) + (size_t)ft * sizeof(double);
         const int threads = (NW + kProducerWarps) * 32;
         auto launch_ws = [&](auto kern) -> int {
             cudaFuncAttributes attr;

@@ -106,7 +106,8 @@ def test_dft_golden(b200, golden):
 
 @pytest.mark.parametrize("nsrc,nrow,nchan,ncorr", [
     (1, 1, 1, 1), (7, 33, 5, 1), (40, 300, 64, 1), (19, 77, 256, 1), (9, 41, 300, 2),
-    (11, 65, 70, 4), (6, 35, 17, 3), (3000, 40, 16, 1),
+    (11, 65, 70, 4), (6, 35, 17, 3), (3000, 40, 16, 1), (33, 257, 48, 2), (50, 531, 128, 4),
+    (21, 1203, 32, 1),
 ])
 def test_dft_vs_oracle_shapes(b200, oracle, nsrc, nrow, nchan, ncorr):
     """ragged / non-multiple-of-tile shapes, channel tails, y-split path (many sources, few rows)"""
@@ -468,6 +469,15 @@ def test_phasor_stream_kernel_variants_agree(b200, monkeypatch):
             out[ws] = b200.dft.im_to_vis(image, uvw, lm, freq)
         monkeypatch.delenv("AFR_WS")
         assert_c128_close(out["1"], out["0"], rtol=1e-12)
+        # adjoint, flagged (TMA-staged tile edited by the producers) and unflagged
+        vis = rng.standard_normal((nrow, nchan, ncorr)) + 1j * rng.standard_normal((nrow, nchan, ncorr))
+        for flags in (rng.random((nrow, nchan, ncorr)) < 0.05, np.zeros((nrow, nchan, ncorr), bool)):
+            out = {}
+            for ws in ("0", "1"):
+                monkeypatch.setenv("AFR_WS", ws)
+                out[ws] = b200.dft.vis_to_im(vis, uvw, lm, freq, flags)
+            monkeypatch.delenv("AFR_WS")
+            assert_c128_close(out["1"], out["0"], rtol=1e-12)
 
 
 def test_row_block_streaming_paths(b200, oracle, monkeypatch):
