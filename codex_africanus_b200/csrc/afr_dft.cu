@@ -429,12 +429,20 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
             // instructions that share a register operand (.reuse).  A DFMA with three
             // distinct 64-bit register operands issues every 3 cycles on sm_100a (register
             // file bandwidth), one with a reused operand every 2 -- measured, see DESIGN.md.
+            // running pointers: every instruction that is not a DFMA still reads the register
+            // file, whose bandwidth is what bounds the DFMA stream
+            const CA *pa = anch + ck * xgw + x_local;
+            const CA *pd = dstp + x_local;
+            const ACC *pw = wt + fo * NV;
+            const int w_step = ft * NV;
 #pragma unroll 1
             for (int yl = 0; yl < yt; ++yl) {
-                const CA z = anch[(yl * nck + ck) * xgw + x_local];
-                const CA d = dstp[yl * xgw + x_local];
-                consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, z, d,
-                                                        wt + (size_t)(yl * ft + fo) * NV);
+                const CA z = *pa;
+                const CA d = *pd;
+                consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, z, d, pw);
+                pa += NW * 32;  // nck * xgw
+                pd += xgw;
+                pw += w_step;
             }
         }
     };
@@ -841,12 +849,20 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
                 }
             }
         } else {
+            // running pointers: every instruction that is not a DFMA still reads the register
+            // file, whose bandwidth is what bounds the DFMA stream
+            const CA *pa = anch + ck * xgw + x_local;
+            const CA *pd = dstp + x_local;
+            const ACC *pw = wt + fo * NV;
+            const int w_step = ft * NV;
 #pragma unroll 1
             for (int yl = 0; yl < yt; ++yl) {
-                const CA z = anch[(yl * nck + ck) * xgw + x_local];
-                const CA d = dstp[yl * xgw + x_local];
-                consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, z, d,
-                                                        wt + (size_t)(yl * ft + fo) * NV);
+                const CA z = *pa;
+                const CA d = *pd;
+                consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, z, d, pw);
+                pa += NWC * 32;  // nck * xgw
+                pd += xgw;
+                pw += w_step;
             }
         }
         __syncwarp();
