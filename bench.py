@@ -341,7 +341,7 @@ def main():
                 peaks = {}
         io_bytes = (wl["image"].nbytes + wl["uvw"].nbytes + terms / wl["nsrc"] * 16)
         line["roofline"] = {
-            "bound": "fp64", "kernel": "phasor_stream_kernel<ncorr=1, real W, forward, double>",
+            "bound": "fp64", "kernel": "phasor_stream_ws_kernel<ncorr=1, real W, forward, double, CH=16, 16+4 warps>",
             "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
             "frac": achieved / (fp64_peak / 1e12),
             "algorithmic_flop_per_term": FLOP_PER_TERM, "terms_per_launch": terms,
