@@ -28,6 +28,7 @@ PROTOTYPES = {
     "afr_last_error": (ctypes.c_char_p, []),
     "afr_device_count": (_int, []),
     "afr_kernel_launches": (ctypes.c_ulonglong, []),
+    "afr_last_fused_path": (_int, []),
     "afr_set_device": (_int, [_int]),
     "afr_device_info": (_int, [_int, _pint, _pint, _pint, _pint]),
     "afr_freq_is_uniform": (_int, [_vp, _i64, _dbl]),

@@ -25,6 +25,8 @@ void set_error(const std::string &msg);
 int fail(const std::string &msg);
 // every kernel launch of the library is counted (afr_kernel_launches())
 void note_launch(int n = 1);
+// which kernel the last afr_predict_fused call of this host thread used (AFR_PATH_*)
+void note_fused_path(int path);
 
 // call right after a <<<...>>> launch: counts it and checks the launch status
 #define AFR_LAUNCH_OK()                                                                \
@@ -71,6 +73,51 @@ struct Scratch {
         if (ptr) cudaFreeAsync(ptr, stream);
     }
 };
+
+// --------------------------------------------------------------------------
+// shared-memory barriers and TMA bulk copies (warp-specialised kernels)
+// --------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n\t}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+// TMA bulk copy global -> shared of `bytes` (multiple of 16, both addresses 16-byte aligned);
+// completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+            smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
 
 // --------------------------------------------------------------------------
 // device math

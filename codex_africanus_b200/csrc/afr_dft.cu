@@ -60,9 +60,6 @@ struct DftParams {
     int arrive_all;       // every consumer lane arrives on the "empty" mbarrier (AFR_SANITIZE=1)
 };
 
-__device__ __forceinline__ unsigned smem_addr(const void *p) {
-    return (unsigned)__cvta_generic_to_shared(p);
-}
 __device__ __forceinline__ void cp_async(unsigned dst, const void *src, int granule, int src_bytes) {
     if (granule == 16)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
@@ -518,39 +515,6 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
 // 512 x 104 + 128 x 64): the extra 8 registers let ptxas keep the operand-reuse-friendly
 // schedule of the rotation loop (tools/sass_dp_model.py: 14.2 vs 16.0 cycles per term).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n\t}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-// TMA bulk copy global -> shared of `bytes` (multiple of 16, both addresses 16-byte aligned);
-// completion is signalled on `bar` as transaction bytes
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-            smem_addr(dst)),
-        "l"(src), "r"(bytes), "r"(smem_addr(bar))
-        : "memory");
-}
-
 constexpr int kProducerWarps = 4;
 
 template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NWC, bool EXACT, int CREGS, int PREGS>

@@ -28,4 +28,28 @@ int run_phasor_stream(const double *xc, int64_t nx, const double *yc, int64_t ny
                       int64_t ncorr, double cst, bool f32dot, bool adjoint, bool exact,
                       bool acc32, void *out, cudaStream_t stream);
 
+// ---- warp-specialised full-RIME predict with DDEs (afr_rime_ws.cu)
+struct DdeWsParams {
+    const double *lmn, *uvw, *freq;
+    const double *bright;      // (nsrc,nchan,2,2) complex128
+    const int32_t *ant1, *ant2;
+    const int32_t *row_start;  // (ntime+1) first row of each timestep (rows sorted by time)
+    const double *dde1, *dde2; // (nsrc,ntime,nant,nchan,2,2) complex128
+    const double *ant_uvw;     // (ntime,nant,3) per-antenna coordinates (antenna mode) or nullptr
+    double *out;               // (nrow,nchan,2,2) complex128
+    double cst;
+    long long nsrc, nrow, ntime, nant;
+    int nchan;
+    int same_dde;
+};
+size_t dde_ws_smem_bytes(int64_t nant);
+// per-timestep antenna coordinates from baseline uvw; ok[0] is cleared when the rows of any
+// timestep are not differences of per-antenna coordinates
+int launch_antenna_uvw(const double *uvw, const int32_t *ant1, const int32_t *ant2,
+                       const int32_t *row_start, int64_t ntime, int64_t nant, const double *lmn,
+                       int64_t nsrc, const double *freq, int64_t nchan, double cst, double *ant_uvw,
+                       int *ok, cudaStream_t stream);
+int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact, bool ant_mode,
+                        cudaStream_t stream);
+
 }  // namespace afr

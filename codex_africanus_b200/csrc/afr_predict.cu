@@ -16,6 +16,7 @@
 //       advances by exp(i*phi*32*dnu) between a lane's channels.
 //   base_vis and the DIE product are applied by the same epilogue as predict_vis.
 #include <algorithm>
+#include <cstdlib>
 
 #include "afr_dft.cuh"
 
@@ -671,6 +672,7 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
                                freq, nchan, ncorr, cst, false, /*adjoint=*/false, exact,
                                out_c64 != 0, out, stream);
         if (rc) return rc;
+        note_fused_path(AFR_PATH_POINT);
     } else {
         FusedParams f{};
         f.lmn = (const double *)lmn.ptr;
@@ -704,10 +706,58 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
             max_rows_kernel<<<(int)((ntime + 255) / 256), 256, 0, stream>>>((const int32_t *)rs.ptr,
                                                                             ntime, (int *)fl.ptr);
             AFR_LAUNCH_OK();
+            // warp-specialised kernel (afr_rime_ws.cu): TMA needs 16-byte aligned sources and
+            // the three-stage antenna tile must fit in shared memory
+            const bool ws_ok = dde_ws_smem_bytes(nant) <= 220 * 1024 &&
+                               reinterpret_cast<uintptr_t>(dde1) % 16 == 0 &&
+                               reinterpret_cast<uintptr_t>(dde2) % 16 == 0 &&
+                               reinterpret_cast<uintptr_t>(brightness) % 16 == 0 &&
+                               !(getenv("AFR_DDE_WS") && atoi(getenv("AFR_DDE_WS")) == 0);
+            Scratch antuvw, antok;
+            if (ws_ok) {
+                AFR_CUDA_OK(antuvw.alloc(sizeof(double) * 3 * (size_t)(ntime * nant), stream));
+                AFR_CUDA_OK(antok.alloc(sizeof(int), stream));
+                const int one = 1;
+                AFR_CUDA_OK(cudaMemcpyAsync(antok.ptr, &one, sizeof(int), cudaMemcpyHostToDevice, stream));
+                rc = launch_antenna_uvw(uvw, antenna1, antenna2, (const int32_t *)rs.ptr, ntime, nant,
+                                        (const double *)lmn.ptr, nsrc, freq, nchan, cst,
+                                        (double *)antuvw.ptr, (int *)antok.ptr, stream);
+                if (rc) return rc;
+            }
             int hflags[2] = {0, 0};
+            int hant = 0;
             AFR_CUDA_OK(cudaMemcpyAsync(hflags, fl.ptr, sizeof(hflags), cudaMemcpyDeviceToHost, stream));
+            if (ws_ok)
+                AFR_CUDA_OK(cudaMemcpyAsync(&hant, antok.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
             AFR_CUDA_OK(cudaStreamSynchronize(stream));
             const bool same = dde1 == dde2;
+            if (ws_ok && hflags[0] == 0 && hflags[1] > 0) {
+                DdeWsParams wp{};
+                wp.lmn = (const double *)lmn.ptr;
+                wp.uvw = uvw;
+                wp.freq = freq;
+                wp.bright = (const double *)brightness;
+                wp.ant1 = antenna1;
+                wp.ant2 = antenna2;
+                wp.row_start = (const int32_t *)rs.ptr;
+                wp.dde1 = (const double *)dde1;
+                wp.dde2 = (const double *)dde2;
+                wp.ant_uvw = (const double *)antuvw.ptr;
+                wp.out = (double *)out;
+                wp.cst = cst;
+                wp.nsrc = nsrc;
+                wp.nrow = nrow;
+                wp.ntime = ntime;
+                wp.nant = nant;
+                wp.nchan = (int)nchan;
+                wp.same_dde = same ? 1 : 0;
+                const char *am = getenv("AFR_DDE_ANT");  // 0 forces the per-row phasor mode
+                const bool ant_mode = hant != 0 && !(am && atoi(am) == 0);
+                rc = launch_fused_dde_ws(wp, hflags[1], exact, ant_mode, stream);
+                if (rc) return rc;
+                note_fused_path(ant_mode ? AFR_PATH_DDE_WS_ANT : AFR_PATH_DDE_WS_ROW);
+                done = true;
+            }
             int nck = 2;
             auto smem_for = [&](int k) {
                 const size_t mat = (size_t)k * kTileCHD * nant * 64;
@@ -715,7 +765,7 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
                        2 * (size_t)kTileRowsMax * 16 + (size_t)k * kTileCHD * 8;
             };
             if (smem_for(nck) > 200 * 1024) nck = 1;
-            if (hflags[0] == 0 && hflags[1] > 0 && smem_for(nck) <= 200 * 1024) {
+            if (!done && hflags[0] == 0 && hflags[1] > 0 && smem_for(nck) <= 200 * 1024) {
                 TiledParams tp{};
                 tp.lmn = (const double *)lmn.ptr;
                 tp.uvw = uvw;
@@ -752,9 +802,11 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
                     fused_dde_tiled_kernel<false><<<grid, kTileThreads, smem, stream>>>(tp);
                 }
                 AFR_LAUNCH_OK();
+                note_fused_path(AFR_PATH_DDE_TILED);
                 done = true;
             }
         }
+        if (!done) note_fused_path(AFR_PATH_DDE_GATHER);
         if (!done)
             rc = out_c64 ? launch_fused_dde<float>(f, jones_mode, exact, stream)
                          : launch_fused_dde<double>(f, jones_mode, exact, stream);

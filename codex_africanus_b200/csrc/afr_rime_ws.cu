@@ -1,0 +1,443 @@
+// Full-RIME fused predict with DDEs, warp-specialised (sm_100a):
+//
+//   V[r,f] += sum_s K[s,r,f] * E1[s,t,a1,f] * B[s,f] * E2[s,t,a2,f]^H        (2x2, complex128)
+//
+// (africanus/rime/predict.py:103-117,193-252 composed with rime/phase.py:20-63; the
+// composition is the one of rime/examples/predict.py:107-134.)
+//
+// A CTA owns one timestep, 512 rows (lane <-> row, 16 consumer warps) and 4 channels; the 64
+// accumulator doubles of a thread stay in registers for the whole source loop.  Per source
+// the 4 PRODUCER warps
+//   * fetch E[s,t,:,f0:f0+4] for ALL antennas (and B[s,f0:f0+4]) with 16-byte cp.async tracked
+//     by an mbarrier, into a padded shared-memory layout (antenna stride 272 B, so lanes
+//     reading consecutive antennas hit distinct banks and lanes reading the same antenna
+//     broadcast);
+//   * precombine A_p = E1_p * B_s (valid because K is a scalar: E1 (K B) E2^H = K (E1 B) E2^H),
+//     in place when E1 != E2;
+//   * and supply the phasors, in one of two forms:
+//       ROW mode  - per row: anchor exp(i phi nu_f0) and channel step exp(i phi dnu), phi from
+//                   the row's uvw exactly as the reference rounds it; the consumer multiplies
+//                   the 2x2 product by the phasor and advances it with the three-term recurrence;
+//       ANT mode  - when the baseline uvw of a timestep are differences of per-antenna
+//                   coordinates (checked on the device, see antenna_uvw_kernel), K factorises as
+//                   k_p conj(k_q) and is folded into the antenna matrices: A_p <- k_p A_p,
+//                   E_q <- k_q E_q.  64 phasors per source instead of 512, and the consumer is
+//                   left with ONE 2x2 product and the accumulate per term.
+// Consumers wait on the stage's "full" mbarrier, do register-only FP64 work fed by LDS.128,
+// and release the stage with one arrive per warp.  Three stages: one being consumed, one
+// being prepared, one in flight from L2/HBM.
+#include <algorithm>
+
+#include "afr_dft.cuh"
+
+namespace afr {
+namespace {
+
+constexpr int kConsWarps = 16;
+constexpr int kProdWarps = 4;
+constexpr int kRows = kConsWarps * 32;  // rows per CTA
+constexpr int kFT = 4;                  // channels per CTA (= per thread)
+constexpr int kNS = 3;                  // pipeline stages
+constexpr int kMatBytes = 64;           // one 2x2 complex128 matrix
+constexpr int kAntStride = kFT * kMatBytes + 16;  // padded shared-memory stride of an antenna
+constexpr int kNTP = kProdWarps * 32;
+
+struct Cd {
+    double re, im;
+};
+__device__ __forceinline__ Cd cmul_(Cd a, Cd b) {
+    return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+__device__ __forceinline__ Cd cmulc_(Cd a, Cd b) {  // a * conj(b)
+    return {a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im};
+}
+__device__ __forceinline__ Cd cadd_(Cd a, Cd b) { return {a.re + b.re, a.im + b.im}; }
+
+__device__ __forceinline__ Cd lds_c(const unsigned char *p) {
+    const double2 v = *reinterpret_cast<const double2 *>(p);
+    return {v.x, v.y};
+}
+__device__ __forceinline__ void sts_c(unsigned char *p, Cd v) {
+    *reinterpret_cast<double2 *>(p) = make_double2(v.re, v.im);
+}
+
+size_t stage_bytes(int na) {
+    // E2 (or E), E1 -> A (or A), B, per-row anchors + steps (ROW mode) / per-antenna (ANT mode)
+    return 2 * (size_t)na * kAntStride + kFT * kMatBytes + 2 * (size_t)kRows * 16;
+}
+
+template <bool EXACT, bool ANT>
+__global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
+    fused_dde_ws_kernel(const DdeWsParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int na = (int)p.nant;
+    const int t = blockIdx.y;
+    const int f0 = blockIdx.z * kFT;
+    const long long rbeg = p.row_start[t] + (long long)blockIdx.x * kRows;
+    const long long rend = min((long long)p.row_start[t + 1], rbeg + kRows);
+    if (rbeg >= rend) return;
+
+    const size_t mat_region = (size_t)na * kAntStride;
+    const size_t stage = 2 * mat_region + kFT * kMatBytes + 2 * (size_t)kRows * 16;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kNS * stage);  // full, empty, landed [kNS]
+    double *fq = reinterpret_cast<double *>(bars + 3 * kNS);            // [kFT]
+    auto e2_of = [&](int st) { return smem + st * stage; };
+    auto a_of = [&](int st) { return smem + st * stage + mat_region; };
+    auto b_of = [&](int st) { return smem + st * stage + 2 * mat_region; };
+    auto z_of = [&](int st) { return reinterpret_cast<C2<double> *>(smem + st * stage + 2 * mat_region + kFT * kMatBytes); };
+    auto d_of = [&](int st) { return z_of(st) + kRows; };
+
+    if (tid == 0) {
+        for (int i = 0; i < kNS; ++i) {
+            mbar_init(&bars[i], kNTP);                 // full: every producer thread
+            mbar_init(&bars[kNS + i], kConsWarps);     // empty: one lane per consumer warp
+            mbar_init(&bars[2 * kNS + i], kNTP);       // landed: the cp.async of every producer thread
+        }
+    }
+    if (tid < kFT) fq[tid] = p.freq[min(f0 + tid, p.nchan - 1)];
+    __syncthreads();
+
+    const int valid_ch = min(kFT, p.nchan - f0);
+    const long long nsrc = p.nsrc;
+    double dnu = 0.0;
+    if (p.nchan > 1) dnu = (p.freq[p.nchan - 1] - p.freq[0]) / (double)(p.nchan - 1);
+    const double nu0 = p.freq[min(f0, p.nchan - 1)];
+
+    if (warp >= kConsWarps) {
+        // =============================== PRODUCERS ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+        const int ptid = tid - kConsWarps * 32;
+        // E[s,t,:,f0:f0+4] (both sides) and B[s,f0:f0+4] -> stage s % kNS by 16-byte cp.async
+        // spread over the 128 producer threads; completion is tracked by the stage's "landed"
+        // mbarrier (cp.async.mbarrier.arrive.noinc, one arrival per producer thread).  TMA bulk
+        // copies were measured first: the tile is 65-129 pieces of 256 B per source, and one
+        // bulk copy per piece costs more issue time than the whole consume phase.
+        const int gran_valid = valid_ch * 4;  // 16-byte granules per antenna that exist
+        auto issue = [&](long long s) {
+            const int st = (int)(s % kNS);
+            const char *src2 = reinterpret_cast<const char *>(
+                p.dde2 + (((s * p.ntime + t) * p.nant) * (long long)p.nchan + f0) * 8);
+            const char *src1 = reinterpret_cast<const char *>(
+                p.dde1 + (((s * p.ntime + t) * p.nant) * (long long)p.nchan + f0) * 8);
+            const long long astride = (long long)p.nchan * kMatBytes;  // bytes between antennas
+            const unsigned d2 = smem_addr(e2_of(st)), d1 = smem_addr(a_of(st));
+            for (int g = ptid; g < na * 16; g += kNTP) {
+                const int a = g >> 4, c = g & 15;
+                if (c < gran_valid) {
+                    const unsigned doff = (unsigned)(a * kAntStride + c * 16);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d2 + doff),
+                                 "l"(src2 + a * astride + c * 16));
+                    if (!p.same_dde)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d1 + doff),
+                                     "l"(src1 + a * astride + c * 16));
+                }
+            }
+            if (ptid < gran_valid)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                                 smem_addr(b_of(st)) + ptid * 16),
+                             "l"(reinterpret_cast<const char *>(p.bright + (s * (long long)p.nchan + f0) * 8) +
+                                 ptid * 16));
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(
+                             smem_addr(&bars[2 * kNS + st]))
+                         : "memory");
+        };
+        for (long long s = 0; s < kNS - 1 && s < nsrc; ++s) issue(s);
+
+        // ROW mode: rows of this thread (4 of the 512); ANT mode: antennas of this thread
+        double ru[kRows / kNTP], rv[kRows / kNTP], rw[kRows / kNTP];
+        if (!ANT) {
+#pragma unroll
+            for (int i = 0; i < kRows / kNTP; ++i) {
+                const long long r = rbeg + ptid + i * kNTP;
+                const bool ok = r < rend;
+                ru[i] = ok ? p.uvw[3 * r] : 0.0;
+                rv[i] = ok ? p.uvw[3 * r + 1] : 0.0;
+                rw[i] = ok ? p.uvw[3 * r + 2] : 0.0;
+            }
+        }
+
+        for (long long s = 0; s < nsrc; ++s) {
+            const int st = (int)(s % kNS);
+            const unsigned par = (unsigned)((s / kNS) & 1);
+            // the stage must have been released by the consumers of source s - kNS
+            if (s >= kNS) mbar_wait(&bars[kNS + st], (unsigned)(((s - kNS) / kNS) & 1));
+            const double sl = p.lmn[3 * s], sm = p.lmn[3 * s + 1], sn = p.lmn[3 * s + 2];
+            C2<double> *zs = z_of(st), *ds = d_of(st);
+            if (!ANT) {
+                // ---- per-row phasor anchors (phase argument rounded exactly as the reference)
+#pragma unroll
+                for (int i = 0; i < kRows / kNTP; ++i) {
+                    const int rl = ptid + i * kNTP;
+                    const bool live = rbeg + rl < rend;
+                    const double phi = __dmul_rn(p.cst, phase_dot(sl, sm, sn, ru[i], rv[i], rw[i], false));
+                    if (EXACT) {
+                        ds[rl].re = phi;
+                    } else {
+                        zs[rl] = live ? cis_fast(__dmul_rn(phi, nu0)) : C2<double>{0.0, 0.0};
+                        ds[rl] = live ? cis_fast(__dmul_rn(phi, dnu)) : C2<double>{0.0, 0.0};
+                    }
+                }
+            }
+            mbar_wait(&bars[2 * kNS + st], par);  // E (and B) of source s have landed
+            // ---- A_p = E1_p * B_s (ANT mode: times k_p; and E2_q <- k_q E2_q)
+            const unsigned char *bsm = b_of(st);
+            unsigned char *e2 = e2_of(st), *am = a_of(st);
+            for (int idx = ptid; idx < na * kFT; idx += kNTP) {
+                const int a = idx >> 2, fl = idx & 3;
+                const unsigned off = (unsigned)(a * kAntStride + fl * kMatBytes);
+                const unsigned char *e1 = (p.same_dde ? e2 : am) + off;
+                const Cd b0 = lds_c(bsm + fl * kMatBytes), b1 = lds_c(bsm + fl * kMatBytes + 16);
+                const Cd b2 = lds_c(bsm + fl * kMatBytes + 32), b3 = lds_c(bsm + fl * kMatBytes + 48);
+                const Cd x0 = lds_c(e1), x1 = lds_c(e1 + 16), x2 = lds_c(e1 + 32), x3 = lds_c(e1 + 48);
+                Cd m0 = cadd_(cmul_(x0, b0), cmul_(x1, b2));
+                Cd m1 = cadd_(cmul_(x0, b1), cmul_(x1, b3));
+                Cd m2 = cadd_(cmul_(x2, b0), cmul_(x3, b2));
+                Cd m3 = cadd_(cmul_(x2, b1), cmul_(x3, b3));
+                if (ANT) {
+                    // antenna phasor k_a(f) = exp(i psi_a nu_f), psi_a from the antenna coordinates
+                    const double *ac = p.ant_uvw + ((long long)t * p.nant + a) * 3;
+                    const double psi = __dmul_rn(p.cst, phase_dot(sl, sm, sn, ac[0], ac[1], ac[2], false));
+                    const C2<double> kk = cis_fast(__dmul_rn(psi, fq[fl]));
+                    const Cd k = {kk.re, kk.im};
+                    m0 = cmul_(k, m0), m1 = cmul_(k, m1), m2 = cmul_(k, m2), m3 = cmul_(k, m3);
+                    if (p.same_dde) {
+                        sts_c(e2 + off, cmul_(k, x0));
+                        sts_c(e2 + off + 16, cmul_(k, x1));
+                        sts_c(e2 + off + 32, cmul_(k, x2));
+                        sts_c(e2 + off + 48, cmul_(k, x3));
+                    } else {
+                        sts_c(e2 + off, cmul_(k, lds_c(e2 + off)));
+                        sts_c(e2 + off + 16, cmul_(k, lds_c(e2 + off + 16)));
+                        sts_c(e2 + off + 32, cmul_(k, lds_c(e2 + off + 32)));
+                        sts_c(e2 + off + 48, cmul_(k, lds_c(e2 + off + 48)));
+                    }
+                }
+                sts_c(am + off, m0);
+                sts_c(am + off + 16, m1);
+                sts_c(am + off + 32, m2);
+                sts_c(am + off + 48, m3);
+            }
+            mbar_arrive(&bars[st]);  // full: anchors, A (and scaled E2) of source s are visible
+            // ---- next TMA: source s + kNS - 1 goes into the stage source s - 1 used
+            if (s + kNS - 1 < nsrc) {
+                if (s >= 1) mbar_wait(&bars[kNS + (int)((s - 1) % kNS)], (unsigned)(((s - 1) / kNS) & 1));
+                issue(s + kNS - 1);
+            }
+        }
+        return;
+    }
+
+    // ================================= CONSUMERS =================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
+    const int row_local = warp * 32 + lane;
+    const long long r = rbeg + row_local;
+    const bool row_ok = r < rend;
+    int a1 = 0, a2 = 0;
+    if (row_ok) {
+        a1 = p.ant1[r];
+        a2 = p.ant2[r];
+    }
+    const unsigned off1 = (unsigned)(a1 * kAntStride), off2 = (unsigned)(a2 * kAntStride);
+
+    Cd acc[kFT][4];
+#pragma unroll
+    for (int j = 0; j < kFT; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[j][c] = {0.0, 0.0};
+
+    for (long long s = 0; s < nsrc; ++s) {
+        const int st = (int)(s % kNS);
+        mbar_wait(&bars[st], (unsigned)((s / kNS) & 1));
+        const unsigned char *e2 = e2_of(st) + off2;
+        const unsigned char *am = a_of(st) + off1;
+        Cd z = {1.0, 0.0}, zp = {1.0, 0.0}, d = {1.0, 0.0};
+        double c2 = 2.0;
+        if (!ANT) {
+            const C2<double> zz = z_of(st)[row_local], dd = d_of(st)[row_local];
+            z = {zz.re, zz.im};
+            d = {dd.re, dd.im};
+            c2 = d.re + d.re;
+        }
+#pragma unroll
+        for (int j = 0; j < kFT; ++j) {
+            if (!ANT && EXACT) {
+                const C2<double> zz = cis_fast(__dmul_rn(d.re, fq[j]));
+                z = {zz.re, zz.im};
+            }
+            const Cd q0 = lds_c(e2 + j * kMatBytes), q1 = lds_c(e2 + j * kMatBytes + 16);
+            const Cd q2 = lds_c(e2 + j * kMatBytes + 32), q3 = lds_c(e2 + j * kMatBytes + 48);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // one output row of A * E^H at a time
+                const Cd x0 = lds_c(am + j * kMatBytes + 32 * h), x1 = lds_c(am + j * kMatBytes + 32 * h + 16);
+                const Cd m0 = cadd_(cmulc_(x0, q0), cmulc_(x1, q1));
+                const Cd m1 = cadd_(cmulc_(x0, q2), cmulc_(x1, q3));
+                if (ANT) {
+                    acc[j][2 * h] = cadd_(acc[j][2 * h], m0);
+                    acc[j][2 * h + 1] = cadd_(acc[j][2 * h + 1], m1);
+                } else {
+                    acc[j][2 * h] = cadd_(acc[j][2 * h], cmul_(z, m0));
+                    acc[j][2 * h + 1] = cadd_(acc[j][2 * h + 1], cmul_(z, m1));
+                }
+            }
+            if (!ANT && !EXACT && j + 1 < kFT) {
+                // three-term recurrence z_{j+1} = 2 Re(d) z_j - z_{j-1} (first step: z * d)
+                Cd zn;
+                if (j == 0) {
+                    zn = cmul_(z, d);
+                } else {
+                    zn.re = fma(c2, z.re, -zp.re);
+                    zn.im = fma(c2, z.im, -zp.im);
+                }
+                zp = z;
+                z = zn;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[kNS + st]);
+    }
+
+    if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < kFT; ++j) {
+            const int f = f0 + j;
+            if (f < p.nchan) {
+                double2 *o = reinterpret_cast<double2 *>(p.out + (r * p.nchan + f) * 8);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[c] = make_double2(acc[j][c].re, acc[j][c].im);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Antenna decomposition of the baseline uvw of each timestep (ANT mode).
+//
+// The uvw of a row are, in every Measurement Set, the difference of two per-antenna
+// coordinates: uvw[r] = U[a1] - U[a2] (or the opposite sign: the same decomposition with U
+// negated).  If that holds for the caller's arrays the phasor factorises per antenna.  One CTA
+// per timestep: the reference antenna is the antenna1 of the timestep's first row, U[ref] = 0,
+// U[a] follows from the rows that join `a` to the reference; then EVERY row is checked.
+// The mode is only allowed when the phase it produces provably stays within 5e-11 rad of the
+// phase the reference rounds (half the 1e-10 parity gate):
+//     |cst| nu_max L (|uvw[r] - (U[a1] - U[a2])| + 9 eps max(|U[a1]|, |U[a2]|)) <= 5e-11,
+// L = max_s (|l| + |m| + |n|): the first term is the decomposition residual, the second the
+// rounding of the two per-antenna phase arguments plus the reference's own.  Wide fields or
+// very long baselines therefore stay in ROW mode.  Any antenna not joined to the reference,
+// or any row that fails, clears ok[0].
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) antenna_uvw_kernel(const double *uvw, const int32_t *ant1,
+                                                          const int32_t *ant2, const int32_t *row_start,
+                                                          long long nant, const double *lmn,
+                                                          long long nsrc, const double *freq,
+                                                          long long nchan, double cst, double *ant_uvw,
+                                                          int *ok) {
+    extern __shared__ unsigned char sm_raw[];
+    int *have = reinterpret_cast<int *>(sm_raw);  // [nant]
+    __shared__ double red[2][256];
+    const int t = blockIdx.x;
+    const long long rb = row_start[t], re = row_start[t + 1];
+    double *U = ant_uvw + (long long)t * nant * 3;
+    for (int a = threadIdx.x; a < nant; a += blockDim.x) {
+        have[a] = 0;
+        U[3 * a] = U[3 * a + 1] = U[3 * a + 2] = 0.0;
+    }
+    double L = 0.0, nu = 0.0;
+    for (long long s = threadIdx.x; s < nsrc; s += blockDim.x)
+        L = fmax(L, fabs(lmn[3 * s]) + fabs(lmn[3 * s + 1]) + fabs(lmn[3 * s + 2]));
+    for (long long f = threadIdx.x; f < nchan; f += blockDim.x) nu = fmax(nu, fabs(freq[f]));
+    red[0][threadIdx.x] = L;
+    red[1][threadIdx.x] = nu;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            red[0][threadIdx.x] = fmax(red[0][threadIdx.x], red[0][threadIdx.x + w]);
+            red[1][threadIdx.x] = fmax(red[1][threadIdx.x], red[1][threadIdx.x + w]);
+        }
+        __syncthreads();
+    }
+    const double rad_per_metre = fabs(cst) * red[1][0] * red[0][0];
+    if (rb >= re) return;
+    const int ref = ant1[rb];
+    if (threadIdx.x == 0) have[ref] = 1;
+    __syncthreads();
+    for (long long r = rb + threadIdx.x; r < re; r += blockDim.x) {
+        const int p1 = ant1[r], p2 = ant2[r];
+        if (p1 == ref && p2 != ref) {
+            U[3 * p2] = -uvw[3 * r];
+            U[3 * p2 + 1] = -uvw[3 * r + 1];
+            U[3 * p2 + 2] = -uvw[3 * r + 2];
+            have[p2] = 1;
+        } else if (p2 == ref && p1 != ref) {
+            U[3 * p1] = uvw[3 * r];
+            U[3 * p1 + 1] = uvw[3 * r + 1];
+            U[3 * p1 + 2] = uvw[3 * r + 2];
+            have[p1] = 1;
+        }
+    }
+    __syncthreads();
+    bool good = true;
+    for (long long r = rb + threadIdx.x; r < re; r += blockDim.x) {
+        const int p1 = ant1[r], p2 = ant2[r];
+        if (!have[p1] || !have[p2]) {
+            good = false;
+            break;
+        }
+        double worst = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double u1 = U[3 * p1 + c], u2 = U[3 * p2 + c], got = uvw[3 * r + c];
+            worst = fmax(worst, fabs(got - (u1 - u2)) + 9.0 * 1.1102230246251565e-16 * fmax(fabs(u1), fabs(u2)));
+        }
+        if (!(rad_per_metre * worst <= 5e-11)) good = false;  // also catches NaN
+    }
+    if (!good) atomicAnd(ok, 0);
+}
+
+}  // namespace
+
+size_t dde_ws_smem_bytes(int64_t nant) {
+    return kNS * stage_bytes((int)nant) + 3 * kNS * sizeof(uint64_t) + kFT * sizeof(double);
+}
+
+int launch_antenna_uvw(const double *uvw, const int32_t *ant1, const int32_t *ant2,
+                       const int32_t *row_start, int64_t ntime, int64_t nant, const double *lmn,
+                       int64_t nsrc, const double *freq, int64_t nchan, double cst, double *ant_uvw,
+                       int *ok, cudaStream_t stream) {
+    if (ntime <= 0) return 0;
+    antenna_uvw_kernel<<<(unsigned)ntime, 256, (size_t)nant * sizeof(int), stream>>>(
+        uvw, ant1, ant2, row_start, nant, lmn, nsrc, freq, nchan, cst, ant_uvw, ok);
+    AFR_LAUNCH_OK();
+    return 0;
+}
+
+int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact, bool ant_mode,
+                        cudaStream_t stream) {
+    const size_t smem = dde_ws_smem_bytes(p.nant);
+    dim3 grid((unsigned)((max_rows_per_time + kRows - 1) / kRows), (unsigned)p.ntime,
+              (unsigned)((p.nchan + kFT - 1) / kFT));
+    AFR_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "afr_predict_fused: grid too large");
+    const int threads = (kConsWarps + kProdWarps) * 32;
+    auto go = [&](auto kern) -> int {
+        cudaFuncAttributes attr;
+        AFR_CUDA_OK(cudaFuncGetAttributes(&attr, kern));
+        // setmaxnreg moves registers inside the launch-time pool: it must hold 512 x 104 + 128 x 64
+        AFR_REQUIRE(threads * attr.numRegs >= kConsWarps * 32 * 104 + kProdWarps * 32 * 64,
+                    "fused_dde_ws: launch-time register pool too small for setmaxnreg");
+        AFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, stream>>>(p);
+        return 0;
+    };
+    int rc;
+    if (ant_mode)
+        rc = go(fused_dde_ws_kernel<false, true>);  // antenna phasors are exact per channel
+    else if (exact)
+        rc = go(fused_dde_ws_kernel<true, false>);
+    else
+        rc = go(fused_dde_ws_kernel<false, false>);
+    if (rc) return rc;
+    AFR_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace afr

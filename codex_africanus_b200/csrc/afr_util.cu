@@ -9,6 +9,7 @@ namespace afr {
 
 static thread_local std::string g_last_error;
 static std::atomic<unsigned long long> g_launches{0};
+static thread_local int g_fused_path = 0;
 
 void retain_pool_memory() {
     static std::atomic<unsigned> done_mask{0};  // one bit per device
@@ -27,6 +28,8 @@ void retain_pool_memory() {
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 void set_error(const std::string &msg) { g_last_error = msg; }
+
+void note_fused_path(int path) { g_fused_path = path; }
 
 int fail(const std::string &msg) {
     g_last_error = msg;
@@ -64,6 +67,8 @@ extern "C" unsigned long long afr_kernel_launches(void) {
 }
 
 extern "C" const char *afr_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int afr_last_fused_path(void) { return g_fused_path; }
 
 extern "C" int afr_device_count(void) {
     int n = 0;

@@ -59,6 +59,14 @@ const char *afr_last_error(void);
 int afr_device_count(void);
 /* number of CUDA kernels this library has launched in this process so far */
 unsigned long long afr_kernel_launches(void);
+/* Which kernel the last afr_predict_fused call of this host thread ran (diagnostics/tests). */
+#define AFR_PATH_NONE 0
+#define AFR_PATH_POINT 1        /* no DDEs: phasor-stream kernel                              */
+#define AFR_PATH_DDE_WS_ANT 2   /* warp-specialised DDE kernel, phasors folded per antenna    */
+#define AFR_PATH_DDE_WS_ROW 3   /* warp-specialised DDE kernel, per-row phasors               */
+#define AFR_PATH_DDE_TILED 4    /* antenna-tiled single-role kernel                           */
+#define AFR_PATH_DDE_GATHER 5   /* gather kernel (unsorted rows, diagonal Jones, complex64)   */
+int afr_last_fused_path(void);
 /* Select the CUDA device used by subsequent calls on this host thread.  The library
  * links its own (static) CUDA runtime, whose current-device state is separate from any
  * other runtime in the process (e.g. PyTorch's): bindings call this before each entry

@@ -408,6 +408,61 @@ def test_fused_predict_vs_oracle(b200, oracle):
             assert rel_l2(got.astype(np.complex128), ref) < 1e-5
 
 
+def test_fused_dde_ws_modes_vs_oracle(b200, oracle, monkeypatch):
+    """The warp-specialised DDE kernel: antenna-phasor mode (baseline uvw that are differences
+    of per-antenna coordinates, as in a Measurement Set), per-row phasor mode (forced, and
+    chosen automatically for uvw that are not antenna-consistent), and the previous tiled
+    kernel must all match the oracle.  Ragged timesteps, channel tail, E1 != E2."""
+    rng = np.random.default_rng(2024)
+    na, ntime, nsrc = 9, 4, 23
+    a1, a2 = np.triu_indices(na, 1)
+    # ragged timesteps; the baselines to antenna 0 (the reference of the decomposition) stay
+    opt = np.flatnonzero(a1 != 0)
+    keep = [np.sort(np.concatenate([np.flatnonzero(a1 == 0),
+                                    rng.choice(opt, size=opt.size - 3 * t, replace=False)]))
+            for t in range(ntime)]
+    ant1 = np.concatenate([a1[k] for k in keep])
+    ant2 = np.concatenate([a2[k] for k in keep])
+    ti = np.concatenate([np.full(k.size, t + 3) for t, k in enumerate(keep)])
+    antpos = rng.standard_normal((ntime, na, 3)) * 1500.0
+    uvw_ant = antpos[ti - 3, ant1] - antpos[ti - 3, ant2]
+    uvw_rnd = rng.standard_normal(uvw_ant.shape) * 1500.0
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    for nchan, uniform in ((37, True), (16, False)):
+        freq = np.linspace(0.856e9, 1.712e9, nchan)
+        if not uniform:
+            freq = np.sort(rng.uniform(0.856e9, 1.712e9, nchan))
+        bright = rc((nsrc, nchan, 2, 2))
+        dde = 1.0 + 0.2 * rc((nsrc, ntime, na, nchan, 2, 2))
+        dde_b = 1.0 + 0.2 * rc((nsrc, ntime, na, nchan, 2, 2))
+        die = 1.0 + 0.1 * rc((ntime, na, nchan, 2, 2))
+        for uvw in (uvw_ant, uvw_rnd):
+            for d1, d2 in ((dde, dde), (dde, dde_b)):
+                ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, d1, d2, die, None, die)
+                for env in ({}, {"AFR_DDE_ANT": "0"}, {"AFR_DDE_WS": "0"}):
+                    for k, v in env.items():
+                        monkeypatch.setenv(k, v)
+                    got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, d1, d2,
+                                                      die, None, die)
+                    for k in env:
+                        monkeypatch.delenv(k)
+                    assert_c128_close(got, ref)
+                    # the path that ran: antenna mode only for antenna-consistent uvw
+                    from codex_africanus_b200 import _lib
+                    path = _lib.lib().afr_last_fused_path()
+                    if "AFR_DDE_WS" in env:
+                        assert path == 4
+                    elif "AFR_DDE_ANT" in env or uvw is uvw_rnd:
+                        assert path == 3
+                    else:
+                        assert path == 2
+
+
+
 # ----------------------------------------------------------------------------- cross-kernel
 def test_fused_equals_unfused_composition_on_gpu(b200):
     """Size-independent property at a size the CPU oracle cannot reach: the fused kernel must

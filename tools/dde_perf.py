@@ -21,4 +21,6 @@ def timed(fn, reps=2):
     return min(ts)
 terms = float(nsrc) * uvw.shape[0] * nchan
 t = timed(lambda: rime.fused_predict_vis(d_lm, d_uvw, d_f, bright, d_t, d_a1, d_a2, dde, dde, die, None, die))
+from codex_africanus_b200 import _lib
+print("path", _lib.lib().afr_last_fused_path(), end=" ")
 print("fused DDE predict: %d src x %d rows x %d chan, DDE %.1f GB: %.3f s  %.1f Gterms/s  DDE read-once %.0f GB/s" % (nsrc, uvw.shape[0], nchan, dde.numel() * 16 / 1e9, t, terms / t / 1e9, dde.numel() * 16 / t / 1e9))
