@@ -42,7 +42,7 @@ struct DdeWsParams {
     int nchan;
     int same_dde;
 };
-size_t dde_ws_smem_bytes(int64_t nant);
+size_t dde_ws_smem_bytes(int64_t nant, int ft, bool ant);
 // per-timestep antenna coordinates from baseline uvw; ok[0] is cleared when the rows of any
 // timestep are not differences of per-antenna coordinates
 int launch_antenna_uvw(const double *uvw, const int32_t *ant1, const int32_t *ant2,

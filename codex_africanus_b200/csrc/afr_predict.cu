@@ -708,7 +708,7 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
             AFR_LAUNCH_OK();
             // warp-specialised kernel (afr_rime_ws.cu): TMA needs 16-byte aligned sources and
             // the three-stage antenna tile must fit in shared memory
-            const bool ws_ok = dde_ws_smem_bytes(nant) <= 220 * 1024 &&
+            const bool ws_ok = dde_ws_smem_bytes(nant, 4, false) <= 220 * 1024 &&
                                reinterpret_cast<uintptr_t>(dde1) % 16 == 0 &&
                                reinterpret_cast<uintptr_t>(dde2) % 16 == 0 &&
                                reinterpret_cast<uintptr_t>(brightness) % 16 == 0 &&

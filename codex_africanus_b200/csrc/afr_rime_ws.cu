@@ -5,9 +5,9 @@
 // (africanus/rime/predict.py:103-117,193-252 composed with rime/phase.py:20-63; the
 // composition is the one of rime/examples/predict.py:107-134.)
 //
-// A CTA owns one timestep, 512 rows (lane <-> row, 16 consumer warps) and 4 channels; the 64
-// accumulator doubles of a thread stay in registers for the whole source loop.  Per source
-// the 4 PRODUCER warps
+// A CTA owns one timestep and 512 rows x 4 channels (or 2048 rows x 1 channel in antenna
+// mode); lane <-> row, 16 consumer warps; the 64 accumulator doubles of a thread stay in
+// registers for the whole source loop.  Per source the 4 PRODUCER warps
 //   * fetch E[s,t,:,f0:f0+4] for ALL antennas (and B[s,f0:f0+4]) with 16-byte cp.async tracked
 //     by an mbarrier, into a padded shared-memory layout (antenna stride 272 B, so lanes
 //     reading consecutive antennas hit distinct banks and lanes reading the same antenna
@@ -35,11 +35,9 @@ namespace {
 
 constexpr int kConsWarps = 16;
 constexpr int kProdWarps = 4;
-constexpr int kRows = kConsWarps * 32;  // rows per CTA
-constexpr int kFT = 4;                  // channels per CTA (= per thread)
-constexpr int kNS = 3;                  // pipeline stages
-constexpr int kMatBytes = 64;           // one 2x2 complex128 matrix
-constexpr int kAntStride = kFT * kMatBytes + 16;  // padded shared-memory stride of an antenna
+constexpr int kConsThreads = kConsWarps * 32;
+constexpr int kNS = 3;         // pipeline stages
+constexpr int kMatBytes = 64;  // one 2x2 complex128 matrix
 constexpr int kNTP = kProdWarps * 32;
 
 struct Cd {
@@ -61,44 +59,61 @@ __device__ __forceinline__ void sts_c(unsigned char *p, Cd v) {
     *reinterpret_cast<double2 *>(p) = make_double2(v.re, v.im);
 }
 
-size_t stage_bytes(int na) {
-    // E2 (or E), E1 -> A (or A), B, per-row anchors + steps (ROW mode) / per-antenna (ANT mode)
-    return 2 * (size_t)na * kAntStride + kFT * kMatBytes + 2 * (size_t)kRows * 16;
+// shared-memory stride of one antenna: FT matrices + 16 bytes, so that lanes reading
+// consecutive antennas with LDS.128 fall into distinct bank groups (8 antennas cover the 32
+// banks) and lanes reading the same antenna broadcast
+__host__ __device__ constexpr int ant_stride(int ft) { return ft * kMatBytes + 16; }
+
+size_t stage_bytes(int na, int ft, bool ant) {
+    // E2 (or E) | E1 -> A (or A) | B | per-row anchors + steps (ROW mode only)
+    return 2 * (size_t)na * ant_stride(ft) + (size_t)ft * kMatBytes + (ant ? 0 : 2 * (size_t)kConsThreads * 16);
 }
 
-template <bool EXACT, bool ANT>
+// FT channels and RPT rows per consumer thread (FT * RPT = 4: 64 accumulator doubles).
+//   <4,1>: a CTA owns 512 rows x 4 channels -- the shape the per-row phasor recurrence needs;
+//   <1,4>: a CTA owns 2048 rows x 1 channel -- antenna mode: a MeerKAT timestep (2016
+//          baselines) is ONE row tile, so every E element is fetched, scaled and precombined
+//          exactly once per (source, time, channel) instead of once per 512-row tile.
+template <bool EXACT, bool ANT, int FT, int RPT>
 __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
     fused_dde_ws_kernel(const DdeWsParams p) {
+    static_assert(ANT || RPT == 1, "per-row phasors advance along the thread's channel run");
+    static_assert(FT == 1 || FT == 2 || FT == 4, "FT");
+    constexpr int AS = ant_stride(FT);
+    constexpr int kRows = kConsThreads * RPT;
+    constexpr int LFT = FT == 4 ? 2 : (FT == 2 ? 1 : 0);
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int na = (int)p.nant;
     const int t = blockIdx.y;
-    const int f0 = blockIdx.z * kFT;
+    const int f0 = blockIdx.z * FT;
     const long long rbeg = p.row_start[t] + (long long)blockIdx.x * kRows;
     const long long rend = min((long long)p.row_start[t + 1], rbeg + kRows);
     if (rbeg >= rend) return;
 
-    const size_t mat_region = (size_t)na * kAntStride;
-    const size_t stage = 2 * mat_region + kFT * kMatBytes + 2 * (size_t)kRows * 16;
+    const size_t mat_region = (size_t)na * AS;
+    const size_t stage = 2 * mat_region + FT * kMatBytes + (ANT ? 0 : 2 * (size_t)kConsThreads * 16);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kNS * stage);  // full, empty, landed [kNS]
-    double *fq = reinterpret_cast<double *>(bars + 3 * kNS);            // [kFT]
+    double *fq = reinterpret_cast<double *>(bars + 3 * kNS);            // [FT]
     auto e2_of = [&](int st) { return smem + st * stage; };
     auto a_of = [&](int st) { return smem + st * stage + mat_region; };
     auto b_of = [&](int st) { return smem + st * stage + 2 * mat_region; };
-    auto z_of = [&](int st) { return reinterpret_cast<C2<double> *>(smem + st * stage + 2 * mat_region + kFT * kMatBytes); };
-    auto d_of = [&](int st) { return z_of(st) + kRows; };
+    auto z_of = [&](int st) {
+        return reinterpret_cast<C2<double> *>(smem + st * stage + 2 * mat_region + FT * kMatBytes);
+    };
+    auto d_of = [&](int st) { return z_of(st) + kConsThreads; };
 
     if (tid == 0) {
         for (int i = 0; i < kNS; ++i) {
-            mbar_init(&bars[i], kNTP);                 // full: every producer thread
-            mbar_init(&bars[kNS + i], kConsWarps);     // empty: one lane per consumer warp
-            mbar_init(&bars[2 * kNS + i], kNTP);       // landed: the cp.async of every producer thread
+            mbar_init(&bars[i], kNTP);             // full: every producer thread
+            mbar_init(&bars[kNS + i], kConsWarps); // empty: one lane per consumer warp
+            mbar_init(&bars[2 * kNS + i], kNTP);   // landed: the cp.async of every producer thread
         }
     }
-    if (tid < kFT) fq[tid] = p.freq[min(f0 + tid, p.nchan - 1)];
+    if (tid < FT) fq[tid] = p.freq[min(f0 + tid, p.nchan - 1)];
     __syncthreads();
 
-    const int valid_ch = min(kFT, p.nchan - f0);
+    const int valid_ch = min(FT, p.nchan - f0);
     const long long nsrc = p.nsrc;
     double dnu = 0.0;
     if (p.nchan > 1) dnu = (p.freq[p.nchan - 1] - p.freq[0]) / (double)(p.nchan - 1);
@@ -108,24 +123,23 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
         // =============================== PRODUCERS ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
         const int ptid = tid - kConsWarps * 32;
-        // E[s,t,:,f0:f0+4] (both sides) and B[s,f0:f0+4] -> stage s % kNS by 16-byte cp.async
+        // E[s,t,:,f0:f0+FT] (both sides) and B[s,f0:f0+FT] -> stage s % kNS by 16-byte cp.async
         // spread over the 128 producer threads; completion is tracked by the stage's "landed"
         // mbarrier (cp.async.mbarrier.arrive.noinc, one arrival per producer thread).  TMA bulk
-        // copies were measured first: the tile is 65-129 pieces of 256 B per source, and one
+        // copies were measured first: the tile is 65-129 pieces of 64-256 B per source, and one
         // bulk copy per piece costs more issue time than the whole consume phase.
         const int gran_valid = valid_ch * 4;  // 16-byte granules per antenna that exist
+        const long long astride = (long long)p.nchan * kMatBytes;  // bytes between antennas
         auto issue = [&](long long s) {
             const int st = (int)(s % kNS);
-            const char *src2 = reinterpret_cast<const char *>(
-                p.dde2 + (((s * p.ntime + t) * p.nant) * (long long)p.nchan + f0) * 8);
-            const char *src1 = reinterpret_cast<const char *>(
-                p.dde1 + (((s * p.ntime + t) * p.nant) * (long long)p.nchan + f0) * 8);
-            const long long astride = (long long)p.nchan * kMatBytes;  // bytes between antennas
+            const long long base = (((s * p.ntime + t) * p.nant) * (long long)p.nchan + f0) * kMatBytes;
+            const char *src2 = reinterpret_cast<const char *>(p.dde2) + base;
+            const char *src1 = reinterpret_cast<const char *>(p.dde1) + base;
             const unsigned d2 = smem_addr(e2_of(st)), d1 = smem_addr(a_of(st));
-            for (int g = ptid; g < na * 16; g += kNTP) {
-                const int a = g >> 4, c = g & 15;
+            for (int g = ptid; g < na * FT * 4; g += kNTP) {
+                const int a = g >> (LFT + 2), c = g & (FT * 4 - 1);
                 if (c < gran_valid) {
-                    const unsigned doff = (unsigned)(a * kAntStride + c * 16);
+                    const unsigned doff = (unsigned)(a * AS + c * 16);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d2 + doff),
                                  "l"(src2 + a * astride + c * 16));
                     if (!p.same_dde)
@@ -136,19 +150,20 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
             if (ptid < gran_valid)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
                                  smem_addr(b_of(st)) + ptid * 16),
-                             "l"(reinterpret_cast<const char *>(p.bright + (s * (long long)p.nchan + f0) * 8) +
-                                 ptid * 16));
+                             "l"(reinterpret_cast<const char *>(p.bright) +
+                                 (s * (long long)p.nchan + f0) * kMatBytes + ptid * 16));
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(
                              smem_addr(&bars[2 * kNS + st]))
                          : "memory");
         };
         for (long long s = 0; s < kNS - 1 && s < nsrc; ++s) issue(s);
 
-        // ROW mode: rows of this thread (4 of the 512); ANT mode: antennas of this thread
-        double ru[kRows / kNTP], rv[kRows / kNTP], rw[kRows / kNTP];
+        // ROW mode: the 4 rows of this thread
+        constexpr int RP = kConsThreads / kNTP;
+        double ru[RP], rv[RP], rw[RP];
         if (!ANT) {
 #pragma unroll
-            for (int i = 0; i < kRows / kNTP; ++i) {
+            for (int i = 0; i < RP; ++i) {
                 const long long r = rbeg + ptid + i * kNTP;
                 const bool ok = r < rend;
                 ru[i] = ok ? p.uvw[3 * r] : 0.0;
@@ -156,6 +171,7 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
                 rw[i] = ok ? p.uvw[3 * r + 2] : 0.0;
             }
         }
+        const double *ant_t = ANT ? p.ant_uvw + (long long)t * p.nant * 3 : nullptr;
 
         for (long long s = 0; s < nsrc; ++s) {
             const int st = (int)(s % kNS);
@@ -163,11 +179,11 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
             // the stage must have been released by the consumers of source s - kNS
             if (s >= kNS) mbar_wait(&bars[kNS + st], (unsigned)(((s - kNS) / kNS) & 1));
             const double sl = p.lmn[3 * s], sm = p.lmn[3 * s + 1], sn = p.lmn[3 * s + 2];
-            C2<double> *zs = z_of(st), *ds = d_of(st);
             if (!ANT) {
                 // ---- per-row phasor anchors (phase argument rounded exactly as the reference)
+                C2<double> *zs = z_of(st), *ds = d_of(st);
 #pragma unroll
-                for (int i = 0; i < kRows / kNTP; ++i) {
+                for (int i = 0; i < RP; ++i) {
                     const int rl = ptid + i * kNTP;
                     const bool live = rbeg + rl < rend;
                     const double phi = __dmul_rn(p.cst, phase_dot(sl, sm, sn, ru[i], rv[i], rw[i], false));
@@ -180,46 +196,39 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
                 }
             }
             mbar_wait(&bars[2 * kNS + st], par);  // E (and B) of source s have landed
-            // ---- A_p = E1_p * B_s (ANT mode: times k_p; and E2_q <- k_q E2_q)
+            // ---- half-items (antenna a, channel fl, output row h): row h of A_a = E1_a * B_s,
+            // and in antenna mode row h of k_a A_a and of k_a E2_a
             const unsigned char *bsm = b_of(st);
             unsigned char *e2 = e2_of(st), *am = a_of(st);
-            for (int idx = ptid; idx < na * kFT; idx += kNTP) {
-                const int a = idx >> 2, fl = idx & 3;
-                const unsigned off = (unsigned)(a * kAntStride + fl * kMatBytes);
+            for (int idx = ptid; idx < na * FT * 2; idx += kNTP) {
+                const int h = idx & 1, fl = (idx >> 1) & (FT - 1), a = idx >> (LFT + 1);
+                const unsigned off = (unsigned)(a * AS + fl * kMatBytes + h * 32);
                 const unsigned char *e1 = (p.same_dde ? e2 : am) + off;
-                const Cd b0 = lds_c(bsm + fl * kMatBytes), b1 = lds_c(bsm + fl * kMatBytes + 16);
-                const Cd b2 = lds_c(bsm + fl * kMatBytes + 32), b3 = lds_c(bsm + fl * kMatBytes + 48);
-                const Cd x0 = lds_c(e1), x1 = lds_c(e1 + 16), x2 = lds_c(e1 + 32), x3 = lds_c(e1 + 48);
+                const unsigned char *bm = bsm + fl * kMatBytes;
+                const Cd b0 = lds_c(bm), b1 = lds_c(bm + 16), b2 = lds_c(bm + 32), b3 = lds_c(bm + 48);
+                const Cd x0 = lds_c(e1), x1 = lds_c(e1 + 16);
                 Cd m0 = cadd_(cmul_(x0, b0), cmul_(x1, b2));
                 Cd m1 = cadd_(cmul_(x0, b1), cmul_(x1, b3));
-                Cd m2 = cadd_(cmul_(x2, b0), cmul_(x3, b2));
-                Cd m3 = cadd_(cmul_(x2, b1), cmul_(x3, b3));
                 if (ANT) {
                     // antenna phasor k_a(f) = exp(i psi_a nu_f), psi_a from the antenna coordinates
-                    const double *ac = p.ant_uvw + ((long long)t * p.nant + a) * 3;
-                    const double psi = __dmul_rn(p.cst, phase_dot(sl, sm, sn, ac[0], ac[1], ac[2], false));
+                    const double psi = __dmul_rn(
+                        p.cst, phase_dot(sl, sm, sn, ant_t[3 * a], ant_t[3 * a + 1], ant_t[3 * a + 2], false));
                     const C2<double> kk = cis_fast(__dmul_rn(psi, fq[fl]));
                     const Cd k = {kk.re, kk.im};
-                    m0 = cmul_(k, m0), m1 = cmul_(k, m1), m2 = cmul_(k, m2), m3 = cmul_(k, m3);
+                    m0 = cmul_(k, m0), m1 = cmul_(k, m1);
                     if (p.same_dde) {
                         sts_c(e2 + off, cmul_(k, x0));
                         sts_c(e2 + off + 16, cmul_(k, x1));
-                        sts_c(e2 + off + 32, cmul_(k, x2));
-                        sts_c(e2 + off + 48, cmul_(k, x3));
                     } else {
                         sts_c(e2 + off, cmul_(k, lds_c(e2 + off)));
                         sts_c(e2 + off + 16, cmul_(k, lds_c(e2 + off + 16)));
-                        sts_c(e2 + off + 32, cmul_(k, lds_c(e2 + off + 32)));
-                        sts_c(e2 + off + 48, cmul_(k, lds_c(e2 + off + 48)));
                     }
                 }
                 sts_c(am + off, m0);
                 sts_c(am + off + 16, m1);
-                sts_c(am + off + 32, m2);
-                sts_c(am + off + 48, m3);
             }
             mbar_arrive(&bars[st]);  // full: anchors, A (and scaled E2) of source s are visible
-            // ---- next TMA: source s + kNS - 1 goes into the stage source s - 1 used
+            // ---- next copies: source s + kNS - 1 goes into the stage source s - 1 used
             if (s + kNS - 1 < nsrc) {
                 if (s >= 1) mbar_wait(&bars[kNS + (int)((s - 1) % kNS)], (unsigned)(((s - 1) / kNS) & 1));
                 issue(s + kNS - 1);
@@ -230,81 +239,96 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
 
     // ================================= CONSUMERS =================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
-    const int row_local = warp * 32 + lane;
-    const long long r = rbeg + row_local;
-    const bool row_ok = r < rend;
-    int a1 = 0, a2 = 0;
-    if (row_ok) {
-        a1 = p.ant1[r];
-        a2 = p.ant2[r];
+    // row k of this thread: rbeg + k * 512 + tid (lanes of a warp = 32 consecutive rows, so the
+    // antenna-2 gathers are conflict-free and the antenna-1 reads mostly broadcast)
+    unsigned offs[RPT];  // shared-memory offsets of (antenna1 | antenna2 << 16)
+    bool any_row = false;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const long long r = rbeg + k * kConsThreads + tid;
+        offs[k] = 0;
+        if (r < rend) {
+            offs[k] = (unsigned)(p.ant1[r] * AS) | ((unsigned)(p.ant2[r] * AS) << 16);
+            any_row = true;
+        }
     }
-    const unsigned off1 = (unsigned)(a1 * kAntStride), off2 = (unsigned)(a2 * kAntStride);
+    (void)any_row;
 
-    Cd acc[kFT][4];
+    Cd acc[RPT][FT][4];
 #pragma unroll
-    for (int j = 0; j < kFT; ++j)
+    for (int k = 0; k < RPT; ++k)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[j][c] = {0.0, 0.0};
+        for (int j = 0; j < FT; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[k][j][c] = {0.0, 0.0};
 
     for (long long s = 0; s < nsrc; ++s) {
         const int st = (int)(s % kNS);
         mbar_wait(&bars[st], (unsigned)((s / kNS) & 1));
-        const unsigned char *e2 = e2_of(st) + off2;
-        const unsigned char *am = a_of(st) + off1;
         Cd z = {1.0, 0.0}, zp = {1.0, 0.0}, d = {1.0, 0.0};
         double c2 = 2.0;
         if (!ANT) {
-            const C2<double> zz = z_of(st)[row_local], dd = d_of(st)[row_local];
+            const C2<double> zz = z_of(st)[tid], dd = d_of(st)[tid];
             z = {zz.re, zz.im};
             d = {dd.re, dd.im};
             c2 = d.re + d.re;
         }
 #pragma unroll
-        for (int j = 0; j < kFT; ++j) {
-            if (!ANT && EXACT) {
-                const C2<double> zz = cis_fast(__dmul_rn(d.re, fq[j]));
-                z = {zz.re, zz.im};
-            }
-            const Cd q0 = lds_c(e2 + j * kMatBytes), q1 = lds_c(e2 + j * kMatBytes + 16);
-            const Cd q2 = lds_c(e2 + j * kMatBytes + 32), q3 = lds_c(e2 + j * kMatBytes + 48);
+        for (int k = 0; k < RPT; ++k) {
+            const unsigned char *e2 = e2_of(st) + (offs[k] >> 16);
+            const unsigned char *am = a_of(st) + (offs[k] & 0xFFFFu);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {  // one output row of A * E^H at a time
-                const Cd x0 = lds_c(am + j * kMatBytes + 32 * h), x1 = lds_c(am + j * kMatBytes + 32 * h + 16);
-                const Cd m0 = cadd_(cmulc_(x0, q0), cmulc_(x1, q1));
-                const Cd m1 = cadd_(cmulc_(x0, q2), cmulc_(x1, q3));
-                if (ANT) {
-                    acc[j][2 * h] = cadd_(acc[j][2 * h], m0);
-                    acc[j][2 * h + 1] = cadd_(acc[j][2 * h + 1], m1);
-                } else {
-                    acc[j][2 * h] = cadd_(acc[j][2 * h], cmul_(z, m0));
-                    acc[j][2 * h + 1] = cadd_(acc[j][2 * h + 1], cmul_(z, m1));
+            for (int j = 0; j < FT; ++j) {
+                if (!ANT && EXACT) {
+                    const C2<double> zz = cis_fast(__dmul_rn(d.re, fq[j]));
+                    z = {zz.re, zz.im};
                 }
-            }
-            if (!ANT && !EXACT && j + 1 < kFT) {
-                // three-term recurrence z_{j+1} = 2 Re(d) z_j - z_{j-1} (first step: z * d)
-                Cd zn;
-                if (j == 0) {
-                    zn = cmul_(z, d);
-                } else {
-                    zn.re = fma(c2, z.re, -zp.re);
-                    zn.im = fma(c2, z.im, -zp.im);
+                const Cd q0 = lds_c(e2 + j * kMatBytes), q1 = lds_c(e2 + j * kMatBytes + 16);
+                const Cd q2 = lds_c(e2 + j * kMatBytes + 32), q3 = lds_c(e2 + j * kMatBytes + 48);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {  // one output row of A * E^H at a time
+                    const Cd x0 = lds_c(am + j * kMatBytes + 32 * h);
+                    const Cd x1 = lds_c(am + j * kMatBytes + 32 * h + 16);
+                    const Cd m0 = cadd_(cmulc_(x0, q0), cmulc_(x1, q1));
+                    const Cd m1 = cadd_(cmulc_(x0, q2), cmulc_(x1, q3));
+                    if (ANT) {
+                        acc[k][j][2 * h] = cadd_(acc[k][j][2 * h], m0);
+                        acc[k][j][2 * h + 1] = cadd_(acc[k][j][2 * h + 1], m1);
+                    } else {
+                        acc[k][j][2 * h] = cadd_(acc[k][j][2 * h], cmul_(z, m0));
+                        acc[k][j][2 * h + 1] = cadd_(acc[k][j][2 * h + 1], cmul_(z, m1));
+                    }
                 }
-                zp = z;
-                z = zn;
+                if (!ANT && !EXACT && j + 1 < FT) {
+                    // three-term recurrence z_{j+1} = 2 Re(d) z_j - z_{j-1} (first step: z * d)
+                    Cd zn;
+                    if (j == 0) {
+                        zn = cmul_(z, d);
+                    } else {
+                        zn.re = fma(c2, z.re, -zp.re);
+                        zn.im = fma(c2, z.im, -zp.im);
+                    }
+                    zp = z;
+                    z = zn;
+                }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[kNS + st]);
     }
 
-    if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < kFT; ++j) {
-            const int f = f0 + j;
-            if (f < p.nchan) {
-                double2 *o = reinterpret_cast<double2 *>(p.out + (r * p.nchan + f) * 8);
+    for (int k = 0; k < RPT; ++k) {
+        const long long r = rbeg + k * kConsThreads + tid;
+        if (r < rend) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) o[c] = make_double2(acc[j][c].re, acc[j][c].im);
+            for (int j = 0; j < FT; ++j) {
+                const int f = f0 + j;
+                if (f < p.nchan) {
+                    double2 *o = reinterpret_cast<double2 *>(p.out + (r * p.nchan + f) * 8);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) o[c] = make_double2(acc[k][j][c].re, acc[k][j][c].im);
+                }
             }
         }
     }
@@ -396,8 +420,8 @@ __global__ void __launch_bounds__(256) antenna_uvw_kernel(const double *uvw, con
 
 }  // namespace
 
-size_t dde_ws_smem_bytes(int64_t nant) {
-    return kNS * stage_bytes((int)nant) + 3 * kNS * sizeof(uint64_t) + kFT * sizeof(double);
+size_t dde_ws_smem_bytes(int64_t nant, int ft, bool ant) {
+    return kNS * stage_bytes((int)nant, ft, ant) + 3 * kNS * sizeof(uint64_t) + 4 * sizeof(double);
 }
 
 int launch_antenna_uvw(const double *uvw, const int32_t *ant1, const int32_t *ant2,
@@ -413,10 +437,15 @@ int launch_antenna_uvw(const double *uvw, const int32_t *ant1, const int32_t *an
 
 int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact, bool ant_mode,
                         cudaStream_t stream) {
-    const size_t smem = dde_ws_smem_bytes(p.nant);
-    dim3 grid((unsigned)((max_rows_per_time + kRows - 1) / kRows), (unsigned)p.ntime,
-              (unsigned)((p.nchan + kFT - 1) / kFT));
+    // antenna mode with more than one 512-row tile per timestep: 2048 rows x 1 channel per CTA
+    const bool wide_rows = ant_mode && max_rows_per_time > kConsThreads;
+    const int ft = wide_rows ? 1 : 4, rpt = wide_rows ? 4 : 1;
+    const size_t smem = dde_ws_smem_bytes(p.nant, ft, ant_mode);
+    const int rows = kConsThreads * rpt;
+    dim3 grid((unsigned)((max_rows_per_time + rows - 1) / rows), (unsigned)p.ntime,
+              (unsigned)((p.nchan + ft - 1) / ft));
     AFR_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "afr_predict_fused: grid too large");
+    AFR_REQUIRE((size_t)p.nant * ant_stride(ft) < 65536, "afr_predict_fused: too many antennas");
     const int threads = (kConsWarps + kProdWarps) * 32;
     auto go = [&](auto kern) -> int {
         cudaFuncAttributes attr;
@@ -429,12 +458,12 @@ int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact,
         return 0;
     };
     int rc;
-    if (ant_mode)
-        rc = go(fused_dde_ws_kernel<false, true>);  // antenna phasors are exact per channel
+    if (ant_mode)  // antenna phasors are evaluated per channel: any frequency array
+        rc = wide_rows ? go(fused_dde_ws_kernel<false, true, 1, 4>) : go(fused_dde_ws_kernel<false, true, 4, 1>);
     else if (exact)
-        rc = go(fused_dde_ws_kernel<true, false>);
+        rc = go(fused_dde_ws_kernel<true, false, 4, 1>);
     else
-        rc = go(fused_dde_ws_kernel<false, false>);
+        rc = go(fused_dde_ws_kernel<false, false, 4, 1>);
     if (rc) return rc;
     AFR_LAUNCH_OK();
     return 0;

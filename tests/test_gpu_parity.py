@@ -500,6 +500,18 @@ def test_fused_equals_unfused_composition_on_gpu(b200):
         ref = b200.rime.predict_vis(tiT, a1T, a2T, d1, coh, d2, die, bvis, die)
         got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, tiT, a1T, a2T, d1, d2, die, bvis, die)
         assert_c128_close(got.cpu().numpy(), ref.cpu().numpy())
+    # Measurement-Set-like uvw (differences of per-antenna coordinates, 8 km array): the DDE
+    # kernel folds the phasor into the antenna Jones (2048-row x 1-channel tiles)
+    from codex_africanus_b200 import _lib
+    antpos = rng.standard_normal((ntime, na, 3)) * 2500.0
+    uvw_a = T(antpos[ti, ant1] - antpos[ti, ant2])
+    Ka = b200.rime.phase_delay(lm, uvw_a, freq)
+    coh_a = torch.einsum("srf,sfij->srfij", Ka, bright).contiguous()
+    for d1, d2 in ((dde, dde), (dde, dde_b)):
+        ref = b200.rime.predict_vis(tiT, a1T, a2T, d1, coh_a, d2, die, bvis, die)
+        got = b200.rime.fused_predict_vis(lm, uvw_a, freq, bright, tiT, a1T, a2T, d1, d2, die, bvis, die)
+        assert _lib.lib().afr_last_fused_path() == 2
+        assert_c128_close(got.cpu().numpy(), ref.cpu().numpy())
     # rows not ordered by time take the gather kernel; same answer
     perm = torch.from_numpy(rng.permutation(nrow)).to(dev)
     ref = b200.rime.predict_vis(tiT, a1T, a2T, dde, coh, dde_b, die, bvis, die)
