@@ -34,6 +34,7 @@ struct DdeWsParams {
     const double *bright;      // (nsrc,nchan,2,2) complex128
     const int32_t *ant1, *ant2;
     const int32_t *row_start;  // (ntime+1) first row of each timestep (rows sorted by time)
+    const int32_t *perm;       // (nrow) rows ordered by (time, antenna tile)
     const double *dde1, *dde2; // (nsrc,ntime,nant,nchan,2,2) complex128
     const double *ant_uvw;     // (ntime,nant,3) per-antenna coordinates (antenna mode) or nullptr
     double *out;               // (nrow,nchan,2,2) complex128
@@ -49,6 +50,8 @@ int launch_antenna_uvw(const double *uvw, const int32_t *ant1, const int32_t *an
                        const int32_t *row_start, int64_t ntime, int64_t nant, const double *lmn,
                        int64_t nsrc, const double *freq, int64_t nchan, double cst, double *ant_uvw,
                        int *ok, cudaStream_t stream);
+int launch_row_tile_order(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2,
+                          int64_t nrow, int64_t ntime, int32_t *perm, cudaStream_t stream);
 int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact, bool ant_mode,
                         cudaStream_t stream);
 

@@ -731,8 +731,14 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
                 AFR_CUDA_OK(cudaMemcpyAsync(&hant, antok.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
             AFR_CUDA_OK(cudaStreamSynchronize(stream));
             const bool same = dde1 == dde2;
-            if (ws_ok && hflags[0] == 0 && hflags[1] > 0) {
+            if (ws_ok && hflags[0] == 0 && hflags[1] > 0 && nrow < (1LL << 31) && nant <= 1024) {
+                Scratch perm;
+                AFR_CUDA_OK(perm.alloc(sizeof(int32_t) * (size_t)nrow, stream));
+                rc = launch_row_tile_order(time_index, antenna1, antenna2, nrow, ntime,
+                                           (int32_t *)perm.ptr, stream);
+                if (rc) return rc;
                 DdeWsParams wp{};
+                wp.perm = (const int32_t *)perm.ptr;
                 wp.lmn = (const double *)lmn.ptr;
                 wp.uvw = uvw;
                 wp.freq = freq;

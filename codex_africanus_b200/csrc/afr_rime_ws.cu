@@ -28,6 +28,8 @@
 // being prepared, one in flight from L2/HBM.
 #include <algorithm>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "afr_dft.cuh"
 
 namespace afr {
@@ -164,8 +166,9 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
         if (!ANT) {
 #pragma unroll
             for (int i = 0; i < RP; ++i) {
-                const long long r = rbeg + ptid + i * kNTP;
-                const bool ok = r < rend;
+                const long long ri = rbeg + ptid + i * kNTP;
+                const bool ok = ri < rend;
+                const long long r = ok ? p.perm[ri] : 0;
                 ru[i] = ok ? p.uvw[3 * r] : 0.0;
                 rv[i] = ok ? p.uvw[3 * r + 1] : 0.0;
                 rw[i] = ok ? p.uvw[3 * r + 2] : 0.0;
@@ -239,20 +242,23 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
 
     // ================================= CONSUMERS =================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
-    // row k of this thread: rbeg + k * 512 + tid (lanes of a warp = 32 consecutive rows, so the
-    // antenna-2 gathers are conflict-free and the antenna-1 reads mostly broadcast)
+    // Row k of this thread: perm[rbeg + k * 512 + tid].  perm orders the rows of a timestep by
+    // (antenna1 / 4, antenna2 / 8) tiles, so the 32 lanes of a warp read <= 4 distinct A and
+    // <= 8 distinct E matrices in distinct bank groups: every LDS.128 is one wavefront
+    // instead of four (shared-memory bandwidth was the limit: l1tex 83 % busy before).
     unsigned offs[RPT];  // shared-memory offsets of (antenna1 | antenna2 << 16)
-    bool any_row = false;
+    int rowid[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
-        const long long r = rbeg + k * kConsThreads + tid;
+        const long long ri = rbeg + k * kConsThreads + tid;
         offs[k] = 0;
-        if (r < rend) {
+        rowid[k] = -1;
+        if (ri < rend) {
+            const int r = p.perm[ri];
+            rowid[k] = r;
             offs[k] = (unsigned)(p.ant1[r] * AS) | ((unsigned)(p.ant2[r] * AS) << 16);
-            any_row = true;
         }
     }
-    (void)any_row;
 
     Cd acc[RPT][FT][4];
 #pragma unroll
@@ -319,8 +325,8 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
 
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
-        const long long r = rbeg + k * kConsThreads + tid;
-        if (r < rend) {
+        const long long r = rowid[k];
+        if (r >= 0) {
 #pragma unroll
             for (int j = 0; j < FT; ++j) {
                 const int f = f0 + j;
@@ -418,7 +424,45 @@ __global__ void __launch_bounds__(256) antenna_uvw_kernel(const double *uvw, con
     if (!good) atomicAnd(ok, 0);
 }
 
+// sort key of a row: time | antenna tile (a1/4, a2/8) | position inside the tile
+__global__ void row_keys_kernel(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2,
+                                long long nrow, unsigned long long *keys, int32_t *rows) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= nrow) return;
+    const unsigned a1 = (unsigned)ant1[r] & 1023u, a2 = (unsigned)ant2[r] & 1023u;
+    keys[r] = ((unsigned long long)(unsigned)time_index[r] << 20) | ((a1 >> 2) << 12) | ((a2 >> 3) << 5) |
+              ((a1 & 3u) << 3) | (a2 & 7u);
+    rows[r] = (int32_t)r;
+}
+
 }  // namespace
+
+// perm (nrow): the rows ordered by (time, antenna tile); rows of one timestep stay contiguous
+int launch_row_tile_order(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2,
+                          int64_t nrow, int64_t ntime, int32_t *perm, cudaStream_t stream) {
+    if (nrow <= 0) return 0;
+    Scratch keys_in, keys_out, rows_in, tmp;
+    AFR_CUDA_OK(keys_in.alloc(sizeof(unsigned long long) * (size_t)nrow, stream));
+    AFR_CUDA_OK(keys_out.alloc(sizeof(unsigned long long) * (size_t)nrow, stream));
+    AFR_CUDA_OK(rows_in.alloc(sizeof(int32_t) * (size_t)nrow, stream));
+    row_keys_kernel<<<(unsigned)((nrow + 255) / 256), 256, 0, stream>>>(
+        time_index, ant1, ant2, nrow, (unsigned long long *)keys_in.ptr, (int32_t *)rows_in.ptr);
+    AFR_LAUNCH_OK();
+    int tbits = 1;
+    while ((1LL << tbits) < ntime && tbits < 43) ++tbits;
+    size_t tmp_bytes = 0;
+    AFR_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long *)keys_in.ptr,
+                                                (unsigned long long *)keys_out.ptr,
+                                                (const int32_t *)rows_in.ptr, perm, (int)nrow, 0,
+                                                20 + tbits, stream));
+    AFR_CUDA_OK(tmp.alloc(tmp_bytes, stream));
+    AFR_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, (const unsigned long long *)keys_in.ptr,
+                                                (unsigned long long *)keys_out.ptr,
+                                                (const int32_t *)rows_in.ptr, perm, (int)nrow, 0,
+                                                20 + tbits, stream));
+    note_launch(3);  // cub's histogram / onesweep kernels
+    return 0;
+}
 
 size_t dde_ws_smem_bytes(int64_t nant, int ft, bool ant) {
     return kNS * stage_bytes((int)nant, ft, ant) + 3 * kNS * sizeof(uint64_t) + 4 * sizeof(double);
