@@ -158,7 +158,21 @@ def run(dev, fp64_peak):
          "dde_GB_per_s_gathered": 128 * terms3 / t / 1e9,
          "note": "configs[2] slice: 64 ant, 1 timestep, 4096 chan, %d src; DDE %.2f GB" % (
              nsrc3, dde.numel() * 16 / 1e9)}
+    from codex_africanus_b200 import _lib as _l
+    e["kernel"] = {2: "fused_dde_ws_kernel, antenna-phasor mode (2048 rows x 1 chan per CTA)",
+                   3: "fused_dde_ws_kernel, per-row phasor mode", 4: "fused_dde_tiled_kernel",
+                   5: "fused_dde_kernel (gather)"}.get(_l.lib().afr_last_fused_path(), "?")
     res["fused_dde_predict_c128_cfg3_slice"] = e
+    # the same slice with the antenna decomposition disabled (what arbitrary uvw get)
+    os.environ["AFR_DDE_ANT"] = "0"
+    try:
+        t = _timed(lambda: rime.fused_predict_vis(d_lm3, d_uvw[:rows3], d_f3, d_b3, tz, d_a1[:rows3],
+                                                  d_a2[:rows3], dde, dde, d_die3, None, d_die3))
+    finally:
+        del os.environ["AFR_DDE_ANT"]
+    res["fused_dde_predict_c128_cfg3_slice_row_phasors"] = {
+        "Gterms_per_s": terms3 / t / 1e9, "ms": 1e3 * t, "terms": terms3, "flop_per_term": 95,
+        "frac_of_fp64_fma_peak": 95 * terms3 / t / fp64_peak}
     return res
 
 
