@@ -31,4 +31,17 @@ rime.predict_vis(ti, ant1, ant2, dde, np.einsum("srf,sfij->srfij", K, bright), d
 beam = rc((9, 9, 5, 2, 2))
 rime.beam_cube_dde(beam, np.array([[-0.03, 0.03], [-0.03, 0.03]]), np.linspace(0.8e9, 1.8e9, 5), lm,
                    rng.uniform(-1, 1, (ntime, na)), np.zeros((ntime, na, nchan, 2)), np.ones((na, nchan, 2)), freq)
+# warp-specialised DDE kernel: antenna-phasor mode (uvw = differences of antenna coordinates),
+# per-row mode, E1 != E2, non-uniform channels; TMA-staged adjoint with 16-sample flag groups
+antpos = rng.standard_normal((ntime, na, 3)) * 1500.0
+uvw_a = antpos[ti, ant1] - antpos[ti, ant2]
+dde_b = rc((nsrc, ntime, na, nchan, 2, 2))
+rime.fused_predict_vis(lm, uvw_a, freq, bright, ti, ant1, ant2, dde, dde_b, die, None, die)
+rime.fused_predict_vis(lm, uvw_a, freq, bright, ti, ant1, ant2, dde, dde)
+rime.fused_predict_vis(lm, uvw, np.sort(rng.uniform(1e9, 2e9, nchan)), bright, ti, ant1, ant2, dde, dde_b)
+freq48 = np.linspace(0.856e9, 1.712e9, 48)
+for ncorr in (1, 2, 4):
+    v = rc((nrow, 48, ncorr))
+    dft.vis_to_im(v, uvw, lm, freq48, rng.random(v.shape) < 0.1)
+    dft.vis_to_im(v, uvw, lm, freq48, np.zeros(v.shape, bool))
 print("sanitize target done")
