@@ -43,6 +43,8 @@ PROTOTYPES = {
     "afr_predict_fused": (_int, [_vp] * 12 + [_i64] * 6 + [_int, _int, _int, _int, _vp, _vp]),
     "afr_beam_cube_dde": (_int, [_vp] * 8 + [_i64] * 8 + [_int, _vp, _vp]),
     "afr_freq_grid_interp": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "afr_wsclean_spectra": (_int, [_vp] * 5 + [_i64] * 3 + [_vp, _vp]),
+    "afr_wsclean_predict": (_int, [_vp] * 9 + [_i64] * 5 + [_int, _vp, _vp]),
 }
 
 _lock = threading.Lock()

@@ -153,6 +153,23 @@ int afr_beam_cube_dde(const void *beam, const double *beam_lm_extents,
 int afr_freq_grid_interp(const double *freq, const double *beam_freq_map, int64_t nchan,
                          int64_t nud, double *freq_data, void *stream);
 
+/* ---- africanus.rime.wsclean_predict (africanus/rime/wsclean_predict.py:11-116) and
+ * africanus.model.wsclean.spectra (africanus/model/wsclean/spec_model.py:76-124) ---------- */
+/* out (nsrc,nchan) float64 = I + sum_c coeffs[c] (nu/ref - 1)^(c+1), or, where log_poly[s],
+ * I exp(sum_c coeffs[c] log(nu/ref)^(c+1)).  flux (nsrc,), coeffs (nsrc,ncoeffs),
+ * log_poly (nsrc,) uint8, ref_freq (nsrc,), freq (nchan,). */
+int afr_wsclean_spectra(const double *flux, const double *coeffs, const uint8_t *log_poly,
+                        const double *ref_freq, const double *freq, int64_t nsrc, int64_t ncoeffs,
+                        int64_t nchan, double *out, void *stream);
+/* out (nrow,nchan,1) complex128.  is_gauss (nsrc,) uint8: 0 = "POINT", 1 = "GAUSSIAN";
+ * gauss_shape (nsrc,3) = (emaj, emin, angle); ngauss = number of GAUSSIAN sources (0 skips the
+ * taper kernel); chan_mode as in afr_im_to_vis.  Phase sign +2pi/c, n not clamped. */
+int afr_wsclean_predict(const double *uvw, const double *lm, const uint8_t *is_gauss,
+                        const double *gauss_shape, const double *flux, const double *coeffs,
+                        const uint8_t *log_poly, const double *ref_freq, const double *freq,
+                        int64_t nsrc, int64_t ncoeffs, int64_t nrow, int64_t nchan, int64_t ngauss,
+                        int chan_mode, void *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

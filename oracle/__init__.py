@@ -19,6 +19,8 @@ Reference entry points restated (paths relative to /root/reference/):
   im_to_vis        africanus/dft/kernels.py:14-69
   vis_to_im        africanus/dft/kernels.py:72-148
   fused_predict    composition in africanus/rime/examples/predict.py:107-134,490,522-527
+  wsclean_spectra  africanus/model/wsclean/spec_model.py:76-124
+  wsclean_predict  africanus/rime/wsclean_predict.py:11-116
 """
 import ctypes
 import os
@@ -291,5 +293,31 @@ def fused_predict(lm, uvw, frequency, brightness, time_index, antenna1, antenna2
         _p(cv[0]), _p(cv[2]), _p(cv[3]), _p(cv[4]), _p(cv[5]),
         _i64(nsrc), _i64(nrow), _i64(ntime), _i64(nant), _i64(nchan), _i64(ncorr),
         _int(mode), _int(sign), _p(out))
+    assert rc == 0, rc
+    return out
+
+
+# ---------------------------------------------------------------------------
+def wsclean_spectra(flux, coeffs, log_poly, ref_freq, frequency):
+    flux, coeffs, ref_freq, frequency = (_as(a, np.float64) for a in (flux, coeffs, ref_freq, frequency))
+    ns, nf = flux.shape[0], frequency.shape[0]
+    lp = np.ascontiguousarray(np.broadcast_to(np.asarray(log_poly, dtype=np.uint8), (ns,)))
+    out = np.zeros((ns, nf), np.float64)
+    rc = lib().orc_wsclean_spectra(_p(flux), _p(coeffs), _p(lp), _p(ref_freq), _p(frequency),
+                                   _i64(ns), _i64(coeffs.shape[1]), _i64(nf), _p(out))
+    assert rc == 0, rc
+    return out
+
+
+def wsclean_predict(uvw, lm, source_type, flux, coeffs, log_poly, ref_freq, gauss_shape, frequency):
+    spectrum = wsclean_spectra(flux, coeffs, log_poly, ref_freq, frequency)
+    st = np.asarray(source_type)
+    if not np.all((st == "POINT") | (st == "GAUSSIAN")):
+        raise ValueError("source_type must be POINT or GAUSSIAN")
+    isg = np.ascontiguousarray((st == "GAUSSIAN").astype(np.uint8))
+    uvw, lm, gs, fr = (_as(a, np.float64) for a in (uvw, lm, gauss_shape, frequency))
+    out = np.zeros((uvw.shape[0], fr.shape[0], 1), np.complex128)
+    rc = lib().orc_wsclean_predict(_p(uvw), _p(lm), _p(isg), _p(gs), _p(fr), _p(spectrum),
+                                   _i64(lm.shape[0]), _i64(uvw.shape[0]), _i64(fr.shape[0]), _p(out))
     assert rc == 0, rc
     return out

@@ -215,9 +215,70 @@ def gen_fused():
     save("fused_predict", **out)
 
 
+def gen_wsclean():
+    """africanus.rime.wsclean_predict (rime/wsclean_predict.py) + model.wsclean.spectra:
+    (i) the reference's own test case (rime/tests/test_wsclean_predict.py:26-61, seed 42);
+    (ii) a MeerKAT-like case: arcminute Gaussians, kilometre baselines, mixed log/ordinary
+    polynomials, boolean and per-source log_poly."""
+    from africanus.model.wsclean.spec_model import spectra
+    from africanus.rime.wsclean_predict import wsclean_predict
+
+    out = {}
+    # (i) reference test inputs
+    rs = np.random.RandomState(42)
+    row, src, chan = 10, 21, 5
+    source_sel = rs.randint(0, 2, src).astype(np.bool_)
+    source_type = np.where(source_sel, "POINT", "GAUSSIAN")
+    gauss_shape = rs.normal(size=(src, 3))
+    uvw = rs.normal(size=(row, 3))
+    lm = rs.normal(size=(src, 2)) * 1e-5
+    flux = rs.normal(size=src)
+    coeffs = rs.normal(size=(src, 2))
+    log_poly = rs.randint(0, 2, src, dtype=np.bool_)
+    flux[log_poly] = np.abs(flux[log_poly])
+    coeffs[log_poly] = np.abs(coeffs[log_poly])
+    freq = np.linspace(0.856e9, 2 * 0.856e9, chan)
+    ref_freq = np.full(src, freq[freq.shape[0] // 2])
+    out.update(t_uvw=uvw, t_lm=lm, t_source_type=source_type, t_flux=flux, t_coeffs=coeffs,
+               t_log_poly=log_poly, t_ref_freq=ref_freq, t_gauss_shape=gauss_shape, t_freq=freq,
+               t_spectra=spectra(flux, coeffs, log_poly, ref_freq, freq),
+               t_vis=wsclean_predict(uvw, lm, source_type, flux, coeffs, log_poly, ref_freq,
+                                     gauss_shape, freq))
+    # (ii) MeerKAT-like
+    rng = np.random.default_rng(909)
+    row, src, chan = 57, 31, 48
+    source_type = np.where(rng.random(src) < 0.6, "POINT", "GAUSSIAN")
+    arcsec = np.pi / 180.0 / 3600.0
+    gauss_shape = np.stack([rng.uniform(20, 120, src) * arcsec, rng.uniform(5, 20, src) * arcsec,
+                            rng.uniform(0, np.pi, src)], axis=1)
+    gauss_shape[3, 0] = 0.0  # emaj == 0 branch (wsclean_predict.py:52)
+    uvw = rng.standard_normal((row, 3)) * 1500.0
+    lm = rng.uniform(-0.02, 0.02, (src, 2))
+    flux = np.abs(rng.standard_normal(src)) + 0.1
+    coeffs = rng.standard_normal((src, 3)) * 0.3
+    log_poly = rng.random(src) < 0.5
+    freq = np.linspace(0.856e9, 1.712e9, chan)
+    ref_freq = rng.uniform(0.9e9, 1.6e9, src)
+    out.update(m_uvw=uvw, m_lm=lm, m_source_type=source_type, m_flux=flux, m_coeffs=coeffs,
+               m_log_poly=log_poly, m_ref_freq=ref_freq, m_gauss_shape=gauss_shape, m_freq=freq,
+               m_spectra=spectra(flux, coeffs, log_poly, ref_freq, freq),
+               m_vis=wsclean_predict(uvw, lm, source_type, flux, coeffs, log_poly, ref_freq,
+                                     gauss_shape, freq),
+               m_vis_logpoly_true=wsclean_predict(uvw, lm, source_type, flux, coeffs, True, ref_freq,
+                                                  gauss_shape, freq),
+               m_vis_logpoly_false=wsclean_predict(uvw, lm, source_type, flux, coeffs, False,
+                                                   ref_freq, gauss_shape, freq))
+    freq_nu = np.sort(rng.uniform(0.856e9, 1.712e9, 13))  # non-uniform channels
+    out.update(m_freq_nu=freq_nu,
+               m_vis_nu=wsclean_predict(uvw, lm, source_type, flux, coeffs, log_poly, ref_freq,
+                                        gauss_shape, freq_nu))
+    save("wsclean", **out)
+
+
 if __name__ == "__main__":
     gen_phase()
     gen_dft()
     gen_predict()
     gen_beam()
     gen_fused()
+    gen_wsclean()

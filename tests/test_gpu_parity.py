@@ -463,6 +463,68 @@ def test_fused_dde_ws_modes_vs_oracle(b200, oracle, monkeypatch):
 
 
 
+# ----------------------------------------------------------------------------- wsclean_predict
+def test_wsclean_predict_golden(b200, golden):
+    """africanus.rime.wsclean_predict / model.wsclean.spectra against the reference's outputs:
+    its own test inputs (seed 42) and a MeerKAT-like POINT/GAUSSIAN mix, scalar and per-source
+    log_poly, non-uniform channels."""
+    g = golden("wsclean")
+    for pre in ("t_", "m_"):
+        args = [g[pre + k] for k in ("flux", "coeffs", "log_poly", "ref_freq", "freq")]
+        assert_c128_close(b200.rime.wsclean_spectra(*args), g[pre + "spectra"])
+        got = b200.rime.wsclean_predict(g[pre + "uvw"], g[pre + "lm"], g[pre + "source_type"], g[pre + "flux"],
+                                        g[pre + "coeffs"], g[pre + "log_poly"], g[pre + "ref_freq"],
+                                        g[pre + "gauss_shape"], g[pre + "freq"])
+        assert got.shape == g[pre + "vis"].shape and got.dtype == np.complex128
+        assert_c128_close(got, g[pre + "vis"])
+    margs = [g["m_" + k] for k in ("uvw", "lm", "source_type", "flux", "coeffs")]
+    for lp, key in ((True, "m_vis_logpoly_true"), (False, "m_vis_logpoly_false")):
+        got = b200.rime.wsclean_predict(*margs, lp, g["m_ref_freq"], g["m_gauss_shape"], g["m_freq"])
+        assert_c128_close(got, g[key])
+    got = b200.rime.wsclean_predict(*margs, g["m_log_poly"], g["m_ref_freq"], g["m_gauss_shape"],
+                                    g["m_freq_nu"])
+    assert_c128_close(got, g["m_vis_nu"])
+    with pytest.raises(ValueError):
+        b200.rime.wsclean_predict(*margs[:2], np.array(["DISK"] * g["m_lm"].shape[0]), *margs[3:],
+                                  True, g["m_ref_freq"], g["m_gauss_shape"], g["m_freq"])
+
+
+def test_wsclean_predict_vs_oracle(b200, oracle):
+    """larger seeded case: 500 sources (30 % Gaussian), 700 rows, 96 channels; torch inputs;
+    only POINT / only GAUSSIAN; complex64 result for float32 inputs."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    nsrc, nrow, nchan = 500, 700, 96
+    st = np.where(rng.random(nsrc) < 0.7, "POINT", "GAUSSIAN")
+    arcsec = np.pi / 180 / 3600
+    gs = np.stack([rng.uniform(10, 90, nsrc) * arcsec, rng.uniform(3, 10, nsrc) * arcsec,
+                   rng.uniform(0, np.pi, nsrc)], axis=1)
+    uvw = rng.standard_normal((nrow, 3)) * 2000.0
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    flux = np.abs(rng.standard_normal(nsrc)) + 0.1
+    coeffs = rng.standard_normal((nsrc, 2)) * 0.2
+    lp = rng.random(nsrc) < 0.5
+    freq = np.linspace(0.856e9, 1.712e9, nchan)
+    rf = np.full(nsrc, 1.284e9)
+    ref = oracle.wsclean_predict(uvw, lm, st, flux, coeffs, lp, rf, gs, freq)
+    assert_c128_close(b200.rime.wsclean_predict(uvw, lm, st, flux, coeffs, lp, rf, gs, freq), ref)
+    dev = torch.device("cuda:0")
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    got = b200.rime.wsclean_predict(T(uvw), T(lm), st, T(flux), T(coeffs), lp, T(rf), T(gs), T(freq))
+    assert isinstance(got, torch.Tensor)
+    assert_c128_close(got.cpu().numpy(), ref)
+    for kind in ("POINT", "GAUSSIAN"):
+        st1 = np.full(nsrc, kind)
+        assert_c128_close(b200.rime.wsclean_predict(uvw, lm, st1, flux, coeffs, lp, rf, gs, freq),
+                          oracle.wsclean_predict(uvw, lm, st1, flux, coeffs, lp, rf, gs, freq))
+    f32 = np.float32
+    got = b200.rime.wsclean_predict(*(a.astype(f32) for a in (uvw, lm)), st, flux.astype(f32),
+                                    coeffs.astype(f32), lp, rf.astype(f32), gs, freq.astype(f32))
+    assert got.dtype == np.complex64
+
+
+
 # ----------------------------------------------------------------------------- cross-kernel
 def test_fused_equals_unfused_composition_on_gpu(b200):
     """Size-independent property at a size the CPU oracle cannot reach: the fused kernel must

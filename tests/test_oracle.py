@@ -303,3 +303,48 @@ def test_fused_predict_golden(oracle, golden):
             got = oracle.fused_predict(lm, uvw, freq, br, ti, a1, a2, dde, dde, die, bvis, die,
                                        convention=conv)
             assert_array_equal(got, g["full_" + key])
+
+
+# ----------------------------------------------------------------------------- wsclean
+def test_wsclean_spectra_and_predict_golden(golden, oracle):
+    """africanus.model.wsclean.spectra + africanus.rime.wsclean_predict: the reference's own test
+    inputs (rime/tests/test_wsclean_predict.py:26-61) and a MeerKAT-like mixed POINT/GAUSSIAN
+    model, bit-exact."""
+    g = golden("wsclean")
+    for pre in ("t_", "m_"):
+        args = [g[pre + k] for k in ("flux", "coeffs", "log_poly", "ref_freq", "freq")]
+        assert np.array_equal(oracle.wsclean_spectra(*args), g[pre + "spectra"])
+        got = oracle.wsclean_predict(g[pre + "uvw"], g[pre + "lm"], g[pre + "source_type"], g[pre + "flux"],
+                                     g[pre + "coeffs"], g[pre + "log_poly"], g[pre + "ref_freq"],
+                                     g[pre + "gauss_shape"], g[pre + "freq"])
+        assert np.array_equal(got, g[pre + "vis"])
+    for lp, key in ((True, "m_vis_logpoly_true"), (False, "m_vis_logpoly_false")):
+        got = oracle.wsclean_predict(g["m_uvw"], g["m_lm"], g["m_source_type"], g["m_flux"], g["m_coeffs"],
+                                     lp, g["m_ref_freq"], g["m_gauss_shape"], g["m_freq"])
+        assert np.array_equal(got, g[key])
+
+
+def test_wsclean_predict_known_answer(golden, oracle):
+    """The reference test's independent composition: einsum(shape, phase_delay(casa), spectra)
+    with shape = 1 for POINT sources (rime/tests/test_wsclean_predict.py:52-61)."""
+    g = golden("wsclean")
+    uvw, lm, freq, gs = g["t_uvw"], g["t_lm"], g["t_freq"], g["t_gauss_shape"]
+    phase = oracle.phase_delay(lm, uvw, freq, convention="casa")
+    spectrum = oracle.wsclean_spectra(g["t_flux"], g["t_coeffs"], g["t_log_poly"], g["t_ref_freq"], freq)
+    # africanus/model/shape/gaussian_shape.py:31-63
+    fwhminv = 1.0 / (2.0 * np.sqrt(2.0 * np.log(2.0)))
+    scale = fwhminv * np.sqrt(2.0) * np.pi / 2.99792458e8
+    emaj, emin, ang = gs[:, 0], gs[:, 1], gs[:, 2]
+    el, em = emaj * np.sin(ang), emaj * np.cos(ang)
+    er = emin / np.where(emaj == 0.0, 1.0, emaj)
+    u, v = uvw[:, 0], uvw[:, 1]
+    u1 = (u[None, :] * em[:, None] - v[None, :] * el[:, None]) * er[:, None]
+    v1 = u[None, :] * el[:, None] + v[None, :] * em[:, None]
+    sf = freq * scale
+    shape = np.exp(-((u1[:, :, None] * sf) ** 2 + (v1[:, :, None] * sf) ** 2))
+    shape[g["t_source_type"] == "POINT"] = 1.0
+    ref = np.einsum("srf,srf,sf->rf", shape, phase, spectrum)[:, :, None]
+    np.testing.assert_almost_equal(ref, g["t_vis"])
+    got = oracle.wsclean_predict(uvw, lm, g["t_source_type"], g["t_flux"], g["t_coeffs"], g["t_log_poly"],
+                                 g["t_ref_freq"], gs, freq)
+    np.testing.assert_almost_equal(ref, got)
