@@ -130,6 +130,31 @@ def run(dev, fp64_peak):
              note="64 B/term load-bound")
     del coh
 
+    # ---- wsclean_predict: 2000 components, 20 % Gaussian, 100 timesteps x 256 chan
+    nsw = 2000
+    st = np.where(rng.random(nsw) < 0.8, "POINT", "GAUSSIAN")
+    arcsec = np.pi / 180.0 / 3600.0
+    gshape = np.stack([rng.uniform(10, 90, nsw) * arcsec, rng.uniform(3, 10, nsw) * arcsec,
+                       rng.uniform(0, np.pi, nsw)], axis=1)
+    lmw = synth.sky_lm(nsw, rng)
+    fluxw = np.abs(rng.standard_normal(nsw)) + 0.1
+    coefw = rng.standard_normal((nsw, 2)) * 0.2
+    lpw = rng.random(nsw) < 0.5
+    rfw = np.full(nsw, 1.284e9)
+    freqw = synth.frequencies(256)
+    rows_w = min(uvw.shape[0], 100 * (uvw.shape[0] // ntime))
+    wargs = (d_uvw[:rows_w], T(lmw), st, T(fluxw), T(coefw), lpw, T(rfw), T(gshape), T(freqw))
+    t = _timed(lambda: rime.wsclean_predict(*wargs))
+    terms_w = float(nsw) * rows_w * 256
+    res["wsclean_predict_c128_2000src_20pct_gauss"] = {
+        "Gterms_per_s": terms_w / t / 1e9, "ms": 1e3 * t, "terms": terms_w,
+        "note": "POINT sources on the phasor-stream kernel, GAUSSIAN ones one sincos + exp per term"}
+    st_p = np.full(nsw, "POINT")
+    t = _timed(lambda: rime.wsclean_predict(wargs[0], wargs[1], st_p, *wargs[3:]))
+    res["wsclean_predict_c128_2000src_points_only"] = {
+        "Gterms_per_s": terms_w / t / 1e9, "ms": 1e3 * t, "terms": terms_w, "flop_per_term": 11,
+        "frac_of_fp64_fma_peak": 11 * terms_w / t / fp64_peak}
+
     # ---- configs[2] slice: beam_cube_dde -> fused DIE+DDE predict, 4096 chan, 1 timestep
     nchan3, nsrc3 = 4096, 96
     freq3 = synth.frequencies(nchan3)
