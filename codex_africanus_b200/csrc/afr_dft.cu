@@ -517,7 +517,10 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
 // ---------------------------------------------------------------------------
 constexpr int kProducerWarps = 4;
 
-template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NWC, bool EXACT, int CREGS, int PREGS>
+// FULLW: the CTA's 16 consumer warps are 16 channel runs of the same 32 owners (nck == NWC,
+// the shape of every launch with >= 16 * CH channels): strides become immediates.
+template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NWC, bool EXACT, int CREGS, int PREGS,
+          bool FULLW>
 __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
     phasor_stream_ws_kernel(const DftParams p) {
     constexpr int NTP = kProducerWarps * 32;  // producer threads
@@ -530,7 +533,7 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nck = p.nck, yt = p.yt;
+    const int nck = FULLW ? NWC : p.nck, yt = p.yt;
     const int xgw = (NWC / nck) * 32;
     const int ft = nck * CH;
     const int cta_f0 = blockIdx.y * ft;
@@ -1044,8 +1047,13 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
             kern<<<grid, threads, smem_ws, stream>>>(p);
             return 0;
         };
-        int rc = exact ? launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, true, CREGS, PREGS>)
-                       : launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS>);
+        int rc;
+        if (exact)
+            rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, true, CREGS, PREGS, false>);
+        else if (nck == NW)
+            rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, true>);
+        else
+            rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, false>);
         if (rc) return rc;
       }
     }
