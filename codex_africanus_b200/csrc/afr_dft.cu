@@ -533,7 +533,7 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nck = FULLW ? NWC : p.nck, yt = p.yt;
+    const int nck = FULLW ? NWC : p.nck, yt = FULLW ? 8 : p.yt;
     const int xgw = (NWC / nck) * 32;
     const int ft = nck * CH;
     const int cta_f0 = blockIdx.y * ft;
@@ -822,14 +822,24 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
             const CA *pd = dstp + x_local;
             const ACC *pw = wt + fo * NV;
             const int w_step = ft * NV;
+            // Tile shape known at compile time (8 y items): every offset becomes an immediate.
+            // Measured: +4 % for the forward ncorr >= 2 variants; ptxas spills in the others
+            // (ncorr = 1: 2.80 vs 2.87 Tterm/s), which keep the rolled loop.
+            if constexpr (FULLW && !ADJ && NCORR >= 2) {
+#pragma unroll
+                for (int yl = 0; yl < 8; ++yl)
+                    consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, pa[yl * NWC * 32], pd[yl * 32],
+                                                            pw + yl * (NWC * CH * NV));
+            } else {
 #pragma unroll 1
-            for (int yl = 0; yl < yt; ++yl) {
-                const CA z = *pa;
-                const CA d = *pd;
-                consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, z, d, pw);
-                pa += NWC * 32;  // nck * xgw
-                pd += xgw;
-                pw += w_step;
+                for (int yl = 0; yl < yt; ++yl) {
+                    const CA z = *pa;
+                    const CA d = *pd;
+                    consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, z, d, pw);
+                    pa += NWC * 32;  // nck * xgw
+                    pd += xgw;
+                    pw += w_step;
+                }
             }
         }
         __syncwarp();
@@ -1050,7 +1060,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
         int rc;
         if (exact)
             rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, true, CREGS, PREGS, false>);
-        else if (nck == NW)
+        else if (nck == NW && yt == 8)
             rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, true>);
         else
             rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, false>);
