@@ -79,6 +79,22 @@ def run(dev, fp64_peak):
     compute_entry("im_to_vis_c128_ncorr4_cfg2_25steps", t, terms / 4, 23, fp64_peak)
     del vis, flags, d_img4, d_img
 
+    # ---- configs[4] slice: vis_to_im onto a 1024 x 1024 image (4" cells), 64 chan, 2 timesteps
+    npix = 1024
+    cell = 4.0 / 3600.0 * np.pi / 180.0
+    gl = (np.arange(npix) - npix // 2) * cell
+    lm5 = np.stack(np.meshgrid(gl, gl, indexing="ij"), axis=-1).reshape(-1, 2)
+    rows5 = 2 * (uvw.shape[0] // ntime)
+    freq5 = synth.frequencies(64)
+    vis5 = torch.randn((rows5, 64, 1), dtype=torch.complex128, device=dev)
+    flags5 = (torch.rand(vis5.shape, device=dev) < 0.05)
+    d_lm5, d_f5 = T(lm5), T(freq5)
+    t = _timed(lambda: dft.vis_to_im(vis5, d_uvw[:rows5], d_lm5, d_f5, flags5))
+    compute_entry("vis_to_im_f64_cfg5_slice_1024x1024", t, float(npix * npix) * rows5 * 64, 11, fp64_peak,
+                  "1,048,576 pixels x 4032 rows (2 of 1550 timesteps) x 64 chan, 5% flags; the "
+                  "multi-GPU run sums the per-rank (npix,chan) partials with one NCCL all_reduce")
+    del vis5, flags5, d_lm5
+
     # ---- configs[0]: fused point-source predict, 64 ant x 100 times, 64 chan, 100 src, 2x2
     nchan1, nsrc1 = 64, 100
     freq1 = synth.frequencies(nchan1)
