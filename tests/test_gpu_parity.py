@@ -525,6 +525,45 @@ def test_wsclean_predict_vs_oracle(b200, oracle):
 
 
 
+def test_fused_predict_vis_beam_chunks(b200, oracle):
+    """Beam-interpolated DDEs reduced chunk by chunk (chunk granularity) equal the
+    reference composition beam_cube_dde -> phase_delay -> einsum -> predict_vis with the whole
+    DDE array materialised (oracle), for several chunk sizes incl. one that does not divide nsrc."""
+    rng = np.random.default_rng(314)
+    na, ntime, nsrc, nchan = 7, 3, 13, 24
+    a1, a2 = np.triu_indices(na, 1)
+    ant1, ant2 = np.tile(a1, ntime), np.tile(a2, ntime)
+    ti = np.repeat(np.arange(ntime), a1.size)
+    nrow = ti.size
+    antpos = rng.standard_normal((ntime, na, 3)) * 1200.0
+    uvw = antpos[ti, ant1] - antpos[ti, ant2]
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    freq = np.linspace(0.856e9, 1.712e9, nchan)
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    beam = rc((11, 11, 6, 2, 2))
+    ext = np.array([[-0.03, 0.03], [-0.03, 0.03]])
+    bfm = np.linspace(0.8e9, 1.8e9, 6)
+    pa = rng.uniform(-1, 1, (ntime, na))
+    pe = rng.uniform(-1e-3, 1e-3, (ntime, na, nchan, 2))
+    asc = rng.uniform(0.9, 1.1, (na, nchan, 2))
+    bright = rc((nsrc, nchan, 2, 2))
+    die = 1.0 + 0.1 * rc((ntime, na, nchan, 2, 2))
+    bvis = rc((nrow, nchan, 2, 2))
+    dde = oracle.beam_cube_dde(beam, ext, bfm, lm, pa, pe, asc, freq)
+    ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die)
+    for chunk in (None, 1, 5, 13):
+        got = b200.rime.fused_predict_vis_beam(lm, uvw, freq, bright, ti, ant1, ant2, beam, ext, bfm, pa,
+                                               pe, asc, die, bvis, die, source_chunk=chunk)
+        assert_c128_close(got, ref)
+    got = b200.rime.fused_predict_vis_beam(lm, uvw, freq, bright, ti, ant1, ant2, beam, ext, bfm, pa, pe,
+                                           asc, source_chunk=4)
+    assert_c128_close(got, oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde))
+
+
+
 # ----------------------------------------------------------------------------- cross-kernel
 def test_fused_equals_unfused_composition_on_gpu(b200):
     """Size-independent property at a size the CPU oracle cannot reach: the fused kernel must

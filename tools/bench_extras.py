@@ -204,6 +204,29 @@ def run(dev, fp64_peak):
                    3: "fused_dde_ws_kernel, per-row phasor mode", 4: "fused_dde_tiled_kernel",
                    5: "fused_dde_kernel (gather)"}.get(_l.lib().afr_last_fused_path(), "?")
     res["fused_dde_predict_c128_cfg3_slice"] = e
+    # ---- configs[2] proper: 1000 sources x 4 timesteps x 4096 chan, DDEs from the beam cube in
+    # source chunks (the full DDE array would be 67 GB; device memory holds one 4 GiB chunk)
+    nt3, ns3 = 4, 1000
+    rows34 = nt3 * rows3
+    lm34 = synth.sky_lm(ns3, rng)
+    b34 = T(synth.brightness_2x2(ns3, nchan3, rng, freq3))
+    die34 = T(synth.gains(nt3, na, nchan3, rng))
+    pa4 = T(rng.uniform(-0.3, 0.3, (nt3, na)))
+    pe4 = torch.zeros((nt3, na, nchan3, 2), dtype=torch.float64, device=dev)
+    t34 = d_t[:rows34].contiguous()
+    torch.cuda.reset_peak_memory_stats(dev)
+    tt = _timed(lambda: rime.fused_predict_vis_beam(T(lm34), d_uvw[:rows34], d_f3, b34, t34, d_a1[:rows34],
+                                                    d_a2[:rows34], d_beam, ext, bfreq, pa4, pe4, d_as,
+                                                    die34, None, die34), reps=1)
+    terms34 = float(ns3) * rows34 * nchan3
+    res["fused_beam_predict_c128_cfg3_4steps_1000src"] = {
+        "Gterms_per_s": terms34 / tt / 1e9, "ms": 1e3 * tt, "terms": terms34, "flop_per_term": 95,
+        "frac_of_fp64_fma_peak": 95 * terms34 / tt / fp64_peak,
+        "torch_peak_device_GB": torch.cuda.max_memory_allocated(dev) / 1e9,
+        "full_dde_array_GB": ns3 * nt3 * na * nchan3 * 64 / 1e9,
+        "note": "beam_cube_dde sampling per source chunk + fused DIE/DDE predict, timed together"}
+    del b34, die34
+
     # the same slice with the antenna decomposition disabled (what arbitrary uvw get)
     os.environ["AFR_DDE_ANT"] = "0"
     try:
