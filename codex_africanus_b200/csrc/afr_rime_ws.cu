@@ -15,9 +15,11 @@
 //   * precombine A_p = E1_p * B_s (valid because K is a scalar: E1 (K B) E2^H = K (E1 B) E2^H),
 //     in place when E1 != E2;
 //   * and supply the phasors, in one of two forms:
-//       ROW mode  - per row: anchor exp(i phi nu_f0) and channel step exp(i phi dnu), phi from
-//                   the row's uvw exactly as the reference rounds it; the consumer multiplies
-//                   the 2x2 product by the phasor and advances it with the three-term recurrence;
+//       ROW mode  - each consumer thread computes its row's anchor exp(i phi nu_f0) and channel
+//                   step exp(i phi dnu) itself (phi from the row's uvw exactly as the reference
+//                   rounds it), multiplies the 2x2 product by the phasor and advances it with
+//                   the three-term recurrence.  (The first version had the 4 producer warps
+//                   compute the 1024 sincos per source: they could not keep up, 96 Gterms/s.)
 //       ANT mode  - when the baseline uvw of a timestep are differences of per-antenna
 //                   coordinates (checked on the device, see antenna_uvw_kernel), K factorises as
 //                   k_p conj(k_q) and is folded into the antenna matrices: A_p <- k_p A_p,
@@ -67,8 +69,9 @@ __device__ __forceinline__ void sts_c(unsigned char *p, Cd v) {
 __host__ __device__ constexpr int ant_stride(int ft) { return ft * kMatBytes + 16; }
 
 size_t stage_bytes(int na, int ft, bool ant) {
-    // E2 (or E) | E1 -> A (or A) | B | per-row anchors + steps (ROW mode only)
-    return 2 * (size_t)na * ant_stride(ft) + (size_t)ft * kMatBytes + (ant ? 0 : 2 * (size_t)kConsThreads * 16);
+    // E2 (or E) | E1 -> A (or A) | B
+    (void)ant;
+    return 2 * (size_t)na * ant_stride(ft) + (size_t)ft * kMatBytes;
 }
 
 // FT channels and RPT rows per consumer thread (FT * RPT = 4: 64 accumulator doubles).
@@ -94,16 +97,12 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
     if (rbeg >= rend) return;
 
     const size_t mat_region = (size_t)na * AS;
-    const size_t stage = 2 * mat_region + FT * kMatBytes + (ANT ? 0 : 2 * (size_t)kConsThreads * 16);
+    const size_t stage = 2 * mat_region + FT * kMatBytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kNS * stage);  // full, empty, landed [kNS]
     double *fq = reinterpret_cast<double *>(bars + 3 * kNS);            // [FT]
     auto e2_of = [&](int st) { return smem + st * stage; };
     auto a_of = [&](int st) { return smem + st * stage + mat_region; };
     auto b_of = [&](int st) { return smem + st * stage + 2 * mat_region; };
-    auto z_of = [&](int st) {
-        return reinterpret_cast<C2<double> *>(smem + st * stage + 2 * mat_region + FT * kMatBytes);
-    };
-    auto d_of = [&](int st) { return z_of(st) + kConsThreads; };
 
     if (tid == 0) {
         for (int i = 0; i < kNS; ++i) {
@@ -160,20 +159,6 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
         };
         for (long long s = 0; s < kNS - 1 && s < nsrc; ++s) issue(s);
 
-        // ROW mode: the 4 rows of this thread
-        constexpr int RP = kConsThreads / kNTP;
-        double ru[RP], rv[RP], rw[RP];
-        if (!ANT) {
-#pragma unroll
-            for (int i = 0; i < RP; ++i) {
-                const long long ri = rbeg + ptid + i * kNTP;
-                const bool ok = ri < rend;
-                const long long r = ok ? p.perm[ri] : 0;
-                ru[i] = ok ? p.uvw[3 * r] : 0.0;
-                rv[i] = ok ? p.uvw[3 * r + 1] : 0.0;
-                rw[i] = ok ? p.uvw[3 * r + 2] : 0.0;
-            }
-        }
         const double *ant_t = ANT ? p.ant_uvw + (long long)t * p.nant * 3 : nullptr;
 
         for (long long s = 0; s < nsrc; ++s) {
@@ -182,22 +167,6 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
             // the stage must have been released by the consumers of source s - kNS
             if (s >= kNS) mbar_wait(&bars[kNS + st], (unsigned)(((s - kNS) / kNS) & 1));
             const double sl = p.lmn[3 * s], sm = p.lmn[3 * s + 1], sn = p.lmn[3 * s + 2];
-            if (!ANT) {
-                // ---- per-row phasor anchors (phase argument rounded exactly as the reference)
-                C2<double> *zs = z_of(st), *ds = d_of(st);
-#pragma unroll
-                for (int i = 0; i < RP; ++i) {
-                    const int rl = ptid + i * kNTP;
-                    const bool live = rbeg + rl < rend;
-                    const double phi = __dmul_rn(p.cst, phase_dot(sl, sm, sn, ru[i], rv[i], rw[i], false));
-                    if (EXACT) {
-                        ds[rl].re = phi;
-                    } else {
-                        zs[rl] = live ? cis_fast(__dmul_rn(phi, nu0)) : C2<double>{0.0, 0.0};
-                        ds[rl] = live ? cis_fast(__dmul_rn(phi, dnu)) : C2<double>{0.0, 0.0};
-                    }
-                }
-            }
             mbar_wait(&bars[2 * kNS + st], par);  // E (and B) of source s have landed
             // ---- half-items (antenna a, channel fl, output row h): row h of A_a = E1_a * B_s,
             // and in antenna mode row h of k_a A_a and of k_a E2_a
@@ -230,7 +199,7 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
                 sts_c(am + off, m0);
                 sts_c(am + off + 16, m1);
             }
-            mbar_arrive(&bars[st]);  // full: anchors, A (and scaled E2) of source s are visible
+            mbar_arrive(&bars[st]);  // full: A (and, antenna mode, the scaled E2) of source s are visible
             // ---- next copies: source s + kNS - 1 goes into the stage source s - 1 used
             if (s + kNS - 1 < nsrc) {
                 if (s >= 1) mbar_wait(&bars[kNS + (int)((s - 1) % kNS)], (unsigned)(((s - 1) / kNS) & 1));
@@ -248,6 +217,7 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
     // instead of four (shared-memory bandwidth was the limit: l1tex 83 % busy before).
     unsigned offs[RPT];  // shared-memory offsets of (antenna1 | antenna2 << 16)
     int rowid[RPT];
+    double ru = 0.0, rv = 0.0, rw = 0.0;  // ROW mode (RPT == 1): uvw of this thread's row
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
         const long long ri = rbeg + k * kConsThreads + tid;
@@ -257,6 +227,11 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
             const int r = p.perm[ri];
             rowid[k] = r;
             offs[k] = (unsigned)(p.ant1[r] * AS) | ((unsigned)(p.ant2[r] * AS) << 16);
+            if (!ANT) {
+                ru = p.uvw[3 * (long long)r];
+                rv = p.uvw[3 * (long long)r + 1];
+                rw = p.uvw[3 * (long long)r + 2];
+            }
         }
     }
 
@@ -270,15 +245,24 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
 
     for (long long s = 0; s < nsrc; ++s) {
         const int st = (int)(s % kNS);
-        mbar_wait(&bars[st], (unsigned)((s / kNS) & 1));
+        // ROW mode: this thread's own phasor anchors, computed while the producers prepare the
+        // stage (the wait for it comes after);
+        // the phase argument is rounded exactly as the reference rounds it (phase.py:49-53)
         Cd z = {1.0, 0.0}, zp = {1.0, 0.0}, d = {1.0, 0.0};
         double c2 = 2.0;
         if (!ANT) {
-            const C2<double> zz = z_of(st)[tid], dd = d_of(st)[tid];
-            z = {zz.re, zz.im};
-            d = {dd.re, dd.im};
-            c2 = d.re + d.re;
+            const double phi = __dmul_rn(
+                p.cst, phase_dot(p.lmn[3 * s], p.lmn[3 * s + 1], p.lmn[3 * s + 2], ru, rv, rw, false));
+            if (EXACT) {
+                d.re = phi;
+            } else {
+                const C2<double> zz = cis_fast(__dmul_rn(phi, nu0)), dd = cis_fast(__dmul_rn(phi, dnu));
+                z = {zz.re, zz.im};
+                d = {dd.re, dd.im};
+                c2 = d.re + d.re;
+            }
         }
+        mbar_wait(&bars[st], (unsigned)((s / kNS) & 1));
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
             const unsigned char *e2 = e2_of(st) + (offs[k] >> 16);
