@@ -68,11 +68,20 @@ def run(dev, fp64_peak):
     flags = (torch.rand(vis.shape, device=dev) < 0.05)
     t = _timed(lambda: dft.vis_to_im(vis, d_uvw, d_lm, d_freq, flags))
     compute_entry("vis_to_im_f64_cfg2_100steps", t, terms, 11, fp64_peak, "5% flags")
+    # FP32 FMA peak measured like the FP64 one (dependent-free FFMA chains on every SM)
+    import ctypes
+    from codex_africanus_b200 import _lib as _l32
+    pk32 = ctypes.c_double()
+    _l32.check(_l32.lib().afr_measure_fma_peak(0, 20000, ctypes.byref(pk32), None))
+    fp32_peak = pk32.value
     t = _timed(lambda: dft.im_to_vis(d_img, d_uvw, d_lm, d_freq, dtype=np.complex64))
     compute_entry("im_to_vis_c64_cfg2_100steps", t, terms, 11,
                   note="FP32 rotation/accumulate, FP64 phase + anchors")
+    res["im_to_vis_c64_cfg2_100steps"].update(
+        frac_of_fp32_fma_peak=11 * terms / t / fp32_peak, fp32_fma_peak_TFLOPs=fp32_peak / 1e12)
     t = _timed(lambda: dft.vis_to_im(vis, d_uvw, d_lm, d_freq, flags, dtype=np.float32))
     compute_entry("vis_to_im_f32_cfg2_100steps", t, terms, 11)
+    res["vis_to_im_f32_cfg2_100steps"].update(frac_of_fp32_fma_peak=11 * terms / t / fp32_peak)
     image4 = synth.stokes_image(nsrc, nchan, 4, rng, freq)
     d_img4 = T(image4)
     t = _timed(lambda: dft.im_to_vis(d_img4, d_uvw[: uvw.shape[0] // 4], d_lm, d_freq))
