@@ -42,6 +42,7 @@ struct DdeWsParams {
     long long nsrc, nrow, ntime, nant;
     int nchan;
     int same_dde;
+    int arrive_all;  // AFR_SANITIZE=1: every consumer lane arrives on the "empty" barriers
 };
 size_t dde_ws_smem_bytes(int64_t nant, int ft, bool ant);
 // per-timestep antenna coordinates from baseline uvw; ok[0] is cleared when the rows of any

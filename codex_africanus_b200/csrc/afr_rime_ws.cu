@@ -29,6 +29,7 @@
 // and release the stage with one arrive per warp.  Three stages: one being consumed, one
 // being prepared, one in flight from L2/HBM.
 #include <algorithm>
+#include <cstdlib>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -107,7 +108,9 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
     if (tid == 0) {
         for (int i = 0; i < kNS; ++i) {
             mbar_init(&bars[i], kNTP);             // full: every producer thread
-            mbar_init(&bars[kNS + i], kConsWarps); // empty: one lane per consumer warp
+            // empty: one elected lane per consumer warp (after __syncwarp); with AFR_SANITIZE=1
+            // every lane arrives, which compute-sanitizer's racecheck can follow
+            mbar_init(&bars[kNS + i], p.arrive_all ? kConsWarps * 32 : kConsWarps);
             mbar_init(&bars[2 * kNS + i], kNTP);   // landed: the cp.async of every producer thread
         }
     }
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[kNS + st]);
+        if (p.arrive_all || lane == 0) mbar_arrive(&bars[kNS + st]);
     }
 
 #pragma unroll
@@ -475,6 +478,8 @@ int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact,
     AFR_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "afr_predict_fused: grid too large");
     AFR_REQUIRE((size_t)p.nant * ant_stride(ft) < 65536, "afr_predict_fused: too many antennas");
     const int threads = (kConsWarps + kProdWarps) * 32;
+    DdeWsParams q = p;
+    q.arrive_all = (getenv("AFR_SANITIZE") && atoi(getenv("AFR_SANITIZE")) != 0) ? 1 : 0;
     auto go = [&](auto kern) -> int {
         cudaFuncAttributes attr;
         AFR_CUDA_OK(cudaFuncGetAttributes(&attr, kern));
@@ -482,7 +487,7 @@ int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact,
         AFR_REQUIRE(threads * attr.numRegs >= kConsWarps * 32 * 104 + kProdWarps * 32 * 64,
                     "fused_dde_ws: launch-time register pool too small for setmaxnreg");
         AFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, threads, smem, stream>>>(p);
+        kern<<<grid, threads, smem, stream>>>(q);
         return 0;
     };
     int rc;
