@@ -708,7 +708,11 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
             AFR_LAUNCH_OK();
             // warp-specialised kernel (afr_rime_ws.cu): TMA needs 16-byte aligned sources and
             // the three-stage antenna tile must fit in shared memory
-            const bool ws_ok = dde_ws_smem_bytes(nant, 4, false) <= 220 * 1024 &&
+            // (the 2048-row x 1-channel antenna-mode tile is 3.4x smaller per antenna than the
+            // 512-row x 4-channel one, so SKA-size arrays still fit in antenna mode)
+            const bool fit4 = dde_ws_smem_bytes(nant, 4, false) <= 220 * 1024;
+            const bool fit1 = dde_ws_smem_bytes(nant, 1, true) <= 220 * 1024;
+            const bool ws_ok = (fit4 || fit1) &&
                                reinterpret_cast<uintptr_t>(dde1) % 16 == 0 &&
                                reinterpret_cast<uintptr_t>(dde2) % 16 == 0 &&
                                reinterpret_cast<uintptr_t>(brightness) % 16 == 0 &&
@@ -731,7 +735,10 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
                 AFR_CUDA_OK(cudaMemcpyAsync(&hant, antok.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
             AFR_CUDA_OK(cudaStreamSynchronize(stream));
             const bool same = dde1 == dde2;
-            if (ws_ok && hflags[0] == 0 && hflags[1] > 0 && nrow < (1LL << 31) && nant <= 1024) {
+            const char *am_env = getenv("AFR_DDE_ANT");  // 0 forces the per-row phasor mode
+            const bool ant_mode = hant != 0 && !(am_env && atoi(am_env) == 0);
+            const bool ws_fits = fit4 || (fit1 && ant_mode && hflags[1] > 512);
+            if (ws_ok && ws_fits && hflags[0] == 0 && hflags[1] > 0 && nrow < (1LL << 31) && nant <= 1024) {
                 Scratch perm;
                 AFR_CUDA_OK(perm.alloc(sizeof(int32_t) * (size_t)nrow, stream));
                 rc = launch_row_tile_order(time_index, antenna1, antenna2, nrow, ntime,
@@ -757,8 +764,6 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
                 wp.nant = nant;
                 wp.nchan = (int)nchan;
                 wp.same_dde = same ? 1 : 0;
-                const char *am = getenv("AFR_DDE_ANT");  // 0 forces the per-row phasor mode
-                const bool ant_mode = hant != 0 && !(am && atoi(am) == 0);
                 rc = launch_fused_dde_ws(wp, hflags[1], exact, ant_mode, stream);
                 if (rc) return rc;
                 note_fused_path(ant_mode ? AFR_PATH_DDE_WS_ANT : AFR_PATH_DDE_WS_ROW);

@@ -564,6 +564,36 @@ def test_fused_predict_vis_beam_chunks(b200, oracle):
 
 
 
+def test_fused_dde_ws_many_antennas(b200, oracle):
+    """140 antennas (9730 baselines): only the 2048-row x 1-channel antenna-mode tile of the
+    warp-specialised DDE kernel fits in shared memory; random uvw fall back to the older kernels."""
+    from codex_africanus_b200 import _lib
+    rng = np.random.default_rng(7)
+    na, nsrc, nchan = 140, 4, 3
+    ant1, ant2 = np.triu_indices(na, 1)
+    ti = np.zeros(ant1.size, np.int64)
+    antpos = rng.standard_normal((na, 3)) * 3000.0
+    uvw = antpos[ant1] - antpos[ant2]
+    lm = rng.uniform(-0.01, 0.01, (nsrc, 2))
+    freq = np.linspace(0.95e9, 1.05e9, nchan)
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    bright = rc((nsrc, nchan, 2, 2))
+    dde = 1.0 + 0.2 * rc((nsrc, 1, na, nchan, 2, 2))
+    ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde)
+    got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde)
+    assert _lib.lib().afr_last_fused_path() == 2
+    assert_c128_close(got, ref)
+    uvw_r = rng.standard_normal(uvw.shape) * 3000.0
+    ref = oracle.fused_predict(lm, uvw_r, freq, bright, ti, ant1, ant2, dde, dde)
+    got = b200.rime.fused_predict_vis(lm, uvw_r, freq, bright, ti, ant1, ant2, dde, dde)
+    assert _lib.lib().afr_last_fused_path() in (4, 5)
+    assert_c128_close(got, ref)
+
+
+
 # ----------------------------------------------------------------------------- cross-kernel
 def test_fused_equals_unfused_composition_on_gpu(b200):
     """Size-independent property at a size the CPU oracle cannot reach: the fused kernel must
