@@ -254,7 +254,9 @@ def run_distributed(dev, rank, world):
     import torch.distributed as dist
 
     rng = np.random.default_rng(5)
-    na, ntime, nchan, npix = 64, 40, 64, 256
+    # the geometry of configs[4]: 1024 x 1024 pixels of 4", 64 channels -> a 512 MiB float64 image;
+    # 2 of the 1550 timesteps per rank keep the default bench short
+    na, ntime, nchan, npix = 64, 2, 64, 1024
     uvw, tidx, a1, a2 = synth.uvw_tracks(na, ntime * world, rng, ntime_total=ntime * world)
     cell = np.deg2rad(4.0 / 3600.0)
     x = (np.arange(npix) - npix // 2) * cell
