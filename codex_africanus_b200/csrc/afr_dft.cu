@@ -517,10 +517,11 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
 // ---------------------------------------------------------------------------
 constexpr int kProducerWarps = 4;
 
-// FULLW: the CTA's 16 consumer warps are 16 channel runs of the same 32 owners (nck == NWC,
+// NCKT: channel runs per CTA as a compile-time constant (0 = runtime).  NCKT == NWC ("full
+// width"): the CTA's 16 consumer warps are 16 channel runs of the same 32 owners (nck == NWC,
 // the shape of every launch with >= 16 * CH channels): strides become immediates.
 template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NWC, bool EXACT, int CREGS, int PREGS,
-          bool FULLW>
+          int NCKT>
 __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
     phasor_stream_ws_kernel(const DftParams p) {
     constexpr int NTP = kProducerWarps * 32;  // producer threads
@@ -533,8 +534,9 @@ __global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr bool FULLW = NCKT == NWC;
     constexpr bool kUnrollTile = FULLW && !ADJ && NCORR >= 2;  // see the consumer loop
-    const int nck = FULLW ? NWC : p.nck, yt = kUnrollTile ? 8 : p.yt;
+    const int nck = NCKT ? NCKT : p.nck, yt = kUnrollTile ? 8 : p.yt;
     const int xgw = (NWC / nck) * 32;
     const int ft = nck * CH;
     const int cta_f0 = blockIdx.y * ft;
@@ -1066,12 +1068,23 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
             return 0;
         };
         int rc;
-        if (exact)
-            rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, true, CREGS, PREGS, false>);
-        else if (nck == NW && yt == 8)
-            rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, true>);
-        else
-            rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, false>);
+        bool launched = false;
+        rc = 0;
+        if (exact) {
+            rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, true, CREGS, PREGS, 0>);
+            launched = true;
+        } else if (nck == NW && yt == 8) {
+            rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, NW>);
+            launched = true;
+        } else if (nck == NW / 2) {
+            // the adjoint variants have long runs (CH = 32 / 16 / 8): 256 channels are 8 runs
+            if constexpr (ADJ) {
+                rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, NW / 2>);
+                launched = true;
+            }
+        }
+        if (!launched)
+            rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, 0>);
         if (rc) return rc;
       }
     }
