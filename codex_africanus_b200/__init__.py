@@ -5,6 +5,8 @@ RIME predict / direct-DFT hot path behind the reference's own Python signatures.
     codex_africanus_b200.rime : phase_delay, predict_vis, apply_gains, beam_cube_dde,
                                 fused_predict_vis (phase_delay (x) brightness -> predict_vis)
     codex_africanus_b200.dft  : im_to_vis, vis_to_im
+    codex_africanus_b200.model: spectral_model, convert, stokes_brightness (brightness from
+                                Stokes parameters, generated on the device)
 
 Mirrors ``africanus.rime`` (africanus/rime/__init__.py:3-10) and ``africanus.dft``
 (africanus/dft/__init__.py:3) as a sibling backend in the style of

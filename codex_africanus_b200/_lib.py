@@ -45,6 +45,9 @@ PROTOTYPES = {
     "afr_freq_grid_interp": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "afr_wsclean_spectra": (_int, [_vp] * 5 + [_i64] * 3 + [_vp, _vp]),
     "afr_wsclean_predict": (_int, [_vp] * 9 + [_i64] * 5 + [_int, _vp, _vp]),
+    "afr_spectral_model": (_int, [_vp] * 5 + [_i64] * 4 + [_vp, _vp]),
+    "afr_convert": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "afr_stokes_brightness": (_int, [_vp] * 5 + [_i64] * 4 + [_vp] * 3 + [_i64, _int, _vp, _vp]),
 }
 
 _lock = threading.Lock()

@@ -16,9 +16,15 @@
 namespace afr {
 namespace {
 
-__device__ __forceinline__ double ipow(double x, int n) {  // x ** n as repeated products
-    double r = 1.0;
-    for (int i = 0; i < n; ++i) r = __dmul_rn(r, x);
+// x ** n in numba's int_power order (binary square-and-multiply from the low bit; it differs
+// from a left-to-right product from the 4th power on)
+__device__ __forceinline__ double ipow(double x, int n) {
+    double r = 1.0, a = x;
+    while (n != 0) {
+        if (n & 1) r = __dmul_rn(r, a);
+        n >>= 1;
+        a = __dmul_rn(a, a);
+    }
     return r;
 }
 

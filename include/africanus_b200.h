@@ -170,6 +170,29 @@ int afr_wsclean_predict(const double *uvw, const double *lm, const uint8_t *is_g
                         int64_t nsrc, int64_t ncoeffs, int64_t nrow, int64_t nchan, int64_t ngauss,
                         int chan_mode, void *out, void *stream);
 
+/* ---- brightness from Stokes parameters ---------------------------------
+ * africanus.model.spectral.spectral_model (africanus/model/spectral/spec_model.py:106-211) and
+ * africanus.model.coherency.convert (africanus/model/coherency/conversion.py:145-243) ------ */
+/* out (nsrc,nchan,npol) float64.  stokes (nsrc,npol), spi (nsrc,nspi,npol), ref_freq (nsrc,),
+ * freq (nchan,) device float64; base: HOST array of npol ints, 0 "std" (stokes prod_i (nu/ref)^spi_i),
+ * 1 "log" (stokes exp(sum_i spi_i log(nu/ref)^(i+1))), 2 "log10"; npol <= 16. */
+int afr_spectral_model(const double *stokes, const double *spi, const double *ref_freq,
+                       const double *freq, const int *base, int64_t nsrc, int64_t nspi,
+                       int64_t npol, int64_t nchan, double *out, void *stream);
+/* out (n,nout) complex128 from in (n,nin) float64 (in_complex 0) or complex128 (1).  src1, src2,
+ * op: HOST arrays of nout ints, the schema resolved as in conversion.py:145-215: output o =
+ * op[o](in[src1[o]], in[src2[o]]), index -1 = the implicit-Stokes zero; ops (conversion.py:19-48)
+ * 0 a+b, 1 a-b, 2 a+b*1j, 3 a-b*1j, 4 (a+b)/2, 5 (a-b)/2, 6 (a-b)/2j; nout <= 16. */
+int afr_convert(const void *in, int in_complex, int64_t n, int64_t nin, const int *src1,
+                const int *src2, const int *op, int64_t nout, void *out, void *stream);
+/* the two composed: out (nsrc,nchan,nout) complex128 (is_c64 0) or complex64 (1) =
+ * convert(spectral_model(stokes, spi, ref_freq, freq, base)); npol <= 4 Stokes inputs.  This is
+ * the `brightness` argument of afr_predict_fused (rime/examples/predict.py:107-134). */
+int afr_stokes_brightness(const double *stokes, const double *spi, const double *ref_freq,
+                          const double *freq, const int *base, int64_t nsrc, int64_t nspi,
+                          int64_t npol, int64_t nchan, const int *src1, const int *src2,
+                          const int *op, int64_t nout, int is_c64, void *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

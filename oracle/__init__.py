@@ -321,3 +321,96 @@ def wsclean_predict(uvw, lm, source_type, flux, coeffs, log_poly, ref_freq, gaus
                                    _i64(lm.shape[0]), _i64(uvw.shape[0]), _i64(fr.shape[0]), _p(out))
     assert rc == 0, rc
     return out
+
+
+# ---------------------------------------------------------------------------
+# Brightness from Stokes parameters
+_BASES = {0: 0, "std": 0, 1: 1, "log": 1, 2: 2, "log10": 2}
+
+
+def spectral_model(stokes, spi, ref_freq, frequency, base=0):
+    """africanus/model/spectral/spec_model.py:106-211."""
+    stokes, spi = np.asarray(stokes), np.asarray(spi)
+    dtype = np.result_type(stokes, spi, np.asarray(ref_freq), np.asarray(frequency))
+    if spi.ndim - 2 != stokes.ndim - 1:
+        raise ValueError("Dimensions on stokes and spi don't agree")
+    out_shape = (stokes.shape[0], np.asarray(frequency).shape[0]) + stokes.shape[1:]
+    npol = int(np.prod(stokes.shape[1:], dtype=np.int64))
+    if npol != int(np.prod(spi.shape[2:], dtype=np.int64)):
+        raise ValueError("Correlations on stokes and spi don't agree")
+    bases = list(base) if isinstance(base, (list, tuple)) else [base]
+    bases = (bases + [bases[-1]] * npol)[:npol]
+    if any(b not in _BASES for b in bases):
+        raise ValueError("Invalid base")
+    b = np.array([_BASES[x] for x in bases], np.int32)
+    ns, nspi, nf = stokes.shape[0], spi.shape[1], out_shape[1]
+    st = _as(stokes.reshape(ns, npol), np.float64)
+    sp = _as(spi.reshape(ns, nspi, npol), np.float64)
+    rf, fr = _as(ref_freq, np.float64), _as(frequency, np.float64)
+    out = np.zeros((ns, nf, npol), np.float64)
+    rc = lib().orc_spectral_model(_p(st), _p(sp), _p(rf), _p(fr), _p(b), _i64(ns), _i64(nspi),
+                                  _i64(npol), _i64(nf), _p(out))
+    assert rc == 0, rc
+    return out.reshape(out_shape).astype(dtype, copy=False)
+
+
+# output element -> ((input one, input two), op code of orc_convert); conversion.py:17-48
+_CONV = {
+    "RR": [(("I", "V"), 0)], "RL": [(("Q", "U"), 2)], "LR": [(("Q", "U"), 3)], "LL": [(("I", "V"), 1)],
+    "XX": [(("I", "Q"), 0)], "XY": [(("U", "V"), 2)], "YX": [(("U", "V"), 3)], "YY": [(("I", "Q"), 1)],
+    "I": [(("XX", "YY"), 4), (("RR", "LL"), 4)], "Q": [(("XX", "YY"), 5), (("RL", "LR"), 4)],
+    "U": [(("XY", "YX"), 4), (("RL", "LR"), 6)], "V": [(("XY", "YX"), 6), (("RR", "LL"), 5)],
+}
+_STOKES_NAMES = ["Undefined", "I", "Q", "U", "V", "RR", "RL", "LR", "LL", "XX", "XY", "YX", "YY"]
+
+
+def _schema(schema):
+    """name -> flat index, shape (conversion.py:93-142)."""
+    arr = np.asarray(schema, dtype=object)
+    if arr.ndim == 0:
+        arr = arr.reshape(1)
+    names = {}
+    for flat, e in enumerate(arr.reshape(-1)):
+        if not isinstance(e, str):
+            e = _STOKES_NAMES[int(e)]
+        if e in names:
+            raise ValueError("'%s' defined multiple times" % e)
+        names[e] = flat
+    return names, arr.shape
+
+
+def convert(input, input_schema, output_schema, implicit_stokes=False):
+    """africanus/model/coherency/conversion.py:145-243."""
+    input = np.asarray(input)
+    in_idx, in_shape = _schema(input_schema)
+    out_idx, out_shape = _schema(output_schema)
+    if input.shape[input.ndim - len(in_shape):] != in_shape:
+        raise ValueError("Last dimension of input doesn't match input schema")
+    nout = len(out_idx)
+    s1, s2, op = (np.zeros(nout, np.int32) for _ in range(3))
+    cplx = False
+    for okey, o in out_idx.items():
+        if okey not in _CONV:
+            raise ValueError("Unknown output %s" % okey)
+        defaults_ok = implicit_stokes and okey in ("RR", "RL", "LR", "LL", "XX", "XY", "YX", "YY")
+        best = None
+        for (c1, c2), code in _CONV[okey]:
+            have = (c1 in in_idx) + (c2 in in_idx)
+            if have < 2 and not defaults_ok:
+                continue
+            if best is None or have > best[0]:
+                best = (have, in_idx.get(c1, -1), in_idx.get(c2, -1), code)
+        if best is None:
+            raise ValueError("None of the supplied inputs can produce output '%s'" % okey)
+        s1[o], s2[o], op[o] = best[1:]
+        cplx = cplx or best[3] not in (4, 5)
+    zero = np.zeros((), input.dtype)
+    dtype = np.result_type((zero + zero + 0j).dtype if cplx else (zero / 2).dtype, (zero / 2).dtype)
+    lead = input.shape[:input.ndim - len(in_shape)]
+    n, nin = int(np.prod(lead, dtype=np.int64)), len(in_idx)
+    flat = _as(input.reshape(n, nin), np.complex128)
+    out = np.zeros((n, nout), np.complex128)
+    rc = lib().orc_convert(_p(flat), _i64(n), _i64(nin), _p(s1), _p(s2), _p(op), _i64(nout), _p(out))
+    assert rc == 0, rc
+    out = out.reshape(lead + out_shape)
+    return (out if np.issubdtype(dtype, np.complexfloating) else out.real).astype(dtype)

@@ -674,12 +674,18 @@ int orc_fused_predict_c128(const double *lm, const double *uvw, const double *fr
  * spectra (spec_model.py:94-124): out (nsrc, nchan) float64.
  *   log_poly[s] != 0 : out = I * exp(sum_c coeffs[s,c] * log(nu/rf)^(c+1))
  *   else             : out = I + sum_c coeffs[s,c] * (nu/rf - 1)^(c+1)
- * x ** (c+1) with an integer exponent is evaluated by numba as an exact-order
- * repeated multiplication (llvm powi expansion); pow() agrees to 1 ulp.
+ * x ** (c+1) with an integer exponent is evaluated by numba's int_power
+ * (numba/cpython/numbers.py): binary square-and-multiply, low bit first.  It
+ * differs from a left-to-right product from the 4th power on (checked against
+ * the reference with 6 coefficients, tests/golden/brightness.npz).
  */
 static double ipow_(double x, int n) {
-    double r = 1.0;
-    for (int i = 0; i < n; ++i) r *= x;
+    double r = 1.0, a = x;
+    while (n != 0) {
+        if (n & 1) r *= a;
+        n >>= 1;
+        a *= a;
+    }
     return r;
 }
 
@@ -755,6 +761,80 @@ int orc_wsclean_predict(const double *uvw, const double *lm, const uint8_t *is_g
                 out[2 * (r * nchan + f)] += re;
                 out[2 * (r * nchan + f) + 1] += im;
             }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Brightness from Stokes parameters:                       */
+/* africanus/model/spectral/spec_model.py:106-211 and                        */
+/* africanus/model/coherency/conversion.py:17-48,218-243                     */
+/* ------------------------------------------------------------------------ */
+/*
+ * spectral_model (spec_model.py:160-211): out (nsrc, nchan, npol) float64.
+ * base[p]: 0 "std"   out = stokes * prod_i (nu/rf) ** spi[s,i,p]      (libm pow)
+ *          1 "log"   out = stokes * exp  (sum_i spi[s,i,p] * log  (nu/rf) ** (i+1))
+ *          2 "log10" out = stokes * 10 ** (sum_i spi[s,i,p] * log10(nu/rf) ** (i+1))
+ * Integer powers as numba's int_power (ipow_ above); 10 ** x is pow(10.0, x).
+ */
+int orc_spectral_model(const double *stokes, const double *spi, const double *ref_freq,
+                       const double *freq, const int *base, int64_t nsrc, int64_t nspi,
+                       int64_t npol, int64_t nchan, double *out) {
+    for (int64_t p = 0; p < npol; ++p) {
+        if (base[p] < 0 || base[p] > 2) return 1;
+        for (int64_t s = 0; s < nsrc; ++s) {
+            const double rf = ref_freq[s];
+            const double st = stokes[s * npol + p];
+            for (int64_t f = 0; f < nchan; ++f) {
+                double v;
+                if (base[p] == 0) {
+                    const double ratio = freq[f] / rf;
+                    v = st;
+                    for (int64_t i = 0; i < nspi; ++i) v *= pow(ratio, spi[(s * nspi + i) * npol + p]);
+                } else {
+                    const double lr = base[p] == 1 ? log(freq[f] / rf) : log10(freq[f] / rf);
+                    double acc = 0.0;
+                    for (int64_t i = 0; i < nspi; ++i)
+                        acc += spi[(s * nspi + i) * npol + p] * ipow_(lr, (int)(i + 1));
+                    v = st * (base[p] == 1 ? exp(acc) : pow(10.0, acc));
+                }
+                out[(s * nchan + f) * npol + p] = v;
+            }
+        }
+    }
+    return 0;
+}
+
+/*
+ * convert (conversion.py:218-243) after the schema has been resolved to one
+ * (source_one, source_two, op) triple per output element (conversion.py:145-215).
+ * in (n, nin) complex128 (real inputs widened), out (n, nout) complex128.
+ * A source index of -1 is the DataSource.Default zero.  ops, conversion.py:19-48:
+ *   0: a + b        (RR, XX)          1: a - b          (LL, YY)
+ *   2: a + b*1j     (RL, XY)          3: a - b*1j       (LR, YX)
+ *   4: (a + b) / 2  (I, Q)            5: (a - b) / 2    (Q, V)
+ *   6: (a - b) / 2j (U, V)
+ */
+int orc_convert(const double *in, int64_t n, int64_t nin, const int *src1, const int *src2,
+                const int *op, int64_t nout, double *out) {
+    for (int64_t i = 0; i < n; ++i) {
+        for (int64_t o = 0; o < nout; ++o) {
+            double ar = 0, ai = 0, br = 0, bi = 0, re, im;
+            if (src1[o] >= 0) { ar = in[2 * (i * nin + src1[o])]; ai = in[2 * (i * nin + src1[o]) + 1]; }
+            if (src2[o] >= 0) { br = in[2 * (i * nin + src2[o])]; bi = in[2 * (i * nin + src2[o]) + 1]; }
+            switch (op[o]) {
+            case 0: re = ar + br; im = ai + bi; break;
+            case 1: re = ar - br; im = ai - bi; break;
+            case 2: re = ar - bi; im = ai + br; break;
+            case 3: re = ar + bi; im = ai - br; break;
+            case 4: re = (ar + br) * 0.5; im = (ai + bi) * 0.5; break;
+            case 5: re = (ar - br) * 0.5; im = (ai - bi) * 0.5; break;
+            case 6: re = (ai - bi) * 0.5; im = -((ar - br) * 0.5); break;
+            default: return 1;
+            }
+            out[2 * (i * nout + o)] = re;
+            out[2 * (i * nout + o) + 1] = im;
         }
     }
     return 0;

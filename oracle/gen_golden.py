@@ -275,6 +275,79 @@ def gen_wsclean():
     save("wsclean", **out)
 
 
+def gen_brightness():
+    """africanus.model.spectral.spectral_model, africanus.model.coherency.convert
+    and their composition into the (source, chan, 2, 2) brightness the predict consumes
+    (rime/examples/predict.py:107-134), plus the reference test's own known answers
+    (model/coherency/tests/test_convert.py:69-110)."""
+    from africanus.model.coherency.conversion import convert
+    from africanus.model.spectral.spec_model import spectral_model
+    from africanus.model.wsclean.spec_model import spectra
+
+    out = {}
+    rng = np.random.default_rng(2024)
+    src, chan = 23, 17
+    freq = np.linspace(0.856e9, 1.712e9, chan)
+    ref_freq = rng.uniform(0.9e9, 1.6e9, src)
+    stokes = rng.standard_normal((src, 4)) * 0.1
+    stokes[:, 0] = np.abs(rng.standard_normal(src)) + 0.5
+    out.update(freq=freq, ref_freq=ref_freq, stokes=stokes)
+    for nspi in (1, 2, 6):
+        spi = rng.standard_normal((src, nspi, 4)) * 0.4 - 0.3
+        out["spi%d" % nspi] = spi
+        for base in ("std", "log", "log10"):
+            out["sm_%s_%d" % (base, nspi)] = spectral_model(stokes, spi, ref_freq, freq, base=base)
+        out["sm_int_%d" % nspi] = np.stack([spectral_model(stokes, spi, ref_freq, freq, base=b)
+                                            for b in (0, 1, 2)])
+    # per-polarisation base list, padded with its last entry (spec_model.py:77-83)
+    out["sm_list"] = spectral_model(stokes, out["spi2"], ref_freq, freq, base=["std", "log", "log10"])
+    # no polarisation dimension
+    out["sm_nopol"] = spectral_model(stokes[:, 0].copy(), out["spi2"][:, :, 0].copy(), ref_freq, freq,
+                                     base="log")
+    # float32 inputs
+    f32 = np.float32
+    out["sm_f32"] = spectral_model(stokes.astype(f32), out["spi2"].astype(f32), ref_freq.astype(f32),
+                                   freq.astype(f32), base="std")
+    # the composed brightness for both feed types
+    sm = out["sm_std_2"]
+    out["b_linear"] = convert(sm, ["I", "Q", "U", "V"], [["XX", "XY"], ["YX", "YY"]])
+    out["b_circular"] = convert(sm, ["I", "Q", "U", "V"], [["RR", "RL"], ["LR", "LL"]])
+    out["b_flat"] = convert(sm, ["I", "Q", "U", "V"], ["XX", "XY", "YX", "YY"])
+    out["b_implicit"] = convert(sm[..., :1], ["I"], ["XX", "XY", "YX", "YY"], implicit_stokes=True)
+    out["b_diag"] = convert(sm[..., :2], ["I", "Q"], ["XX", "YY"])
+    out["b_f32"] = convert(sm.astype(f32), ["I", "Q", "U", "V"], [["XX", "XY"], ["YX", "YY"]])
+    # back to Stokes from complex correlations (int schema too)
+    vis = rc(rng, (9, 5, 2, 2))
+    out["vis"] = vis
+    out["s_linear"] = convert(vis, [["XX", "XY"], ["YX", "YY"]], ["I", "Q", "U", "V"])
+    out["s_circular"] = convert(vis, [["RR", "RL"], ["LR", "LL"]], [["I", "Q"], ["U", "V"]])
+    out["s_int"] = convert(vis[..., 0, :], [9, 12], [1, 2])
+    out["s_real"] = convert(vis.real, [["XX", "XY"], ["YX", "YY"]], ["I", "Q"])
+    # WSClean spectra with 6 coefficients: integer powers >= 4 (numba int_power ordering)
+    coeffs = rng.standard_normal((src, 6)) * 0.3
+    log_poly = rng.random(src) < 0.5
+    out.update(w_coeffs=coeffs, w_log_poly=log_poly,
+               w_spectra=spectra(stokes[:, 0], coeffs, log_poly, ref_freq, freq))
+    # predict with that brightness: MeerKAT-like, DIE gains, base_vis
+    na, ntime = 7, 3
+    a1, a2 = np.triu_indices(na, 1)
+    nbl = a1.size
+    ant1, ant2 = np.tile(a1, ntime).astype(np.int32), np.tile(a2, ntime).astype(np.int32)
+    time_index = np.repeat(np.arange(ntime), nbl).astype(np.int32)
+    pos = rng.standard_normal((ntime, na, 3)) * 800.0
+    uvw = (pos[:, a1] - pos[:, a2]).reshape(-1, 3)
+    lm = rng.uniform(-0.02, 0.02, (src, 2))
+    die = 1.0 + 0.1 * rc(rng, (ntime, na, chan, 2, 2))
+    base_vis = rc(rng, (uvw.shape[0], chan, 2, 2))
+    K = phase_delay(lm, uvw, freq)
+    for feed in ("linear", "circular"):
+        coh = np.einsum("srf,sfij->srfij", K, out["b_" + feed])
+        out["p_" + feed] = predict_vis(time_index, ant1, ant2, None, coh, None, die, base_vis, die)
+    out.update(p_lm=lm, p_uvw=uvw, p_time_index=time_index, p_ant1=ant1, p_ant2=ant2, p_die=die,
+               p_base_vis=base_vis)
+    save("brightness", **out)
+
+
 if __name__ == "__main__":
     gen_phase()
     gen_dft()
@@ -282,3 +355,4 @@ if __name__ == "__main__":
     gen_beam()
     gen_fused()
     gen_wsclean()
+    gen_brightness()

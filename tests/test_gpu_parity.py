@@ -21,13 +21,14 @@ C = 2.99792458e8
 @pytest.fixture(scope="module")
 def b200():
     import codex_africanus_b200.dft as dft
+    import codex_africanus_b200.model as model
     import codex_africanus_b200.rime as rime
 
     class NS:
         pass
 
     ns = NS()
-    ns.dft, ns.rime = dft, rime
+    ns.dft, ns.rime, ns.model = dft, rime, model
     return ns
 
 
@@ -721,3 +722,127 @@ def test_row_block_streaming_paths(b200, oracle, monkeypatch):
     assert_c128_close(got, ref)
     got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2)
     assert_c128_close(got, oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2))
+
+
+# ----------------------------------------------------------------------------- brightness (8f-2)
+_LIN = [["XX", "XY"], ["YX", "YY"]]
+_CIRC = [["RR", "RL"], ["LR", "LL"]]
+_IQUV = ["I", "Q", "U", "V"]
+
+
+def test_spectral_model_golden(b200, golden):
+    """africanus.model.spectral.spectral_model against the reference's outputs: every base, 1/2/6
+    spectral-index components, per-polarisation base list, no polarisation axis, float32."""
+    g = golden("brightness")
+    st, rf, fr = g["stokes"], g["ref_freq"], g["freq"]
+    sm = b200.model.spectral_model
+    for n in (1, 2, 6):
+        spi = g["spi%d" % n]
+        for i, b in enumerate(("std", "log", "log10")):
+            got = sm(st, spi, rf, fr, base=b)
+            assert got.dtype == np.float64
+            assert_c128_close(got, g["sm_%s_%d" % (b, n)])
+            assert_c128_close(sm(st, spi, rf, fr, base=i), g["sm_int_%d" % n][i])
+    assert_c128_close(sm(st, g["spi2"], rf, fr, base=["std", "log", "log10"]), g["sm_list"])
+    assert_c128_close(sm(st[:, 0], g["spi2"][:, :, 0], rf, fr, base="log"), g["sm_nopol"])  # strided views
+    f32 = np.float32
+    got = sm(st.astype(f32), g["spi2"].astype(f32), rf.astype(f32), fr.astype(f32))
+    assert got.dtype == np.float32 and got.shape == g["sm_f32"].shape
+    assert rel_l2(got, g["sm_f32"]) < 1e-5
+    assert sm(st[:0], g["spi2"][:0], rf[:0], fr).shape == (0, fr.shape[0], 4)
+
+
+def test_convert_golden(b200, golden):
+    """africanus.model.coherency.convert against the reference's outputs (dtype and shape incl.)
+    and the reference test's known answers (model/coherency/tests/test_convert.py:69-110)."""
+    import torch
+
+    g = golden("brightness")
+    sm, vis = g["sm_std_2"], g["vis"]
+    cases = [
+        ("b_linear", sm, _IQUV, _LIN, False), ("b_circular", sm, _IQUV, _CIRC, False),
+        ("b_flat", sm, _IQUV, ["XX", "XY", "YX", "YY"], False),
+        ("b_implicit", sm[..., :1], ["I"], ["XX", "XY", "YX", "YY"], True),
+        ("b_diag", sm[..., :2], ["I", "Q"], ["XX", "YY"], False),
+        ("s_linear", vis, _LIN, _IQUV, False), ("s_circular", vis, _CIRC, [["I", "Q"], ["U", "V"]], False),
+        ("s_int", vis[..., 0, :], [9, 12], [1, 2], False),
+        ("s_real", vis.real, _LIN, ["I", "Q"], False),
+    ]
+    for key, inp, isch, osch, implicit in cases:
+        got = b200.model.convert(inp, isch, osch, implicit_stokes=implicit)
+        assert_c128_close(got, g[key])
+    got = b200.model.convert(sm.astype(np.float32), _IQUV, _LIN)
+    assert_c64_close(got, g["b_f32"])
+    got = b200.model.convert(torch.from_numpy(sm).cuda(), _IQUV, _LIN)
+    assert isinstance(got, torch.Tensor) and got.is_cuda
+    assert_c128_close(got.cpu().numpy(), g["b_linear"])
+    I, Q, U, V = 1.0 + 1j, 2.0 + 2j, 3.0 + 3j, 4.0 + 4j  # noqa: E741
+    inp = np.asarray([[I, Q, U, V]])
+    assert np.all(b200.model.convert(inp, _IQUV, ["XX", "XY", "YX", "YY"])
+                  == [[I + Q, U + V * 1j, U - V * 1j, I - Q]])
+    assert np.all(b200.model.convert(inp, [1, 2, 3, 4], [5, 6, 7, 8])
+                  == [[I + V, Q + U * 1j, Q - U * 1j, I - V]])
+    # round trip Stokes -> correlations -> Stokes
+    back = b200.model.convert(b200.model.convert(sm, _IQUV, _CIRC), _CIRC, _IQUV)
+    assert_c128_close(back, sm.astype(np.complex128), rtol=1e-14)
+
+
+def test_stokes_brightness_and_wsclean_powers(b200, golden):
+    """The composed kernel equals convert(spectral_model(...)) of the reference for both feed
+    types / every base; WSClean spectra with 6 coefficients (integer powers >= 4)."""
+    g = golden("brightness")
+    st, rf, fr = g["stokes"], g["ref_freq"], g["freq"]
+    sb = b200.model.stokes_brightness
+    assert_c128_close(sb(st, g["spi2"], rf, fr), g["b_linear"])
+    assert_c128_close(sb(st, g["spi2"], rf, fr, corr_schema=_CIRC), g["b_circular"])
+    assert_c128_close(sb(st, g["spi2"], rf, fr, corr_schema=["XX", "XY", "YX", "YY"]), g["b_flat"])
+    assert_c128_close(sb(st[:, :1], g["spi2"][:, :, :1], rf, fr, stokes_schema=["I"],
+                         corr_schema=["XX", "XY", "YX", "YY"], implicit_stokes=True), g["b_implicit"])
+    got = sb(st, g["spi2"], rf, fr, dtype=np.complex64)
+    assert_c64_close(got, g["b_linear"].astype(np.complex64))
+    assert_c128_close(b200.rime.wsclean_spectra(st[:, 0], g["w_coeffs"], g["w_log_poly"], rf, fr),
+                      g["w_spectra"])
+
+
+def test_fused_predict_vis_stokes(b200, golden, oracle):
+    """fused_predict_vis_stokes (brightness generated per source chunk on the device) equals the
+    reference composition spectral_model -> convert -> phase_delay (x) brightness -> predict_vis
+    (golden), for chunk sizes that do and do not divide nsrc; with DDEs and torch inputs vs the
+    oracle; complex64 on request."""
+    import torch
+
+    g = golden("brightness")
+    st, spi, rf, fr = g["stokes"], g["spi2"], g["ref_freq"], g["freq"]
+    lm, uvw, ti, a1, a2 = g["p_lm"], g["p_uvw"], g["p_time_index"], g["p_ant1"], g["p_ant2"]
+    die, bvis = g["p_die"], g["p_base_vis"]
+    f = b200.rime.fused_predict_vis_stokes
+    for feed, schema in (("linear", _LIN), ("circular", _CIRC)):
+        for chunk in (None, 5, 23, 1):
+            got = f(lm, uvw, fr, st, spi, rf, ti, a1, a2, None, None, die, bvis, die,
+                    corr_schema=schema, source_chunk=chunk)
+            assert_c128_close(got, g["p_" + feed])
+    # DDEs (sliced per chunk), log-polynomial spectra, casa convention, int16 indices
+    rng = np.random.default_rng(77)
+    nsrc, nchan = lm.shape[0], fr.shape[0]
+    ntime, na = die.shape[:2]
+    dde = 1.0 + 0.2 * (rng.standard_normal((nsrc, ntime, na, nchan, 2, 2))
+                       + 1j * rng.standard_normal((nsrc, ntime, na, nchan, 2, 2)))
+    bright = oracle.convert(oracle.spectral_model(st, spi, rf, fr, base="log"), _IQUV, _LIN)
+    ref = oracle.fused_predict(lm, uvw, fr, bright, ti, a1, a2, dde, dde, die, bvis, die, convention="casa")
+    i16 = np.int16
+    got = f(lm, uvw, fr, st, spi, rf, ti.astype(i16), a1.astype(i16), a2.astype(i16), dde, dde, die, bvis,
+            die, convention="casa", base="log", source_chunk=7)
+    assert_c128_close(got, ref)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    got = f(T(lm), T(uvw), T(fr), T(st), T(spi), T(rf), T(ti), T(a1), T(a2), T(dde), T(dde), T(die),
+            T(bvis), T(die), convention="casa", base="log", source_chunk=4)
+    assert isinstance(got, torch.Tensor)
+    assert_c128_close(got.cpu().numpy(), ref)
+    # no Jones terms at all; complex64 brightness -> complex64 visibilities
+    ref0 = oracle.fused_predict(lm, uvw, fr, g["b_linear"], ti, a1, a2)
+    assert_c128_close(f(lm, uvw, fr, st, spi, rf, ti, a1, a2, source_chunk=6), ref0)
+    got = f(lm, uvw, fr, st, spi, rf, ti, a1, a2, dtype=np.complex64)
+    assert got.dtype == np.complex64
+    assert rel_l2(got.astype(np.complex128), ref0) < 1e-5
+    with pytest.raises(ValueError):
+        f(lm, uvw, fr, st, spi, rf, ti, a1, a2, die1_jones=die)

@@ -93,6 +93,59 @@ def test_errors_match_reference_before_device_work():
                            np.ones((1, 1, 2)), np.ones(1))
 
 
+def test_convert_schema_resolution_and_errors():
+    """Host logic of model.convert / spectral_model (conversion.py:93-215, spec_model.py:77-171):
+    schema flattening, rule choice, output dtype, and the reference's errors -- all before any
+    device work."""
+    from codex_africanus_b200.model import coherency as coh, convert, spectral_model
+    from codex_africanus_b200.model.spectral import promote_bases
+
+    names, shape = coh.schema_elements([["XX", "XY"], ["YX", "YY"]])
+    assert names == {"XX": 0, "XY": 1, "YX": 2, "YY": 3} and shape == (2, 2)
+    assert coh.schema_elements([9, 12]) == ({"XX": 0, "YY": 1}, (2,))
+    assert coh.schema_elements("I") == ({"I": 0}, (1,))
+    iquv = coh.schema_elements(["I", "Q", "U", "V"])[0]
+    s1, s2, op = coh.resolve(iquv, names, False)
+    assert (list(s1), list(s2), list(op)) == ([0, 2, 2, 0], [1, 3, 3, 1], [0, 2, 3, 1])
+    s1, s2, op = coh.resolve(iquv, coh.schema_elements([["RR", "RL"], ["LR", "LL"]])[0], False)
+    assert (list(s1), list(s2), list(op)) == ([0, 1, 1, 0], [3, 2, 2, 3], [0, 2, 3, 1])
+    # implicit Stokes: missing inputs are the default zero (-1)
+    s1, s2, op = coh.resolve({"I": 0}, names, True)
+    assert (list(s1), list(s2)) == ([0, -1, -1, 0], [-1, -1, -1, -1])
+    # both circular and linear inputs: first listed rule wins ties (XX,YY for I)
+    both = coh.schema_elements(["XX", "YY", "RR", "LL"])[0]
+    assert [list(x) for x in coh.resolve(both, {"I": 0, "V": 1}, False)] == [[0, 2], [1, 3], [4, 5]]
+    assert coh._output_dtype(np.dtype(np.float64), [0, 2]) == np.complex128
+    assert coh._output_dtype(np.dtype(np.float32), [0, 2]) == np.complex64
+    assert coh._output_dtype(np.dtype(np.float32), [4, 5]) == np.float32
+    assert coh._output_dtype(np.dtype(np.float64), [4, 6]) == np.complex128
+    with pytest.raises(ValueError, match="defined multiple times"):
+        coh.schema_elements(["I", "I"])
+    with pytest.raises(coh.DimensionMismatch):
+        coh.schema_elements([["XX", "XY"], ["YX"]])
+    with pytest.raises(TypeError):
+        coh.schema_elements([1.5])
+    with pytest.raises(ValueError, match="Invalid id"):
+        coh.schema_elements([99])
+    with pytest.raises(coh.MissingConversionInputs):
+        coh.resolve({"I": 0}, names, False)
+    with pytest.raises(ValueError, match="Unknown output"):
+        coh.resolve(iquv, {"PP": 0}, False)
+    with pytest.raises(ValueError, match="doesn't match input schema"):
+        convert(np.zeros((3, 3)), ["I", "Q", "U", "V"], ["XX"])
+    assert list(promote_bases("log", 3)) == [1, 1, 1]
+    assert list(promote_bases(["std", 2], 4)) == [0, 2, 2, 2]
+    with pytest.raises(ValueError, match="Invalid base"):
+        promote_bases("ln", 2)
+    with pytest.raises(TypeError):
+        promote_bases(1.0, 2)
+    st, spi = np.ones((3, 4)), np.ones((3, 2, 4))
+    with pytest.raises(ValueError, match="Dimensions on stokes and spi"):
+        spectral_model(st, spi[:, :, 0], np.ones(3), np.ones(5))
+    with pytest.raises(ValueError, match="Correlations on stokes and spi"):
+        spectral_model(st, spi[:, :, :2], np.ones(3), np.ones(5))
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
     import torch

@@ -16,6 +16,8 @@ import numpy as np
 import pytest
 from numpy.testing import assert_array_almost_equal, assert_array_equal
 
+from conftest import rel_l2
+
 C = 2.99792458e8
 MINUS_TWO_PI_OVER_C = -2 * np.pi / C
 
@@ -348,3 +350,100 @@ def test_wsclean_predict_known_answer(golden, oracle):
     got = oracle.wsclean_predict(uvw, lm, g["t_source_type"], g["t_flux"], g["t_coeffs"], g["t_log_poly"],
                                  g["t_ref_freq"], gs, freq)
     np.testing.assert_almost_equal(ref, got)
+
+
+# ----------------------------------------------------------------------------- brightness (8f-2)
+_LIN = [["XX", "XY"], ["YX", "YY"]]
+_CIRC = [["RR", "RL"], ["LR", "LL"]]
+_IQUV = ["I", "Q", "U", "V"]
+
+
+def test_spectral_model_golden(golden, oracle):
+    """africanus.model.spectral.spectral_model: every base (string and integer spelling), 1 / 2 /
+    6 spectral-index components (integer powers >= 4 pin numba's square-and-multiply order),
+    per-polarisation base list, no polarisation axis -- bit-exact; float32 inputs to 1e-6."""
+    g = golden("brightness")
+    st, rf, fr = g["stokes"], g["ref_freq"], g["freq"]
+    for n in (1, 2, 6):
+        spi = g["spi%d" % n]
+        for i, b in enumerate(("std", "log", "log10")):
+            ref = g["sm_%s_%d" % (b, n)]
+            assert np.array_equal(oracle.spectral_model(st, spi, rf, fr, base=b), ref)
+            assert np.array_equal(oracle.spectral_model(st, spi, rf, fr, base=i), g["sm_int_%d" % n][i])
+            assert np.array_equal(ref, g["sm_int_%d" % n][i])
+    assert np.array_equal(oracle.spectral_model(st, g["spi2"], rf, fr, base=["std", "log", "log10"]),
+                          g["sm_list"])
+    assert np.array_equal(oracle.spectral_model(st[:, 0], g["spi2"][:, :, 0], rf, fr, base="log"),
+                          g["sm_nopol"])
+    f32 = np.float32
+    got = oracle.spectral_model(st.astype(f32), g["spi2"].astype(f32), rf.astype(f32), fr.astype(f32))
+    assert got.dtype == np.float32 and got.shape == g["sm_f32"].shape
+    assert rel_l2(got, g["sm_f32"]) < 1e-6
+    with pytest.raises(ValueError):
+        oracle.spectral_model(st, g["spi2"][:, :, 0], rf, fr)
+    with pytest.raises(ValueError):
+        oracle.spectral_model(st, g["spi2"], rf, fr, base="ln")
+
+
+def test_spectral_model_known_answer(golden, oracle):
+    """The reference test's independent numpy formulation
+    (model/spectral/tests/test_spectral_model.py / spec_model.py:11-54)."""
+    g = golden("brightness")
+    st, rf, fr, spi = g["stokes"], g["ref_freq"], g["freq"], g["spi2"]
+    ratio = fr[None, :] / rf[:, None]
+    std = st[:, None, :] * np.prod(ratio[:, None, :, None] ** spi[:, :, None, :], axis=1)
+    np.testing.assert_allclose(oracle.spectral_model(st, spi, rf, fr, base="std"), std, rtol=1e-13)
+    exps = np.arange(1, spi.shape[1] + 1)
+    lg = st[:, None, :] * np.exp(np.sum(spi[:, :, None, :] * np.log(ratio)[:, None, :, None]
+                                        ** exps[None, :, None, None], axis=1))
+    np.testing.assert_allclose(oracle.spectral_model(st, spi, rf, fr, base="log"), lg, rtol=1e-13)
+
+
+def test_convert_golden(golden, oracle):
+    """africanus.model.coherency.convert: Stokes -> linear / circular brightness (nested, flat,
+    implicit Stokes, two-element), correlations -> Stokes (complex, real, integer ids) --
+    bit-exact incl. dtype; and the reference test's known answers
+    (model/coherency/tests/test_convert.py:69-110)."""
+    g = golden("brightness")
+    sm, vis = g["sm_std_2"], g["vis"]
+    cases = [
+        ("b_linear", sm, _IQUV, _LIN, False), ("b_circular", sm, _IQUV, _CIRC, False),
+        ("b_flat", sm, _IQUV, ["XX", "XY", "YX", "YY"], False),
+        ("b_implicit", sm[..., :1], ["I"], ["XX", "XY", "YX", "YY"], True),
+        ("b_diag", sm[..., :2], ["I", "Q"], ["XX", "YY"], False),
+        ("b_f32", sm.astype(np.float32), _IQUV, _LIN, False),
+        ("s_linear", vis, _LIN, _IQUV, False), ("s_circular", vis, _CIRC, [["I", "Q"], ["U", "V"]], False),
+        ("s_int", vis[..., 0, :], [9, 12], [1, 2], False),
+        ("s_real", vis.real, _LIN, ["I", "Q"], False),
+    ]
+    for key, inp, isch, osch, implicit in cases:
+        got = oracle.convert(inp, isch, osch, implicit_stokes=implicit)
+        assert got.dtype == g[key].dtype and got.shape == g[key].shape, key
+        assert np.array_equal(got, g[key]), key
+    I, Q, U, V = 1.0 + 1j, 2.0 + 2j, 3.0 + 3j, 4.0 + 4j  # noqa: E741
+    inp = np.asarray([[I, Q, U, V]])
+    assert np.all(oracle.convert(inp, _IQUV, ["XX", "XY", "YX", "YY"])
+                  == [[I + Q, U + V * 1j, U - V * 1j, I - Q]])
+    assert np.all(oracle.convert(inp, _IQUV, ["RR", "RL", "LR", "LL"])
+                  == [[I + V, Q + U * 1j, Q - U * 1j, I - V]])
+    with pytest.raises(ValueError):
+        oracle.convert(sm[..., :1], ["I"], ["XX", "XY", "YX", "YY"])  # no implicit Stokes
+
+
+def test_wsclean_spectra_six_coefficients(golden, oracle):
+    """model.wsclean.spectra with powers up to 6 (numba int_power ordering), bit-exact."""
+    g = golden("brightness")
+    got = oracle.wsclean_spectra(g["stokes"][:, 0], g["w_coeffs"], g["w_log_poly"], g["ref_freq"], g["freq"])
+    assert np.array_equal(got, g["w_spectra"])
+
+
+def test_stokes_predict_composition_golden(golden, oracle):
+    """spectral_model -> convert -> phase_delay (x) brightness -> predict_vis with DIEs and base_vis
+    (rime/examples/predict.py:107-134,490,522-527), both feed types, bit-exact."""
+    g = golden("brightness")
+    sm = oracle.spectral_model(g["stokes"], g["spi2"], g["ref_freq"], g["freq"])
+    for feed, schema in (("linear", _LIN), ("circular", _CIRC)):
+        b = oracle.convert(sm, _IQUV, schema)
+        got = oracle.fused_predict(g["p_lm"], g["p_uvw"], g["freq"], b, g["p_time_index"], g["p_ant1"],
+                                   g["p_ant2"], None, None, g["p_die"], g["p_base_vis"], g["p_die"])
+        assert np.array_equal(got, g["p_" + feed])

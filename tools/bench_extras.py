@@ -133,6 +133,21 @@ def run(dev, fp64_peak):
     compute_entry("fused_point_predict_c128_cfg4_block", t, terms4, 39, fp64_peak,
                   "one row block (1 timestep, 19306 rows) x 4096 chan x 500 sources of configs[3]")
     del d_b4
+    # the same block with the brightness generated on the device from (stokes, spi, ref_freq)
+    # in chunks of 128 sources: 4 chunks -> 4 brightness kernels + 4 predict passes
+    stokes4 = np.stack([np.abs(rng.standard_normal(nsrc4))] + [0.1 * rng.standard_normal(nsrc4)] * 3, axis=1)
+    spi4 = np.full((nsrc4, 1, 4), -0.7)
+    d_st4, d_spi4, d_rf4 = T(stokes4), T(spi4), T(np.full(nsrc4, 1.284e9))
+    t = _timed(lambda: rime.fused_predict_vis_stokes(d_lm4, d_uvw4, d_f4, d_st4, d_spi4, d_rf4, d_t4, d_a14,
+                                                     d_a24, source_chunk=128))
+    compute_entry("fused_stokes_predict_c128_cfg4_block", t, terms4, 39, fp64_peak,
+                  "same block, brightness from (stokes, spi, ref_freq) on the device, 128-source chunks")
+    from codex_africanus_b200 import model
+    nsb = 20000
+    d_stb, d_spib, d_rfb = (T(np.resize(a, (nsb,) + a.shape[1:])) for a in (stokes4, spi4, np.full(nsrc4, 1.284e9)))
+    t = _timed(lambda: model.stokes_brightness(d_stb, d_spib, d_rfb, d_f4))
+    bw_entry("stokes_brightness_c128", t, nsb * nchan4 * 64.0,
+             note="20000 sources x 4096 chan -> (s,f,2,2) c128, std base, 1 spectral index; bytes = output")
 
     # ---- pure store reference for the phase_delay number: torch fill of the same bytes
     fill = torch.empty(2 << 30, dtype=torch.uint8, device=dev)
