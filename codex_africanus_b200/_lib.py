@@ -15,6 +15,8 @@ AFR_CHAN_EXACT = 0
 AFR_CHAN_UNIFORM = 1
 AFR_JONES_DIAG = 0
 AFR_JONES_2X2 = 1
+AFR_FEED_LINEAR = 0
+AFR_FEED_CIRCULAR = 1
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -42,6 +44,8 @@ PROTOTYPES = {
     "afr_predict_vis": (_int, [_vp] * 9 + [_i64] * 6 + [_int, _int, _vp, _vp]),
     "afr_predict_fused": (_int, [_vp] * 12 + [_i64] * 6 + [_int, _int, _int, _int, _vp, _vp]),
     "afr_beam_cube_dde": (_int, [_vp] * 8 + [_i64] * 8 + [_int, _vp, _vp]),
+    "afr_beam_cube_dde_rot": (_int, [_vp] * 9 + [_i64] * 8 + [_int, _vp, _vp]),
+    "afr_feed_rotation": (_int, [_vp, _i64, _int, _int, _vp, _vp]),
     "afr_freq_grid_interp": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "afr_wsclean_spectra": (_int, [_vp] * 5 + [_i64] * 3 + [_vp, _vp]),
     "afr_wsclean_predict": (_int, [_vp] * 9 + [_i64] * 5 + [_int, _vp, _vp]),

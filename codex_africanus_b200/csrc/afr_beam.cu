@@ -62,6 +62,7 @@ struct BeamParams {
     void *out;  // (nsrc,ntime,nant,nchan,ncorr)
     const void *babs;     // |beam| per element, same layout as beam without the re/im axis
     const double *pa_sc;  // (ntime,nant,2) sin, cos of the parallactic angles
+    const void *feed;     // optional (ntime,nant,2,2) complex feed rotation applied on the right
     double lower_l, lower_m, lscale, mscale, lmaxf, mmaxf;
     long long lw, mh, nud, nsrc, ntime, nant, nchan;
     int ncorr, coff;
@@ -102,7 +103,11 @@ __global__ void pa_sincos_kernel(const double *pa, long long n, double *sc) {
     sc[2 * i + 1] = cs;
 }
 
-template <typename T, int NC>
+// ROT (NC == 4 only): the epilogue right-multiplies the interpolated 2x2 Jones by the feed
+// rotation L[t,a] -- einsum("stafij,tajk->stafik", beam_dde, feed_rot) of
+// africanus/rime/examples/predict.py:469-472 -- before the one store, so the rotated DDE costs
+// no extra pass over the (source,time,ant,chan,2,2) array.
+template <typename T, int NC, bool ROT = false>
 __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) {
     const T *beam = (const T *)p.beam;
     const T *babs = (const T *)p.babs;
@@ -167,13 +172,50 @@ __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) 
             }
         }
         T *o = out + (i * p.ncorr + p.coff) * 2;
+        T er[NC], ei[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {  // :227-238
             const T div = habs(csr[c], csi[c]);
             const T k = (div == T(0)) ? asum[c] : asum[c] / div;
-            o[2 * c] = csr[c] * k;
-            o[2 * c + 1] = csi[c] * k;
+            er[c] = csr[c] * k;
+            ei[c] = csi[c] * k;
         }
+        if (ROT && NC == 4) {
+            const T *L = (const T *)p.feed + (t * p.nant + a) * 8;
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {  // out[r,k] = E[r,0] L[0,k] + E[r,1] L[1,k]
+                    const T l0r = L[2 * k], l0i = L[2 * k + 1], l1r = L[2 * (2 + k)], l1i = L[2 * (2 + k) + 1];
+                    const T e0r = er[(2 * r) % NC], e0i = ei[(2 * r) % NC];
+                    const T e1r = er[(2 * r + 1) % NC], e1i = ei[(2 * r + 1) % NC];
+                    o[2 * (2 * r + k)] = (e0r * l0r - e0i * l0i) + (e1r * l1r - e1i * l1i);
+                    o[2 * (2 * r + k) + 1] = (e0r * l0i + e0i * l0r) + (e1r * l1i + e1i * l1r);
+                }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                o[2 * c] = er[c];
+                o[2 * c + 1] = ei[c];
+            }
+        }
+    }
+}
+
+// africanus/rime/feeds.py:13-48: (n,) parallactic angles -> (n,2,2) complex.
+// linear [[cos, sin], [-sin, cos]]; circular diag(exp(-i pa), exp(+i pa))
+template <typename T>
+__global__ void feed_rotation_kernel(const double *pa, long long n, int circular, T *out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double sn, cs;
+    sincos(pa[i], &sn, &cs);
+    T *o = out + 8 * i;
+    const T c = (T)cs, s = (T)sn, z = T(0);
+    if (circular) {
+        o[0] = c, o[1] = -s, o[2] = z, o[3] = z, o[4] = z, o[5] = z, o[6] = c, o[7] = s;
+    } else {
+        o[0] = c, o[1] = z, o[2] = s, o[3] = z, o[4] = -s, o[5] = z, o[6] = c, o[7] = z;
     }
 }
 
@@ -194,7 +236,10 @@ int launch_beam(BeamParams p, cudaStream_t stream) {
     while (c < p.ncorr) {  // correlations are independent: blocks of 4, 2, 1
         p.coff = c;
         if (p.ncorr - c >= 4) {
-            beam_cube_dde_kernel<T, 4><<<grid, 256, 0, stream>>>(p);
+            if (p.feed)
+                beam_cube_dde_kernel<T, 4, true><<<grid, 256, 0, stream>>>(p);
+            else
+                beam_cube_dde_kernel<T, 4><<<grid, 256, 0, stream>>>(p);
             c += 4;
         } else if (p.ncorr - c >= 2) {
             beam_cube_dde_kernel<T, 2><<<grid, 256, 0, stream>>>(p);
@@ -225,6 +270,22 @@ extern "C" int afr_freq_grid_interp(const double *freq, const double *beam_freq_
     return 0;
 }
 
+extern "C" int afr_feed_rotation(const double *parallactic_angles, int64_t n, int feed_type,
+                                 int is_c64, void *out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AFR_REQUIRE(n >= 0, "negative extent");
+    AFR_REQUIRE(feed_type == AFR_FEED_LINEAR || feed_type == AFR_FEED_CIRCULAR, "Invalid feed_type");
+    if (n == 0) return 0;
+    if (is_c64)
+        feed_rotation_kernel<float><<<(int)((n + 255) / 256), 256, 0, stream>>>(parallactic_angles, n,
+                                                                                feed_type, (float *)out);
+    else
+        feed_rotation_kernel<double><<<(int)((n + 255) / 256), 256, 0, stream>>>(parallactic_angles, n,
+                                                                                 feed_type, (double *)out);
+    AFR_LAUNCH_OK();
+    return 0;
+}
+
 extern "C" int afr_beam_cube_dde(const void *beam, const double *ext_host_or_dev,
                                  const double *beam_freq_map, const double *lm,
                                  const double *parallactic_angles, const double *point_errors,
@@ -232,7 +293,21 @@ extern "C" int afr_beam_cube_dde(const void *beam, const double *ext_host_or_dev
                                  int64_t mh, int64_t nud, int64_t ncorr, int64_t nsrc,
                                  int64_t ntime, int64_t nant, int64_t nchan, int is_c64,
                                  void *out, void *stream_) {
+    return afr_beam_cube_dde_rot(beam, ext_host_or_dev, beam_freq_map, lm, parallactic_angles,
+                                 point_errors, antenna_scaling, freq, nullptr, lw, mh, nud, ncorr, nsrc,
+                                 ntime, nant, nchan, is_c64, out, stream_);
+}
+
+extern "C" int afr_beam_cube_dde_rot(const void *beam, const double *ext_host_or_dev,
+                                     const double *beam_freq_map, const double *lm,
+                                     const double *parallactic_angles, const double *point_errors,
+                                     const double *antenna_scaling, const double *freq,
+                                     const void *feed_rotation, int64_t lw, int64_t mh, int64_t nud,
+                                     int64_t ncorr, int64_t nsrc, int64_t ntime, int64_t nant,
+                                     int64_t nchan, int is_c64, void *out, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    AFR_REQUIRE(feed_rotation == nullptr || ncorr == 4,
+                "a feed rotation needs 2x2 correlations (beam of shape (lw,mh,nud,2,2))");
     // fast_beam_cubes.py:74-75
     AFR_REQUIRE(lw >= 2 && mh >= 2 && nud >= 2, "beam_lw, beam_mh and beam_nud must be >= 2");
     AFR_REQUIRE(ncorr >= 1 && nsrc >= 0 && ntime >= 0 && nant >= 0 && nchan >= 0, "bad extent");
@@ -265,6 +340,7 @@ extern "C" int afr_beam_cube_dde(const void *beam, const double *ext_host_or_dev
     p.beam = beam;
     p.babs = babs.ptr;
     p.pa_sc = (const double *)pasc.ptr;
+    p.feed = feed_rotation;
     p.fd = (const double *)fd.ptr;
     p.lm = lm;
     p.pa = parallactic_angles;

@@ -29,6 +29,18 @@ def beam_cube_dde(beam, beam_lm_extents, beam_freq_map, lm, parallactic_angles, 
     beam (lw, mh, nud, corr...) complex -> (source, time, ant, chan, corr...) in
     ``beam.dtype``.  Coordinate arithmetic is float64.
     """
+    return beam_cube_dde_rotated(beam, beam_lm_extents, beam_freq_map, lm, parallactic_angles,
+                                 point_errors, antenna_scaling, frequency, None)
+
+
+def beam_cube_dde_rotated(beam, beam_lm_extents, beam_freq_map, lm, parallactic_angles, point_errors,
+                          antenna_scaling, frequency, feed_rotation):
+    """``einsum("stafij,tajk->stafik", beam_cube_dde(...), feed_rotation)`` -- the DDE term of
+    africanus/rime/examples/predict.py:469-472 -- with the product done in the interpolation
+    kernel's epilogue (no second pass over the DDE array).  ``feed_rotation`` (time, ant, 2, 2)
+    complex (see ``feed_rotation``) or None for the plain ``beam_cube_dde``; needs a
+    (lw, mh, nud, 2, 2) beam.
+    """
     bshape = pl.shape_of(beam)
     if len(bshape) < 3:
         raise ValueError("beam must have at least 3 dimensions")
@@ -45,14 +57,20 @@ def beam_cube_dde(beam, beam_lm_extents, beam_freq_map, lm, parallactic_angles, 
     nchan = pl.shape_of(frequency)[0]
     args = (beam, beam_lm_extents, beam_freq_map, lm, parallactic_angles, point_errors,
             antenna_scaling, frequency)
-    device = pl.pick_device(*args)
-    as_torch = pl.wants_torch(*args)
+    if feed_rotation is not None:
+        if corrs != (2, 2):
+            raise ValueError("a feed rotation needs a beam of shape (lw, mh, nud, 2, 2)")
+        if tuple(pl.shape_of(feed_rotation)) != (ntime, nant, 2, 2):
+            raise ValueError("feed_rotation must have shape (time, ant, 2, 2)")
+    device = pl.pick_device(*args, feed_rotation)
+    as_torch = pl.wants_torch(*args, feed_rotation)
     f64 = np.float64
     with torch.cuda.device(device):
         d_beam = pl.to_device(beam, bdt, device)
         d = [pl.to_device(a, f64, device) for a in args[1:]]
+        d_rot = None if feed_rotation is None else pl.to_device(feed_rotation, bdt, device)
         d_out = pl.empty_device((nsrc, ntime, nant, nchan) + corrs, bdt, device)
-        pl.call("afr_beam_cube_dde", device, pl.ptr(d_beam), *(pl.ptr(x) for x in d),
+        pl.call("afr_beam_cube_dde_rot", device, pl.ptr(d_beam), *(pl.ptr(x) for x in d), pl.ptr(d_rot),
                 lw, mh, nud, ncorr, nsrc, ntime, nant, nchan, int(bdt == np.complex64),
                 pl.ptr(d_out), pl.stream_ptr(device))
         return d_out if as_torch else pl.to_host(d_out)

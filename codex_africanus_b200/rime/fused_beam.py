@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 from .. import _plumbing as pl
-from .fast_beam_cubes import beam_cube_dde
+from .fast_beam_cubes import beam_cube_dde_rotated
+from .feeds import feed_rotation
 from .fused import fused_predict_vis
 from .predict import apply_gains
 
@@ -26,11 +27,14 @@ _DDE_CHUNK_BYTES = 4 << 30
 def fused_predict_vis_beam(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
                            beam, beam_lm_extents, beam_freq_map, parallactic_angles,
                            point_errors, antenna_scaling, die1_jones=None, base_vis=None,
-                           die2_jones=None, convention="fourier", source_chunk=None):
+                           die2_jones=None, convention="fourier", source_chunk=None, feed_type=None):
     """``fused_predict_vis(..., dde1 = dde2 = beam_cube_dde(beam, ..., lm, ...))`` without the
     full DDE array.  Arguments: those of ``fused_predict_vis`` with the two DDE arrays replaced
     by the arguments of ``beam_cube_dde``; ``source_chunk`` (sources per chunk) defaults to
-    what fits ``_DDE_CHUNK_BYTES``.  Returns (row, chan, corr...) like ``predict_vis``."""
+    what fits ``_DDE_CHUNK_BYTES``.  ``feed_type`` "linear" / "circular" additionally multiplies
+    the beam by the feed rotation of the same parallactic angles, ``dde = beam_dde . L[t,a]``
+    (africanus/rime/examples/predict.py:469-472, rime/feeds.py:13-48), inside the interpolation
+    kernel.  Returns (row, chan, corr...) like ``predict_vis``."""
     if (die1_jones is None) != (die2_jones is None):
         raise ValueError("Both die1_jones and die2_jones must be present or absent")
     bshape = pl.shape_of(beam)
@@ -68,9 +72,14 @@ def fused_predict_vis_beam(lm, uvw, frequency, brightness, time_index, antenna1,
         d_a2 = antenna2 if pl.is_torch(antenna2) else torch.from_numpy(np.ascontiguousarray(antenna2))
         d_ti, d_a1, d_a2 = (x.to(device) for x in (d_ti, d_a1, d_a2))
         acc = None if base_vis is None else pl.to_device(base_vis, out_dtype, device)
+        d_rot = None
+        if feed_type is not None:
+            d_rot = feed_rotation(d_pa, feed_type)
+            if pl.dtype_of(d_rot) != bdt:
+                d_rot = d_rot.to(pl.torch_dtype(bdt))
         for s0 in range(0, nsrc, source_chunk):
             s1 = min(nsrc, s0 + source_chunk)
-            dde = beam_cube_dde(d_beam, d_ext, d_bfm, d_lm[s0:s1], d_pa, d_pe, d_as, d_f)
+            dde = beam_cube_dde_rotated(d_beam, d_ext, d_bfm, d_lm[s0:s1], d_pa, d_pe, d_as, d_f, d_rot)
             if dde.dtype != d_b.dtype:
                 dde = dde.to(d_b.dtype)
             acc = fused_predict_vis(d_lm[s0:s1], d_uvw, d_f, d_b[s0:s1], d_ti, d_a1, d_a2, dde, dde,

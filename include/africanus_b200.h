@@ -149,6 +149,24 @@ int afr_beam_cube_dde(const void *beam, const double *beam_lm_extents,
                       const double *antenna_scaling, const double *freq, int64_t lw, int64_t mh,
                       int64_t nud, int64_t ncorr, int64_t nsrc, int64_t ntime, int64_t nant,
                       int64_t nchan, int is_c64, void *out, void *stream);
+/* The same with the feed rotation of africanus/rime/examples/predict.py:469-472 applied in the
+ * kernel's epilogue: out = einsum("stafij,tajk->stafik", beam_cube_dde(...), feed_rotation).
+ * feed_rotation (ntime,nant,2,2) complex of the beam's precision, or NULL (= afr_beam_cube_dde);
+ * requires ncorr == 4. */
+int afr_beam_cube_dde_rot(const void *beam, const double *beam_lm_extents,
+                          const double *beam_freq_map, const double *lm,
+                          const double *parallactic_angles, const double *point_errors,
+                          const double *antenna_scaling, const double *freq,
+                          const void *feed_rotation, int64_t lw, int64_t mh, int64_t nud,
+                          int64_t ncorr, int64_t nsrc, int64_t ntime, int64_t nant, int64_t nchan,
+                          int is_c64, void *out, void *stream);
+/* feed_rotation (africanus/rime/feeds.py:13-71): parallactic_angles (n,) float64 -> out (n,2,2)
+ * complex128 (is_c64 0) / complex64 (1).  AFR_FEED_LINEAR [[cos,sin],[-sin,cos]],
+ * AFR_FEED_CIRCULAR diag(exp(-i pa), exp(+i pa)). */
+#define AFR_FEED_LINEAR 0
+#define AFR_FEED_CIRCULAR 1
+int afr_feed_rotation(const double *parallactic_angles, int64_t n, int feed_type, int is_c64,
+                      void *out, void *stream);
 /* freq_grid_interp (fast_beam_cubes.py:10-54): freq_data (nchan,3) float64 */
 int afr_freq_grid_interp(const double *freq, const double *beam_freq_map, int64_t nchan,
                          int64_t nud, double *freq_data, void *stream);

@@ -414,3 +414,20 @@ def convert(input, input_schema, output_schema, implicit_stokes=False):
     assert rc == 0, rc
     out = out.reshape(lead + out_shape)
     return (out if np.issubdtype(dtype, np.complexfloating) else out.real).astype(dtype)
+
+
+# ---------------------------------------------------------------------------
+def feed_rotation(parallactic_angles, feed_type="linear"):
+    """africanus/rime/feeds.py:13-71."""
+    if feed_type not in ("linear", "circular"):
+        raise ValueError("Invalid feed_type '%s'" % feed_type)
+    pa = np.asarray(parallactic_angles)
+    if pa.dtype not in (np.float32, np.float64):
+        raise ValueError("parallactic_angles has none-floating point type %s" % pa.dtype)
+    f32 = pa.dtype == np.float32
+    flat = _as(pa.reshape(-1), pa.dtype)
+    out = np.zeros((flat.shape[0], 2, 2), np.complex64 if f32 else np.complex128)
+    fn = lib().orc_feed_rotation_f32 if f32 else lib().orc_feed_rotation_f64
+    rc = fn(_p(flat), _i64(flat.shape[0]), _int(feed_type == "circular"), _p(out))
+    assert rc == 0, rc
+    return out.reshape(pa.shape + (2, 2))

@@ -839,3 +839,35 @@ int orc_convert(const double *in, int64_t n, int64_t nin, const int *src1, const
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------ */
+/* feed_rotation: africanus/rime/feeds.py:13-48.  out (n,2,2) complex.       */
+/* feed_type 0 linear [[cos, sin], [-sin, cos]]; 1 circular diag(e^-ipa, e^+ipa) */
+/* ------------------------------------------------------------------------ */
+int orc_feed_rotation_f64(const double *pa, int64_t n, int feed_type, double *out) {
+    if (feed_type != 0 && feed_type != 1) return 1;
+    for (int64_t i = 0; i < n; ++i) {
+        const double c = cos(pa[i]), s = sin(pa[i]);
+        double *o = out + 8 * i;
+        if (feed_type == 0) {
+            o[0] = c; o[1] = 0.0; o[2] = s; o[3] = 0.0; o[4] = -s; o[5] = 0.0; o[6] = c; o[7] = 0.0;
+        } else {
+            o[0] = c; o[1] = -s; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0; o[5] = 0.0; o[6] = c; o[7] = s;
+        }
+    }
+    return 0;
+}
+
+int orc_feed_rotation_f32(const float *pa, int64_t n, int feed_type, float *out) {
+    if (feed_type != 0 && feed_type != 1) return 1;
+    for (int64_t i = 0; i < n; ++i) {
+        const float c = cosf(pa[i]), s = sinf(pa[i]);
+        float *o = out + 8 * i;
+        if (feed_type == 0) {
+            o[0] = c; o[1] = 0.0f; o[2] = s; o[3] = 0.0f; o[4] = -s; o[5] = 0.0f; o[6] = c; o[7] = 0.0f;
+        } else {
+            o[0] = c; o[1] = -s; o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f; o[5] = 0.0f; o[6] = c; o[7] = s;
+        }
+    }
+    return 0;
+}

@@ -348,6 +348,46 @@ def gen_brightness():
     save("brightness", **out)
 
 
+def gen_feeds():
+    """africanus.rime.feed_rotation (rime/feeds.py) and the DDE term of the predict example
+    (rime/examples/predict.py:469-472): einsum("stafij,tajk->stafik", beam_cube_dde, feed_rot),
+    carried through phase_delay (x) brightness -> predict_vis."""
+    from africanus.rime.feeds import feed_rotation
+
+    out = {}
+    rng = np.random.default_rng(4711)
+    na, ntime, nsrc, nchan = 6, 3, 9, 12
+    pa = rng.uniform(-np.pi, np.pi, (ntime, na))
+    out["pa"] = pa
+    for ft in ("linear", "circular"):
+        out["rot_" + ft] = feed_rotation(pa, ft)
+        out["rot32_" + ft] = feed_rotation(pa.astype(np.float32), ft)
+    a1, a2 = np.triu_indices(na, 1)
+    ant1, ant2 = np.tile(a1, ntime).astype(np.int32), np.tile(a2, ntime).astype(np.int32)
+    time_index = np.repeat(np.arange(ntime), a1.size).astype(np.int32)
+    pos = rng.standard_normal((ntime, na, 3)) * 900.0
+    uvw = (pos[:, a1] - pos[:, a2]).reshape(-1, 3)
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    freq = np.linspace(0.856e9, 1.712e9, nchan)
+    beam = rc(rng, (9, 9, 5, 2, 2))
+    ext = np.array([[-0.03, 0.03], [-0.03, 0.03]])
+    bfm = np.linspace(0.8e9, 1.8e9, 5)
+    pe = rng.uniform(-1e-3, 1e-3, (ntime, na, nchan, 2))
+    asc = rng.uniform(0.9, 1.1, (na, nchan, 2))
+    bright = rc(rng, (nsrc, nchan, 2, 2))
+    die = 1.0 + 0.1 * rc(rng, (ntime, na, nchan, 2, 2))
+    K = phase_delay(lm, uvw, freq)
+    coh = np.einsum("srf,sfij->srfij", K, bright)
+    beam_dde = beam_cube_dde(beam, ext, bfm, lm, pa, pe, asc, freq)
+    out.update(uvw=uvw, lm=lm, freq=freq, beam=beam, ext=ext, bfm=bfm, pe=pe, asc=asc, bright=bright,
+               die=die, ant1=ant1, ant2=ant2, time_index=time_index)
+    for ft in ("linear", "circular"):
+        dde = np.einsum("stafij,tajk->stafik", beam_dde, out["rot_" + ft])
+        out["dde_" + ft] = dde
+        out["vis_" + ft] = predict_vis(time_index, ant1, ant2, dde, coh, dde, die, None, die)
+    save("feeds", **out)
+
+
 if __name__ == "__main__":
     gen_phase()
     gen_dft()
@@ -356,3 +396,4 @@ if __name__ == "__main__":
     gen_fused()
     gen_wsclean()
     gen_brightness()
+    gen_feeds()

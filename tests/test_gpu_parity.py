@@ -846,3 +846,41 @@ def test_fused_predict_vis_stokes(b200, golden, oracle):
     assert rel_l2(got.astype(np.complex128), ref0) < 1e-5
     with pytest.raises(ValueError):
         f(lm, uvw, fr, st, spi, rf, ti, a1, a2, die1_jones=die)
+
+
+# ----------------------------------------------------------------------------- feed rotation (8f-1)
+def test_feed_rotation_and_rotated_beam_predict(b200, golden):
+    """feed_rotation, the rotated DDE produced in the beam kernel's epilogue, and the chunked
+    beam-interpolated predict with feed_type -- against the reference's outputs
+    (rime/feeds.py:13-71, rime/examples/predict.py:469-472,522-527)."""
+    import torch
+
+    g = golden("feeds")
+    beam_args = (g["beam"], g["ext"], g["bfm"], g["lm"], g["pa"], g["pe"], g["asc"], g["freq"])
+    for ft in ("linear", "circular"):
+        rot = b200.rime.feed_rotation(g["pa"], ft)
+        assert_c128_close(rot, g["rot_" + ft], rtol=1e-15)
+        rot32 = b200.rime.feed_rotation(g["pa"].astype(np.float32), ft)
+        assert_c64_close(rot32, g["rot32_" + ft], tol=2e-7)
+        dde = b200.rime.beam_cube_dde_rotated(*beam_args, rot)
+        assert_c128_close(dde, g["dde_" + ft])
+        got = b200.rime.fused_predict_vis_beam(g["lm"], g["uvw"], g["freq"], g["bright"], g["time_index"],
+                                               g["ant1"], g["ant2"], *beam_args[:3], *beam_args[4:7],
+                                               g["die"], None, g["die"], source_chunk=4, feed_type=ft)
+        assert_c128_close(got, g["vis_" + ft])
+    # complex64 beam: rotation applied in float32; torch inputs
+    c64 = np.complex64
+    ref = np.einsum("stafij,tajk->stafik",
+                    b200.rime.beam_cube_dde(g["beam"].astype(c64), *beam_args[1:]).astype(np.complex128),
+                    g["rot_linear"])
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    got = b200.rime.beam_cube_dde_rotated(T(g["beam"].astype(c64)), *(T(a) for a in beam_args[1:]),
+                                          T(g["rot_linear"].astype(c64)))
+    assert got.dtype == torch.complex64
+    assert rel_l2(got.cpu().numpy().astype(np.complex128), ref) < 1e-6
+    with pytest.raises(ValueError):
+        b200.rime.feed_rotation(g["pa"], "elliptical")
+    with pytest.raises(ValueError):
+        b200.rime.feed_rotation(g["pa"].astype(np.int32))
+    with pytest.raises(ValueError):
+        b200.rime.beam_cube_dde_rotated(g["beam"][..., 0], *beam_args[1:], g["rot_linear"])

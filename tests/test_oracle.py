@@ -447,3 +447,31 @@ def test_stokes_predict_composition_golden(golden, oracle):
         got = oracle.fused_predict(g["p_lm"], g["p_uvw"], g["freq"], b, g["p_time_index"], g["p_ant1"],
                                    g["p_ant2"], None, None, g["p_die"], g["p_base_vis"], g["p_die"])
         assert np.array_equal(got, g["p_" + feed])
+
+
+# ----------------------------------------------------------------------------- feed rotation (8f-1)
+def test_feed_rotation_and_rotated_dde_golden(golden, oracle):
+    """africanus.rime.feed_rotation (feeds.py:13-71), bit-exact for float64 and float32 angles, and
+    the DDE term of rime/examples/predict.py:469-472 -- einsum("stafij,tajk->stafik", beam_cube_dde,
+    feed_rot) -- carried through the fused predict, bit-exact."""
+    g = golden("feeds")
+    for ft in ("linear", "circular"):
+        rot = oracle.feed_rotation(g["pa"], ft)
+        assert rot.dtype == np.complex128 and np.array_equal(rot, g["rot_" + ft])
+        rot32 = oracle.feed_rotation(g["pa"].astype(np.float32), ft)
+        assert rot32.dtype == np.complex64 and np.array_equal(rot32, g["rot32_" + ft])
+        bd = oracle.beam_cube_dde(g["beam"], g["ext"], g["bfm"], g["lm"], g["pa"], g["pe"], g["asc"], g["freq"])
+        dde = np.einsum("stafij,tajk->stafik", bd, rot)
+        assert np.array_equal(dde, g["dde_" + ft])
+        vis = oracle.fused_predict(g["lm"], g["uvw"], g["freq"], g["bright"], g["time_index"], g["ant1"],
+                                   g["ant2"], dde, dde, g["die"], None, g["die"])
+        assert np.array_equal(vis, g["vis_" + ft])
+    # known answers (feeds.py:80-95): unitary; linear is a real rotation, circular is diagonal
+    lin, circ = g["rot_linear"], g["rot_circular"]
+    eye = np.broadcast_to(np.eye(2), lin.shape)
+    np.testing.assert_allclose(np.einsum("taij,takj->taik", lin, lin.conj()), eye, atol=1e-15)
+    np.testing.assert_allclose(np.einsum("taij,takj->taik", circ, circ.conj()), eye, atol=1e-15)
+    np.testing.assert_allclose(circ[..., 0, 0], np.exp(-1j * g["pa"]), rtol=1e-15)
+    assert np.all(circ[..., 0, 1] == 0) and np.all(lin.imag == 0)
+    with pytest.raises(ValueError):
+        oracle.feed_rotation(g["pa"], "elliptical")
