@@ -55,6 +55,20 @@ __device__ __forceinline__ Cd cmulc_(Cd a, Cd b) {  // a * conj(b)
     return {a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im};
 }
 __device__ __forceinline__ Cd cadd_(Cd a, Cd b) { return {a.re + b.re, a.im + b.im}; }
+// acc += a * conj(b) / acc += a * b as four chained DFMA (no separate DMUL / DADD: the consumer
+// loop is FP64-issue and register-file bound, and a DFMA costs no more than either of those)
+__device__ __forceinline__ void cfmac_(Cd &acc, Cd a, Cd b) {
+    acc.re = fma(a.re, b.re, acc.re);
+    acc.im = fma(a.im, b.re, acc.im);
+    acc.re = fma(a.im, b.im, acc.re);
+    acc.im = fma(-a.re, b.im, acc.im);
+}
+__device__ __forceinline__ void cfma_(Cd &acc, Cd a, Cd b) {
+    acc.re = fma(a.re, b.re, acc.re);
+    acc.im = fma(a.re, b.im, acc.im);
+    acc.re = fma(-a.im, b.im, acc.re);
+    acc.im = fma(a.im, b.re, acc.im);
+}
 
 __device__ __forceinline__ Cd lds_c(const unsigned char *p) {
     const double2 v = *reinterpret_cast<const double2 *>(p);
@@ -282,14 +296,21 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
                 for (int h = 0; h < 2; ++h) {  // one output row of A * E^H at a time
                     const Cd x0 = lds_c(am + j * kMatBytes + 32 * h);
                     const Cd x1 = lds_c(am + j * kMatBytes + 32 * h + 16);
-                    const Cd m0 = cadd_(cmulc_(x0, q0), cmulc_(x1, q1));
-                    const Cd m1 = cadd_(cmulc_(x0, q2), cmulc_(x1, q3));
                     if (ANT) {
-                        acc[k][j][2 * h] = cadd_(acc[k][j][2 * h], m0);
-                        acc[k][j][2 * h + 1] = cadd_(acc[k][j][2 * h + 1], m1);
+                        // 16 DFMA per output row, accumulated in place (32 per term; the
+                        // mul / fma / add form was 48 FP64 instructions per term)
+                        cfmac_(acc[k][j][2 * h], x0, q0);
+                        cfmac_(acc[k][j][2 * h + 1], x0, q2);
+                        cfmac_(acc[k][j][2 * h], x1, q1);
+                        cfmac_(acc[k][j][2 * h + 1], x1, q3);
                     } else {
-                        acc[k][j][2 * h] = cadd_(acc[k][j][2 * h], cmul_(z, m0));
-                        acc[k][j][2 * h + 1] = cadd_(acc[k][j][2 * h + 1], cmul_(z, m1));
+                        Cd m0 = {x0.re * q0.re, x0.im * q0.re}, m1 = {x0.re * q2.re, x0.im * q2.re};
+                        m0.re = fma(x0.im, q0.im, m0.re), m0.im = fma(-x0.re, q0.im, m0.im);
+                        m1.re = fma(x0.im, q2.im, m1.re), m1.im = fma(-x0.re, q2.im, m1.im);
+                        cfmac_(m0, x1, q1);
+                        cfmac_(m1, x1, q3);
+                        cfma_(acc[k][j][2 * h], z, m0);
+                        cfma_(acc[k][j][2 * h + 1], z, m1);
                     }
                 }
                 if (!ANT && !EXACT && j + 1 < FT) {

@@ -142,6 +142,23 @@ def run(dev, fp64_peak):
                                                      d_a24, source_chunk=128))
     compute_entry("fused_stokes_predict_c128_cfg4_block", t, terms4, 39, fp64_peak,
                   "same block, brightness from (stokes, spi, ref_freq) on the device, 128-source chunks")
+    # row-block streaming driver, host buffers in and out: 3 timesteps of the SKA-Mid layout x 1024
+    # channels, one timestep (19306 rows, 1.27 GB of visibilities) per block, D2H of block i under
+    # the compute of block i+1
+    from codex_africanus_b200.rime.stream import stream_predict_vis_stokes
+    uvw4s, tidx4s, a14s, a24s = synth.uvw_tracks(na4, 3, rng, ntime_total=1000, max_radius=150e3)
+    freq4s = synth.frequencies(1024)
+
+    def stream_all():
+        tot = 0.0
+        for _, blk in stream_predict_vis_stokes(lm4, uvw4s, freq4s, stokes4, spi4, np.full(nsrc4, 1.284e9),
+                                                tidx4s, a14s, a24s, rows_per_block=uvw4.shape[0]):
+            tot += float(blk[0, 0, 0, 0].real)
+        return tot
+
+    t = _timed(stream_all, reps=1)
+    compute_entry("stream_stokes_predict_c128_ska_3blocks_e2e", t, float(nsrc4) * uvw4s.shape[0] * 1024, 39,
+                  fp64_peak, "numpy in -> numpy blocks out (3 x 1.27 GB), H2D + D2H inside the timed region")
     from codex_africanus_b200 import model
     nsb = 20000
     d_stb, d_spib, d_rfb = (T(np.resize(a, (nsb,) + a.shape[1:])) for a in (stokes4, spi4, np.full(nsrc4, 1.284e9)))
