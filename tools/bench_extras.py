@@ -134,14 +134,19 @@ def run(dev, fp64_peak):
                   "one row block (1 timestep, 19306 rows) x 4096 chan x 500 sources of configs[3]")
     del d_b4
     # the same block with the brightness generated on the device from (stokes, spi, ref_freq)
-    # in chunks of 128 sources: 4 chunks -> 4 brightness kernels + 4 predict passes
+    # (SURVEY.md 8f-2), default chunking (one chunk here) and forced 128-source chunks (4 brightness
+    # kernels + 4 predict passes, each re-reading and re-writing the 5 GB accumulator)
     stokes4 = np.stack([np.abs(rng.standard_normal(nsrc4))] + [0.1 * rng.standard_normal(nsrc4)] * 3, axis=1)
     spi4 = np.full((nsrc4, 1, 4), -0.7)
     d_st4, d_spi4, d_rf4 = T(stokes4), T(spi4), T(np.full(nsrc4, 1.284e9))
     t = _timed(lambda: rime.fused_predict_vis_stokes(d_lm4, d_uvw4, d_f4, d_st4, d_spi4, d_rf4, d_t4, d_a14,
-                                                     d_a24, source_chunk=128))
+                                                     d_a24))
     compute_entry("fused_stokes_predict_c128_cfg4_block", t, terms4, 39, fp64_peak,
-                  "same block, brightness from (stokes, spi, ref_freq) on the device, 128-source chunks")
+                  "same block, brightness from (stokes, spi, ref_freq) on the device, default chunking")
+    t = _timed(lambda: rime.fused_predict_vis_stokes(d_lm4, d_uvw4, d_f4, d_st4, d_spi4, d_rf4, d_t4, d_a14,
+                                                     d_a24, source_chunk=128))
+    compute_entry("fused_stokes_predict_c128_cfg4_block_128src_chunks", t, terms4, 39, fp64_peak,
+                  "same, forced 128-source chunks: 4 passes over the 5 GB accumulator")
     # row-block streaming driver, host buffers in and out: 3 timesteps of the SKA-Mid layout x 1024
     # channels, one timestep (19306 rows, 1.27 GB of visibilities) per block, D2H of block i under
     # the compute of block i+1
@@ -149,16 +154,21 @@ def run(dev, fp64_peak):
     uvw4s, tidx4s, a14s, a24s = synth.uvw_tracks(na4, 3, rng, ntime_total=1000, max_radius=150e3)
     freq4s = synth.frequencies(1024)
 
+    nss = 2000  # enough sources that a block's compute (~65 ms) exceeds its D2H copy (~25 ms)
+    lm4s = synth.sky_lm(nss, rng)
+    stokes4s, spi4s = np.resize(stokes4, (nss, 4)), np.resize(spi4, (nss, 1, 4))
+
     def stream_all():
         tot = 0.0
-        for _, blk in stream_predict_vis_stokes(lm4, uvw4s, freq4s, stokes4, spi4, np.full(nsrc4, 1.284e9),
+        for _, blk in stream_predict_vis_stokes(lm4s, uvw4s, freq4s, stokes4s, spi4s, np.full(nss, 1.284e9),
                                                 tidx4s, a14s, a24s, rows_per_block=uvw4.shape[0]):
             tot += float(blk[0, 0, 0, 0].real)
         return tot
 
     t = _timed(stream_all, reps=1)
-    compute_entry("stream_stokes_predict_c128_ska_3blocks_e2e", t, float(nsrc4) * uvw4s.shape[0] * 1024, 39,
-                  fp64_peak, "numpy in -> numpy blocks out (3 x 1.27 GB), H2D + D2H inside the timed region")
+    compute_entry("stream_stokes_predict_c128_ska_3blocks_e2e", t, float(nss) * uvw4s.shape[0] * 1024, 39,
+                  fp64_peak, "2000 sources; numpy in -> numpy blocks out (3 x 1.27 GB), H2D + D2H inside the "
+                  "timed region")
     from codex_africanus_b200 import model
     nsb = 20000
     d_stb, d_spib, d_rfb = (T(np.resize(a, (nsb,) + a.shape[1:])) for a in (stokes4, spi4, np.full(nsrc4, 1.284e9)))
