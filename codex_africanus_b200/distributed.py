@@ -138,3 +138,42 @@ def sharded_vis_to_im(vis, uvw, lm, frequency, flags, time_index, convention="fo
     t = _to_tensor(partial, dev).contiguous()
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.cpu().numpy() if as_numpy else t
+
+
+def sharded_stream_predict_vis_stokes(lm, uvw, frequency, stokes, spi, ref_freq, time_index, antenna1,
+                                      antenna2, dde1_jones=None, dde2_jones=None, die1_jones=None,
+                                      base_vis=None, die2_jones=None, group=None, **kwargs):
+    """SKA-Mid-scale predict (BASELINE configs[3]) on N GPUs: rows are sharded over the ranks in
+    whole-timestep blocks (``row_shards``) and every rank streams ITS shard block by block with
+    ``rime.stream_predict_vis_stokes`` -- brightness generated on the device from the catalogue
+    columns, DDE / DIE arrays sliced to the block's timesteps, finished blocks copied out under the
+    next block's compute.  No collective: like the reference's dask row chunks
+    (africanus/rime/dask_predict.py:667-726) the blocks are independent and each rank writes its
+    own.  Yields ``((row0, row1), vis_block)`` with GLOBAL row indices.  ``kwargs`` go to
+    ``stream_predict_vis_stokes`` (rows_per_block, block_bytes, convention, base, corr_schema,
+    local_fn, ...)."""
+    from .rime.stream import stream_predict_vis_stokes
+
+    rank, world = _rank_world(group)
+    r0, r1 = row_shards(time_index, world)[rank]
+    if r1 <= r0:
+        return
+    ti = np.asarray(time_index.cpu() if isinstance(time_index, torch.Tensor) else time_index)
+    tmin = int(ti.min())
+    t_lo, t_hi = int(ti[r0]) - tmin, int(ti[r1 - 1]) - tmin + 1
+
+    def tslice(a, axis):
+        if a is None:
+            return None
+        idx = [slice(None)] * a.ndim
+        idx[axis] = slice(t_lo, t_hi)
+        return a[tuple(idx)]
+
+    e1 = tslice(dde1_jones, 1)
+    e2 = e1 if dde2_jones is dde1_jones else tslice(dde2_jones, 1)
+    g1 = tslice(die1_jones, 0)
+    g2 = g1 if die2_jones is die1_jones else tslice(die2_jones, 0)
+    for (b0, b1), blk in stream_predict_vis_stokes(
+            lm, uvw[r0:r1], frequency, stokes, spi, ref_freq, time_index[r0:r1], antenna1[r0:r1],
+            antenna2[r0:r1], e1, e2, g1, None if base_vis is None else base_vis[r0:r1], g2, **kwargs):
+        yield (r0 + b0, r0 + b1), blk
