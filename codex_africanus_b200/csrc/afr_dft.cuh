@@ -52,7 +52,8 @@ int launch_antenna_uvw(const double *uvw, const int32_t *ant1, const int32_t *an
                        int64_t nsrc, const double *freq, int64_t nchan, double cst, double *ant_uvw,
                        int *ok, cudaStream_t stream);
 int launch_row_tile_order(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2,
-                          int64_t nrow, int64_t ntime, int32_t *perm, cudaStream_t stream);
+                          int64_t nrow, int64_t ntime, bool pair_order, int32_t *perm,
+                          cudaStream_t stream);
 int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact, bool ant_mode,
                         cudaStream_t stream);
 

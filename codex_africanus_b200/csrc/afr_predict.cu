@@ -741,8 +741,9 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
             if (ws_ok && ws_fits && hflags[0] == 0 && hflags[1] > 0 && nrow < (1LL << 31) && nant <= 1024) {
                 Scratch perm;
                 AFR_CUDA_OK(perm.alloc(sizeof(int32_t) * (size_t)nrow, stream));
+                // antenna mode with 2048-row tiles pairs baselines that share antenna 1
                 rc = launch_row_tile_order(time_index, antenna1, antenna2, nrow, ntime,
-                                           (int32_t *)perm.ptr, stream);
+                                           ant_mode && hflags[1] > 512, (int32_t *)perm.ptr, stream);
                 if (rc) return rc;
                 DdeWsParams wp{};
                 wp.perm = (const int32_t *)perm.ptr;

@@ -232,12 +232,16 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
     // (antenna1 / 4, antenna2 / 8) tiles, so the 32 lanes of a warp read <= 4 distinct A and
     // <= 8 distinct E matrices in distinct bank groups: every LDS.128 is one wavefront
     // instead of four (shared-memory bandwidth was the limit: l1tex 83 % busy before).
+    constexpr bool kPairs = ANT && RPT == 4;
     unsigned offs[RPT];  // shared-memory offsets of (antenna1 | antenna2 << 16)
     int rowid[RPT];
     double ru = 0.0, rv = 0.0, rw = 0.0;  // ROW mode (RPT == 1): uvw of this thread's row
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
-        const long long ri = rbeg + k * kConsThreads + tid;
+        // RPT == 4 (antenna mode): rows 2pp, 2pp+1 of a thread are CONSECUTIVE in perm, which the
+        // pair ordering of launch_row_tile_order makes two baselines of the same antenna 1
+        const long long ri = kPairs ? rbeg + 2 * ((k >> 1) * kConsThreads + tid) + (k & 1)
+                                    : rbeg + k * kConsThreads + tid;
         offs[k] = 0;
         rowid[k] = -1;
         if (ri < rend) {
@@ -280,6 +284,35 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
             }
         }
         mbar_wait(&bars[st], (unsigned)((s / kNS) & 1));
+        if constexpr (kPairs) {
+            // Two baselines sharing antenna 1: A_{a1} stays in registers (4 LDS.128 per pair), each
+            // E_{a2} streams through as two half-matrices (2 x 2 LDS.128): 12 instead of 16
+            // LDS.128 per two terms.  Shared memory delivers 128 B per clock per SM however many
+            // lanes share an address, and it -- not the FP64 pipe -- bounds this loop.
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const unsigned char *am = a_of(st) + (offs[2 * pp] & 0xFFFFu);
+                Cd x0 = lds_c(am), x1 = lds_c(am + 16), x2 = lds_c(am + 32), x3 = lds_c(am + 48);
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int k = 2 * pp + r;
+                    if (r == 1 && (offs[k] & 0xFFFFu) != (offs[k - 1] & 0xFFFFu)) {
+                        // a pair straddling two antenna-1 runs (at most one per run)
+                        const unsigned char *am1 = a_of(st) + (offs[k] & 0xFFFFu);
+                        x0 = lds_c(am1), x1 = lds_c(am1 + 16), x2 = lds_c(am1 + 32), x3 = lds_c(am1 + 48);
+                    }
+                    const unsigned char *e2 = e2_of(st) + (offs[k] >> 16);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {  // column c of A E^H needs row c of E
+                        const Cd q0 = lds_c(e2 + 32 * c), q1 = lds_c(e2 + 32 * c + 16);
+                        cfmac_(acc[k][0][c], x0, q0);
+                        cfmac_(acc[k][0][2 + c], x2, q0);
+                        cfmac_(acc[k][0][c], x1, q1);
+                        cfmac_(acc[k][0][2 + c], x3, q1);
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
             const unsigned char *e2 = e2_of(st) + (offs[k] >> 16);
@@ -326,6 +359,7 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
                     z = zn;
                 }
             }
+        }
         }
         __syncwarp();
         if (p.arrive_all || lane == 0) mbar_arrive(&bars[kNS + st]);
@@ -432,14 +466,25 @@ __global__ void __launch_bounds__(256) antenna_uvw_kernel(const double *uvw, con
     if (!good) atomicAnd(ok, 0);
 }
 
-// sort key of a row: time | antenna tile (a1/4, a2/8) | position inside the tile
+// sort key of a row: time | antenna tile (a1/4, a2/8) | position inside the tile.
+// pair_order (antenna mode, 2048-row tiles): time | a2/16 | a1/4 | a1 % 4 | a2 % 8 | (a2/8) % 2 --
+// tiles of 4 x 16 antennas = 64 rows = one warp of row PAIRS: consecutive rows are (a1, q) and
+// (a1, q + 8), so a thread's two consecutive rows share antenna 1 (except where a ragged tile
+// shifts the pairing across an antenna-1 boundary), and a warp still touches only ~4 distinct A and
+// ~8 + 8 distinct E matrices in distinct bank groups (shared-memory wavefronts go with the
+// distinct data a warp reads: a run-ordered pairing with 32 distinct E per load was measured
+// SLOWER than no pairing, 214 vs 228 Gterms/s, with 5x the bank conflicts).
 __global__ void row_keys_kernel(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2,
-                                long long nrow, unsigned long long *keys, int32_t *rows) {
+                                long long nrow, int pair_order, unsigned long long *keys, int32_t *rows) {
     const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (r >= nrow) return;
     const unsigned a1 = (unsigned)ant1[r] & 1023u, a2 = (unsigned)ant2[r] & 1023u;
-    keys[r] = ((unsigned long long)(unsigned)time_index[r] << 20) | ((a1 >> 2) << 12) | ((a2 >> 3) << 5) |
-              ((a1 & 3u) << 3) | (a2 & 7u);
+    const unsigned long long tkey = (unsigned long long)(unsigned)time_index[r] << 20;
+    if (pair_order)
+        keys[r] = tkey | ((a2 >> 4) << 14) | ((a1 >> 2) << 6) | ((a1 & 3u) << 4) | ((a2 & 7u) << 1) |
+                  ((a2 >> 3) & 1u);
+    else
+        keys[r] = tkey | ((a1 >> 2) << 12) | ((a2 >> 3) << 5) | ((a1 & 3u) << 3) | (a2 & 7u);
     rows[r] = (int32_t)r;
 }
 
@@ -447,14 +492,16 @@ __global__ void row_keys_kernel(const int32_t *time_index, const int32_t *ant1, 
 
 // perm (nrow): the rows ordered by (time, antenna tile); rows of one timestep stay contiguous
 int launch_row_tile_order(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2,
-                          int64_t nrow, int64_t ntime, int32_t *perm, cudaStream_t stream) {
+                          int64_t nrow, int64_t ntime, bool pair_order, int32_t *perm,
+                          cudaStream_t stream) {
     if (nrow <= 0) return 0;
     Scratch keys_in, keys_out, rows_in, tmp;
     AFR_CUDA_OK(keys_in.alloc(sizeof(unsigned long long) * (size_t)nrow, stream));
     AFR_CUDA_OK(keys_out.alloc(sizeof(unsigned long long) * (size_t)nrow, stream));
     AFR_CUDA_OK(rows_in.alloc(sizeof(int32_t) * (size_t)nrow, stream));
     row_keys_kernel<<<(unsigned)((nrow + 255) / 256), 256, 0, stream>>>(
-        time_index, ant1, ant2, nrow, (unsigned long long *)keys_in.ptr, (int32_t *)rows_in.ptr);
+        time_index, ant1, ant2, nrow, pair_order ? 1 : 0, (unsigned long long *)keys_in.ptr,
+        (int32_t *)rows_in.ptr);
     AFR_LAUNCH_OK();
     int tbits = 1;
     while ((1LL << tbits) < ntime && tbits < 43) ++tbits;
