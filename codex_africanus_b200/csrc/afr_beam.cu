@@ -103,6 +103,20 @@ __global__ void pa_sincos_kernel(const double *pa, long long n, double *sc) {
     sc[2 * i + 1] = cs;
 }
 
+// 16-byte (complex128) / 8-byte (complex64) vector accesses: one request per complex value and
+// per pair of |beam| values instead of one per scalar (ncu: 107 -> ~55 global-load requests per warp
+// and output element; the L1 wavefront pipe, 69 % busy, and lg-throttle stalls were the limit)
+template <typename T>
+struct Vec2;
+template <>
+struct Vec2<double> {
+    using type = double2;
+};
+template <>
+struct Vec2<float> {
+    using type = float2;
+};
+
 // ROT (NC == 4 only): the epilogue right-multiplies the interpolated 2x2 Jones by the feed
 // rotation L[t,a] -- einsum("stafij,tajk->stafik", beam_dde, feed_rot) of
 // africanus/rime/examples/predict.py:469-472 -- before the one store, so the rotated DDE costs
@@ -130,13 +144,13 @@ __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) 
 
         // fast_beam_cubes.py:130-151
         const double sl = __dmul_rn(l, fscale), sm = __dmul_rn(m, fscale);
-        const double *pe = p.perr + ((t * p.nant + a) * p.nchan + f) * 2;
-        const double tl = __dadd_rn(sl, pe[0]), tm = __dadd_rn(sm, pe[1]);
+        const double2 pe = *reinterpret_cast<const double2 *>(p.perr + ((t * p.nant + a) * p.nchan + f) * 2);
+        const double tl = __dadd_rn(sl, pe.x), tm = __dadd_rn(sm, pe.y);
         double vl = __dsub_rn(__dmul_rn(tl, cos_pa), __dmul_rn(tm, sin_pa));
         double vm = __dadd_rn(__dmul_rn(tl, sin_pa), __dmul_rn(tm, cos_pa));
-        const double *as = p.ascale + (a * p.nchan + f) * 2;
-        vl = __dmul_rn(vl, as[0]);
-        vm = __dmul_rn(vm, as[1]);
+        const double2 as = *reinterpret_cast<const double2 *>(p.ascale + (a * p.nchan + f) * 2);
+        vl = __dmul_rn(vl, as.x);
+        vm = __dmul_rn(vm, as.y);
         vl = __dmul_rn(p.lscale, __dsub_rn(vl, p.lower_l));
         vm = __dmul_rn(p.mscale, __dsub_rn(vm, p.lower_m));
         vl = fmax(0.0, fmin(vl, p.lmaxf));
@@ -160,11 +174,25 @@ __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) 
             const long long gc = k < 4 ? gc0 : gc1;
             const double wt = __dmul_rn(w4[k & 3], k < 4 ? nudw : inv_nud);
             const long long e = ((gls[k] * p.mh + gms[k]) * p.nud + gc) * p.ncorr + p.coff;
-            const T *b = beam + e * 2;
+            using V2 = typename Vec2<T>::type;
+            const V2 *b = reinterpret_cast<const V2 *>(beam + e * 2);
+            T abv[NC];
+            if (NC >= 2 && (p.ncorr & 1) == 0) {  // e is even: blocks of 4 / 2 start at even offsets
+#pragma unroll
+                for (int c = 0; c < NC; c += 2) {
+                    const V2 v = *reinterpret_cast<const V2 *>(babs + e + c);
+                    abv[c] = v.x;
+                    abv[(c + 1) % NC] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) abv[c] = babs[e + c];
+            }
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                const T br = b[2 * c], bi = b[2 * c + 1];
-                const T ab = babs[e + c];
+                const V2 bv = b[c];
+                const T br = bv.x, bi = bv.y;
+                const T ab = abv[c];
                 // accumulators live in the beam's precision, weights in float64 (:106-108)
                 asum[c] = (T)__dadd_rn((double)asum[c], __dmul_rn(wt, (double)ab));
                 csr[c] = (T)__dadd_rn((double)csr[c], __dmul_rn(wt, (double)br));
@@ -189,14 +217,18 @@ __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) 
                     const T l0r = L[2 * k], l0i = L[2 * k + 1], l1r = L[2 * (2 + k)], l1i = L[2 * (2 + k) + 1];
                     const T e0r = er[(2 * r) % NC], e0i = ei[(2 * r) % NC];
                     const T e1r = er[(2 * r + 1) % NC], e1i = ei[(2 * r + 1) % NC];
-                    o[2 * (2 * r + k)] = (e0r * l0r - e0i * l0i) + (e1r * l1r - e1i * l1i);
-                    o[2 * (2 * r + k) + 1] = (e0r * l0i + e0i * l0r) + (e1r * l1i + e1i * l1r);
+                    typename Vec2<T>::type w;
+                    w.x = (e0r * l0r - e0i * l0i) + (e1r * l1r - e1i * l1i);
+                    w.y = (e0r * l0i + e0i * l0r) + (e1r * l1i + e1i * l1r);
+                    reinterpret_cast<typename Vec2<T>::type *>(o)[2 * r + k] = w;
                 }
         } else {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                o[2 * c] = er[c];
-                o[2 * c + 1] = ei[c];
+                typename Vec2<T>::type w;
+                w.x = er[c];
+                w.y = ei[c];
+                reinterpret_cast<typename Vec2<T>::type *>(o)[c] = w;
             }
         }
     }
@@ -308,6 +340,13 @@ extern "C" int afr_beam_cube_dde_rot(const void *beam, const double *ext_host_or
     cudaStream_t stream = (cudaStream_t)stream_;
     AFR_REQUIRE(feed_rotation == nullptr || ncorr == 4,
                 "a feed rotation needs 2x2 correlations (beam of shape (lw,mh,nud,2,2))");
+    // the kernel reads / writes complex values and (l, m) pairs as one vector each
+    const uintptr_t cal = is_c64 ? 8 : 16;
+    AFR_REQUIRE(reinterpret_cast<uintptr_t>(beam) % cal == 0 && reinterpret_cast<uintptr_t>(out) % cal == 0 &&
+                    reinterpret_cast<uintptr_t>(point_errors) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(antenna_scaling) % 16 == 0,
+                "afr_beam_cube_dde: beam / out must be aligned to one complex value, point_errors / "
+                "antenna_scaling to 16 bytes");
     // fast_beam_cubes.py:74-75
     AFR_REQUIRE(lw >= 2 && mh >= 2 && nud >= 2, "beam_lw, beam_mh and beam_nud must be >= 2");
     AFR_REQUIRE(ncorr >= 1 && nsrc >= 0 && ntime >= 0 && nant >= 0 && nchan >= 0, "bad extent");

@@ -142,7 +142,8 @@ int afr_predict_fused(const double *lm, const double *uvw, const double *freq,
 /* ---- africanus.rime.beam_cube_dde (africanus/rime/fast_beam_cubes.py:57-240) */
 /* beam (lw,mh,nud,ncorr) complex; extents (2,2); beam_freq_map (nud,); lm (nsrc,2);
  * parallactic_angles (ntime,nant); point_errors (ntime,nant,nchan,2);
- * antenna_scaling (nant,nchan,2); freq (nchan,); out (nsrc,ntime,nant,nchan,ncorr). */
+ * antenna_scaling (nant,nchan,2); freq (nchan,); out (nsrc,ntime,nant,nchan,ncorr).
+ * beam / out aligned to one complex value, point_errors / antenna_scaling to 16 bytes. */
 int afr_beam_cube_dde(const void *beam, const double *beam_lm_extents,
                       const double *beam_freq_map, const double *lm,
                       const double *parallactic_angles, const double *point_errors,
