@@ -52,72 +52,25 @@ def _time_slice(a, axis, t0, t1):
     return a[tuple(idx)]
 
 
-def stream_predict_vis_stokes(lm, uvw, frequency, stokes, spi, ref_freq, time_index, antenna1,
-                              antenna2, dde1_jones=None, dde2_jones=None, die1_jones=None,
-                              base_vis=None, die2_jones=None, rows_per_block=None,
-                              block_bytes=1 << 30, nbuf=3, local_fn=None, **kwargs):
-    """Generator over whole-timestep row blocks: yields ``((row0, row1), vis_block)`` with
-    ``vis_block = fused_predict_vis_stokes(...)`` of those rows, in row order.
-
-    Arguments as ``fused_predict_vis_stokes`` (``kwargs``: convention, base, corr_schema, dtype,
-    source_chunk, ...).  ``rows_per_block`` defaults to what fits ``block_bytes`` of output.
-    With numpy inputs the blocks are numpy views of ``nbuf`` rotating page-locked buffers: a
-    yielded block stays valid until ``nbuf - 1`` further blocks have been requested (consume or
-    copy it before that); the device -> host copy of block i overlaps the computation of block
-    i + 1.  With CUDA-tensor inputs the blocks are fresh CUDA tensors.  ``local_fn`` replaces the
-    per-block predict (CPU tests substitute the oracle; the default is always the CUDA path).
-    """
-    if local_fn is None:
-        from .fused_stokes import fused_predict_vis_stokes as local_fn
-        cuda_path = True
-    else:
-        cuda_path = False
-    nrow = pl.shape_of(uvw)[0]
-    if pl.shape_of(time_index) != (nrow,):
-        raise ValueError("stream_predict_vis_stokes: uvw / time_index rows mismatch")
-    nchan = pl.shape_of(frequency)[0]
-    ncorr = int(np.asarray(kwargs.get("corr_schema", [[0, 0], [0, 0]]), dtype=object).size)
-    if rows_per_block is None:
-        rows_per_block = max(1, int(block_bytes) // max(1, nchan * ncorr * 16))
-    blocks = timestep_row_blocks(time_index, rows_per_block)
-    same_dde = dde1_jones is dde2_jones
-    same_die = die1_jones is die2_jones
-
-    small = (lm, frequency, stokes, spi, ref_freq)
-    every = small + (uvw, time_index, antenna1, antenna2, dde1_jones, dde2_jones, die1_jones,
-                     base_vis, die2_jones)
-    to_host = cuda_path and not pl.wants_torch(*every)
-    if cuda_path:  # per-source inputs go to the device once, not once per block
-        device = pl.pick_device(*every)
-        with torch.cuda.device(device):
-            small = tuple(pl.to_device(a, np.float64, device) for a in small)
-    d_lm, d_f, d_st, d_spi, d_rf = small
-
-    def predict(r0, r1, t0, t1):
-        e1 = _time_slice(dde1_jones, 1, t0, t1)
-        e2 = e1 if same_dde else _time_slice(dde2_jones, 1, t0, t1)
-        g1 = _time_slice(die1_jones, 0, t0, t1)
-        g2 = g1 if same_die else _time_slice(die2_jones, 0, t0, t1)
-        return local_fn(d_lm, uvw[r0:r1], d_f, d_st, d_spi, d_rf, time_index[r0:r1], antenna1[r0:r1],
-                        antenna2[r0:r1], e1, e2, g1, None if base_vis is None else base_vis[r0:r1],
-                        g2, **kwargs)
-
+def _run_blocks(predict, blocks, to_host, device, nbuf):
+    """Drive ``predict(r0, r1, t0, t1)`` over the row blocks.  ``to_host``: copy each CUDA block to
+    one of ``nbuf`` rotating page-locked buffers on a copy stream while the next block computes and
+    yield numpy views; otherwise yield what ``predict`` returns."""
     if not to_host:
         for r0, r1, t0, t1 in blocks:
             yield (r0, r1), predict(r0, r1, t0, t1)
         return
-
     nbuf = max(2, int(nbuf))
     with torch.cuda.device(device):
         compute = torch.cuda.current_stream(device)
         copier = pl.side_stream(device)
         bufs = [None] * nbuf
         pending = None  # ((r0, r1), host view, copy-done event)
+        most = max(b1 - b0 for b0, b1, _, _ in blocks) if blocks else 0
         for i, (r0, r1, t0, t1) in enumerate(blocks):
-            vis = predict(r0, r1, t0, t1)  # CUDA tensor: the small inputs are CUDA tensors
+            vis = predict(r0, r1, t0, t1)  # CUDA tensor: the per-source inputs are CUDA tensors
             k = i % nbuf
             if bufs[k] is None or bufs[k].numel() < vis.numel() or bufs[k].dtype != vis.dtype:
-                most = max(b1 - b0 for b0, b1, _, _ in blocks)
                 bufs[k] = pl.empty_pinned((most * int(np.prod(vis.shape[1:])),), pl.dtype_of(vis))
             host = bufs[k][: vis.numel()].view(vis.shape)
             ready = torch.cuda.Event()
@@ -135,3 +88,89 @@ def stream_predict_vis_stokes(lm, uvw, frequency, stokes, spi, ref_freq, time_in
         if pending is not None:
             pending[2].synchronize()
             yield pending[0], pending[1].numpy()
+
+
+def _stream(local_fn, cuda_path, per_source, f64_mask, uvw, time_index, antenna1, antenna2, dde1_jones,
+            dde2_jones, die1_jones, base_vis, die2_jones, rows_per_block, block_bytes, ncorr, nchan,
+            nbuf, kwargs):
+    """Shared body of the streaming generators: ``per_source`` are the arrays indexed by source /
+    channel only (uploaded once on the CUDA path; ``f64_mask`` says which are real float64)."""
+    nrow = pl.shape_of(uvw)[0]
+    if pl.shape_of(time_index) != (nrow,):
+        raise ValueError("stream predict: uvw / time_index rows mismatch")
+    if rows_per_block is None:
+        rows_per_block = max(1, int(block_bytes) // max(1, nchan * ncorr * 16))
+    blocks = timestep_row_blocks(time_index, rows_per_block)
+    same_dde = dde1_jones is dde2_jones
+    same_die = die1_jones is die2_jones
+    every = tuple(per_source) + (uvw, time_index, antenna1, antenna2, dde1_jones, dde2_jones,
+                                 die1_jones, base_vis, die2_jones)
+    to_host = cuda_path and not pl.wants_torch(*every)
+    device = None
+    if cuda_path:  # per-source inputs go to the device once, not once per block
+        device = pl.pick_device(*every)
+        with torch.cuda.device(device):
+            per_source = tuple(pl.to_device(a, np.float64 if is_f64 else pl.dtype_of(a), device)
+                               for a, is_f64 in zip(per_source, f64_mask))
+
+    def predict(r0, r1, t0, t1):
+        e1 = _time_slice(dde1_jones, 1, t0, t1)
+        e2 = e1 if same_dde else _time_slice(dde2_jones, 1, t0, t1)
+        g1 = _time_slice(die1_jones, 0, t0, t1)
+        g2 = g1 if same_die else _time_slice(die2_jones, 0, t0, t1)
+        return local_fn(per_source, uvw[r0:r1], time_index[r0:r1], antenna1[r0:r1], antenna2[r0:r1],
+                        e1, e2, g1, None if base_vis is None else base_vis[r0:r1], g2, kwargs)
+
+    return _run_blocks(predict, blocks, to_host, device, nbuf)
+
+
+def stream_predict_vis_stokes(lm, uvw, frequency, stokes, spi, ref_freq, time_index, antenna1,
+                              antenna2, dde1_jones=None, dde2_jones=None, die1_jones=None,
+                              base_vis=None, die2_jones=None, rows_per_block=None,
+                              block_bytes=1 << 30, nbuf=3, local_fn=None, **kwargs):
+    """Generator over whole-timestep row blocks: yields ``((row0, row1), vis_block)`` with
+    ``vis_block = fused_predict_vis_stokes(...)`` of those rows, in row order.
+
+    Arguments as ``fused_predict_vis_stokes`` (``kwargs``: convention, base, corr_schema, dtype,
+    source_chunk, ...).  ``rows_per_block`` defaults to what fits ``block_bytes`` of output.
+    With numpy inputs the blocks are numpy views of ``nbuf`` rotating page-locked buffers: a
+    yielded block stays valid until ``nbuf - 1`` further blocks have been requested (consume or
+    copy it before that); the device -> host copy of block i overlaps the computation of block
+    i + 1.  With CUDA-tensor inputs the blocks are fresh CUDA tensors.  ``local_fn`` replaces the
+    per-block predict (CPU tests substitute the oracle; the default is always the CUDA path).
+    """
+    cuda_path = local_fn is None
+    if cuda_path:
+        from .fused_stokes import fused_predict_vis_stokes as local_fn
+    fn = local_fn
+
+    def block_fn(ps, uvw_b, ti_b, a1_b, a2_b, e1, e2, g1, bv, g2, kw):
+        d_lm, d_f, d_st, d_spi, d_rf = ps
+        return fn(d_lm, uvw_b, d_f, d_st, d_spi, d_rf, ti_b, a1_b, a2_b, e1, e2, g1, bv, g2, **kw)
+
+    ncorr = int(np.asarray(kwargs.get("corr_schema", [[0, 0], [0, 0]]), dtype=object).size)
+    return _stream(block_fn, cuda_path, (lm, frequency, stokes, spi, ref_freq), (True,) * 5, uvw, time_index,
+                   antenna1, antenna2, dde1_jones, dde2_jones, die1_jones, base_vis, die2_jones,
+                   rows_per_block, block_bytes, ncorr, pl.shape_of(frequency)[0], nbuf, kwargs)
+
+
+def stream_fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
+                             dde1_jones=None, dde2_jones=None, die1_jones=None, base_vis=None,
+                             die2_jones=None, convention="fourier", rows_per_block=None,
+                             block_bytes=1 << 30, nbuf=3, local_fn=None):
+    """The same streaming loop for ``fused_predict_vis`` (brightness given as a
+    (source, chan, corr...) array, uploaded once): yields ``((row0, row1), vis_block)``."""
+    cuda_path = local_fn is None
+    if cuda_path:
+        from .fused import fused_predict_vis as local_fn
+    fn = local_fn
+
+    def block_fn(ps, uvw_b, ti_b, a1_b, a2_b, e1, e2, g1, bv, g2, kw):
+        d_lm, d_f, d_b = ps
+        return fn(d_lm, uvw_b, d_f, d_b, ti_b, a1_b, a2_b, e1, e2, g1, bv, g2, **kw)
+
+    ncorr = int(np.prod(pl.shape_of(brightness)[2:], dtype=np.int64))
+    return _stream(block_fn, cuda_path, (lm, frequency, brightness), (True, True, False), uvw, time_index,
+                   antenna1, antenna2, dde1_jones, dde2_jones, die1_jones, base_vis, die2_jones,
+                   rows_per_block, block_bytes, ncorr, pl.shape_of(frequency)[0], nbuf,
+                   {"convention": convention})

@@ -64,3 +64,25 @@ def test_stream_predict_blocks_equal_whole(oracle, golden):
         local_fn=local_fn)])
     assert calls == [(2 * nbl, 2), (nbl, 1)]
     assert np.array_equal(got, ref)
+
+
+def test_stream_fused_predict_blocks_equal_whole(oracle, golden):
+    """The plain-brightness variant: blocks concatenate to the one-shot fused predict."""
+    from codex_africanus_b200.rime.stream import stream_fused_predict_vis
+
+    g = golden("brightness")
+    fr, lm, uvw, ti, a1, a2 = g["freq"], g["p_lm"], g["p_uvw"], g["p_time_index"], g["p_ant1"], g["p_ant2"]
+    die, bvis, bright = g["p_die"], g["p_base_vis"], g["b_circular"]
+    ntime = die.shape[0]
+    nbl = uvw.shape[0] // ntime
+    rows = []
+    parts = []
+    for (r0, r1), blk in stream_fused_predict_vis(lm, uvw, fr, bright, ti, a1, a2, None, None, die, bvis, die,
+                                                  convention="fourier", rows_per_block=nbl + 1,
+                                                  local_fn=oracle.fused_predict):
+        rows.append((r0, r1))
+        parts.append(blk)
+    assert rows == [(k * nbl, (k + 1) * nbl) for k in range(ntime)]
+    assert np.array_equal(np.concatenate(parts), g["p_circular"])
+    with pytest.raises(ValueError):
+        stream_fused_predict_vis(lm, uvw, fr, bright, ti[:-1], a1, a2, local_fn=oracle.fused_predict)

@@ -49,3 +49,18 @@ def test_stream_predict_vis_stokes(golden, oracle):
     assert [rng_ for rng_, _ in blocks] == [(0, 2 * nbl), (2 * nbl, 3 * nbl)]
     assert all(isinstance(blk, torch.Tensor) and blk.is_cuda for _, blk in blocks)
     assert_c128_close(torch.cat([blk for _, blk in blocks]).cpu().numpy(), ref)
+
+
+def test_stream_fused_predict_vis(golden):
+    """Plain-brightness streaming: numpy blocks through the page-locked buffers."""
+    from codex_africanus_b200.rime.stream import stream_fused_predict_vis
+
+    g = golden("brightness")
+    fr, lm, uvw, ti, a1, a2 = g["freq"], g["p_lm"], g["p_uvw"], g["p_time_index"], g["p_ant1"], g["p_ant2"]
+    die, bvis = g["p_die"], g["p_base_vis"]
+    nbl = uvw.shape[0] // die.shape[0]
+    for feed in ("linear", "circular"):
+        parts = [blk.copy() for _, blk in stream_fused_predict_vis(
+            lm, uvw, fr, g["b_" + feed], ti, a1, a2, None, None, die, bvis, die, rows_per_block=nbl)]
+        assert len(parts) == die.shape[0]
+        assert_c128_close(np.concatenate(parts), g["p_" + feed])
