@@ -44,4 +44,37 @@ for ncorr in (1, 2, 4):
     v = rc((nrow, 48, ncorr))
     dft.vis_to_im(v, uvw, lm, freq48, rng.random(v.shape) < 0.1)
     dft.vis_to_im(v, uvw, lm, freq48, np.zeros(v.shape, bool))
+# antenna mode with > 512 rows per timestep: 2048-row x 1-channel tiles, row PAIRS sharing antenna 1
+# (ragged 4 x 16 antenna tiles, straddling pairs, a partial last tile)
+na_w, nt_w, nc_w, ns_w = 37, 2, 3, 4
+b1, b2 = np.triu_indices(na_w, 1)
+w1, w2 = np.tile(b1, nt_w), np.tile(b2, nt_w)
+tw = np.repeat(np.arange(nt_w), b1.size)
+pos_w = rng.standard_normal((nt_w, na_w, 3)) * 1500.0
+uvw_w = pos_w[tw, w1] - pos_w[tw, w2]
+fw = np.linspace(0.856e9, 1.712e9, nc_w)
+dde_w = rc((ns_w, nt_w, na_w, nc_w, 2, 2))
+rime.fused_predict_vis(lm[:ns_w], uvw_w, fw, rc((ns_w, nc_w, 2, 2)), tw, w1, w2, dde_w, dde_w)
+# brightness from Stokes parameters, convert, feed rotation in the beam epilogue, streaming driver
+from codex_africanus_b200 import model
+stokes = rng.standard_normal((nsrc, 4)); spi = rng.standard_normal((nsrc, 2, 4)) * 0.3; rf = np.full(nsrc, 1.2e9)
+for base in ("std", "log", ["log10", "std"]):
+    model.spectral_model(stokes, spi, rf, freq, base=base)
+    model.stokes_brightness(stokes, spi, rf, freq, base=base)
+model.spectral_model(stokes[:, 0], spi[:, :, 0], rf, freq)
+model.convert(model.convert(stokes, ["I", "Q", "U", "V"], [["RR", "RL"], ["LR", "LL"]]),
+              [["RR", "RL"], ["LR", "LL"]], ["I", "V"])
+model.convert(stokes[:, :1], ["I"], ["XX", "XY", "YX", "YY"], implicit_stokes=True)
+pa = rng.uniform(-1, 1, (ntime, na))
+for ft in ("linear", "circular"):
+    rime.beam_cube_dde_rotated(beam, np.array([[-0.03, 0.03], [-0.03, 0.03]]), np.linspace(0.8e9, 1.8e9, 5), lm,
+                               pa, np.zeros((ntime, na, nchan, 2)), np.ones((na, nchan, 2)), freq,
+                               rime.feed_rotation(pa, ft))
+rime.beam_cube_dde(beam[..., 0, :], np.array([[-0.03, 0.03], [-0.03, 0.03]]), np.linspace(0.8e9, 1.8e9, 5), lm,
+                   pa, np.zeros((ntime, na, nchan, 2)), np.ones((na, nchan, 2)), freq)
+rime.fused_predict_vis_stokes(lm, uvw_a, freq, stokes, spi, rf, ti, ant1, ant2, dde, dde, die, None, die,
+                              source_chunk=7)
+for _, blk in rime.stream_predict_vis_stokes(lm, uvw_a, freq, stokes, spi, rf, ti, ant1, ant2, None, None, die,
+                                             None, die, rows_per_block=a1.size):
+    blk.sum()
 print("sanitize target done")
