@@ -92,9 +92,10 @@ def _run_blocks(predict, blocks, to_host, device, nbuf):
 
 def _stream(local_fn, cuda_path, per_source, f64_mask, uvw, time_index, antenna1, antenna2, dde1_jones,
             dde2_jones, die1_jones, base_vis, die2_jones, rows_per_block, block_bytes, ncorr, nchan,
-            nbuf, kwargs):
+            nbuf, kwargs, e_axis=1):
     """Shared body of the streaming generators: ``per_source`` are the arrays indexed by source /
-    channel only (uploaded once on the CUDA path; ``f64_mask`` says which are real float64)."""
+    channel only (uploaded once on the CUDA path; ``f64_mask`` says which are real float64).  The
+    two ``dde`` slots are sliced along ``e_axis`` to the block's timesteps, the DIEs along axis 0."""
     nrow = pl.shape_of(uvw)[0]
     if pl.shape_of(time_index) != (nrow,):
         raise ValueError("stream predict: uvw / time_index rows mismatch")
@@ -114,8 +115,8 @@ def _stream(local_fn, cuda_path, per_source, f64_mask, uvw, time_index, antenna1
                                for a, is_f64 in zip(per_source, f64_mask))
 
     def predict(r0, r1, t0, t1):
-        e1 = _time_slice(dde1_jones, 1, t0, t1)
-        e2 = e1 if same_dde else _time_slice(dde2_jones, 1, t0, t1)
+        e1 = _time_slice(dde1_jones, e_axis, t0, t1)
+        e2 = e1 if same_dde else _time_slice(dde2_jones, e_axis, t0, t1)
         g1 = _time_slice(die1_jones, 0, t0, t1)
         g2 = g1 if same_die else _time_slice(die2_jones, 0, t0, t1)
         return local_fn(per_source, uvw[r0:r1], time_index[r0:r1], antenna1[r0:r1], antenna2[r0:r1],
@@ -174,3 +175,32 @@ def stream_fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna
                    antenna1, antenna2, dde1_jones, dde2_jones, die1_jones, base_vis, die2_jones,
                    rows_per_block, block_bytes, ncorr, pl.shape_of(frequency)[0], nbuf,
                    {"convention": convention})
+
+
+def stream_fused_predict_vis_beam(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
+                                  beam, beam_lm_extents, beam_freq_map, parallactic_angles,
+                                  point_errors, antenna_scaling, die1_jones=None, base_vis=None,
+                                  die2_jones=None, rows_per_block=None, block_bytes=1 << 30, nbuf=3,
+                                  local_fn=None, **kwargs):
+    """The streaming loop for ``fused_predict_vis_beam`` (DDEs interpolated from the beam cube per
+    source chunk): the (time, ant, ...) inputs of the beam -- parallactic angles and pointing
+    errors -- and the DIEs are sliced to each block's timesteps; beam, brightness and the other
+    per-source / per-antenna inputs go to the device once.  ``kwargs``: convention, source_chunk,
+    feed_type.  Yields ``((row0, row1), vis_block)``."""
+    cuda_path = local_fn is None
+    if cuda_path:
+        from .fused_beam import fused_predict_vis_beam as local_fn
+    fn = local_fn
+    pa, pe = parallactic_angles, point_errors
+
+    def block_fn(ps, uvw_b, ti_b, a1_b, a2_b, pa_b, pe_b, g1, bv, g2, kw):
+        d_lm, d_f, d_b, d_beam, d_ext, d_bfm, d_as = ps
+        return fn(d_lm, uvw_b, d_f, d_b, ti_b, a1_b, a2_b, d_beam, d_ext, d_bfm, pa_b, pe_b, d_as, g1, bv, g2,
+                  **kw)
+
+    ncorr = int(np.prod(pl.shape_of(brightness)[2:], dtype=np.int64))
+    return _stream(block_fn, cuda_path,
+                   (lm, frequency, brightness, beam, beam_lm_extents, beam_freq_map, antenna_scaling),
+                   (True, True, False, False, True, True, True), uvw, time_index, antenna1, antenna2,
+                   pa, pe, die1_jones, base_vis, die2_jones, rows_per_block, block_bytes, ncorr,
+                   pl.shape_of(frequency)[0], nbuf, kwargs, e_axis=0)

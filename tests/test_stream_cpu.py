@@ -86,3 +86,29 @@ def test_stream_fused_predict_blocks_equal_whole(oracle, golden):
     assert np.array_equal(np.concatenate(parts), g["p_circular"])
     with pytest.raises(ValueError):
         stream_fused_predict_vis(lm, uvw, fr, bright, ti[:-1], a1, a2, local_fn=oracle.fused_predict)
+
+
+def test_stream_beam_predict_blocks_equal_whole(oracle, golden):
+    """Beam-interpolated variant: parallactic angles / pointing errors / DIEs sliced per block; the
+    blocks concatenate to the reference composition with the rotated DDE (golden)."""
+    from codex_africanus_b200.rime.stream import stream_fused_predict_vis_beam
+
+    g = golden("feeds")
+    seen = []
+
+    def local_fn(lm, uvw, fr, b, ti, a1, a2, beam, ext, bfm, pa, pe, asc, g1, bv, g2, feed_type=None):
+        seen.append((uvw.shape[0], pa.shape[0], pe.shape[0], g1.shape[0]))
+        dde = oracle.beam_cube_dde(beam, ext, bfm, lm, pa, pe, asc, fr)
+        dde = np.einsum("stafij,tajk->stafik", dde, oracle.feed_rotation(pa, feed_type))
+        return oracle.fused_predict(lm, uvw, fr, b, ti, a1, a2, dde, dde, g1, bv, g2)
+
+    ntime = g["pa"].shape[0]
+    nbl = g["uvw"].shape[0] // ntime
+    for ft in ("linear", "circular"):
+        seen.clear()
+        parts = [blk for _, blk in stream_fused_predict_vis_beam(
+            g["lm"], g["uvw"], g["freq"], g["bright"], g["time_index"], g["ant1"], g["ant2"], g["beam"],
+            g["ext"], g["bfm"], g["pa"], g["pe"], g["asc"], g["die"], None, g["die"], rows_per_block=nbl,
+            local_fn=local_fn, feed_type=ft)]
+        assert seen == [(nbl, 1, 1, 1)] * ntime
+        assert np.array_equal(np.concatenate(parts), g["vis_" + ft])

@@ -64,3 +64,18 @@ def test_stream_fused_predict_vis(golden):
             lm, uvw, fr, g["b_" + feed], ti, a1, a2, None, None, die, bvis, die, rows_per_block=nbl)]
         assert len(parts) == die.shape[0]
         assert_c128_close(np.concatenate(parts), g["p_" + feed])
+
+
+def test_stream_fused_predict_vis_beam(golden):
+    """Beam-interpolated streaming against the reference outputs (rotated DDE through the predict)."""
+    from codex_africanus_b200.rime.stream import stream_fused_predict_vis_beam
+
+    g = golden("feeds")
+    ntime = g["pa"].shape[0]
+    nbl = g["uvw"].shape[0] // ntime
+    for ft, rpb in (("linear", nbl), ("circular", 2 * nbl)):
+        parts = [blk.copy() for _, blk in stream_fused_predict_vis_beam(
+            g["lm"], g["uvw"], g["freq"], g["bright"], g["time_index"], g["ant1"], g["ant2"], g["beam"],
+            g["ext"], g["bfm"], g["pa"], g["pe"], g["asc"], g["die"], None, g["die"], rows_per_block=rpb,
+            feed_type=ft, source_chunk=4)]
+        assert_c128_close(np.concatenate(parts), g["vis_" + ft])
