@@ -884,3 +884,26 @@ def test_feed_rotation_and_rotated_beam_predict(b200, golden):
         b200.rime.feed_rotation(g["pa"].astype(np.int32))
     with pytest.raises(ValueError):
         b200.rime.beam_cube_dde_rotated(g["beam"][..., 0], *beam_args[1:], g["rot_linear"])
+
+
+@pytest.mark.parametrize("base", [0, 2, "log", ["log", "std", "std", "std"]])
+@pytest.mark.parametrize("npol", [0, 1, 2, 4])
+def test_spectral_model_multiple_spi(b200, oracle, base, npol):
+    """The reference's own parametrisation (model/spectral/tests/test_spectral_model.py:41-76):
+    6 spectral indices, 0/1/2/4 polarisations, broadcast (strided) stokes -- CUDA vs oracle."""
+    rng = np.random.default_rng(7)
+    nsrc, nchan, nspi = 10, 16, 6
+    if isinstance(base, list):
+        base = base[0] if npol == 0 else base[:npol]
+    flux = rng.normal(size=nsrc)
+    if npol > 0:
+        stokes = np.broadcast_to(flux[:, None], (nsrc, npol))
+        spi = 0.7 + rng.random((nsrc, nspi, npol)) * 0.2
+    else:
+        stokes = flux
+        spi = 0.7 + rng.random((nsrc, nspi)) * 0.2
+    ref_freq = np.full(nsrc, 3 * 0.856e9 / 2)
+    freq = np.linspace(0.856e9, 2 * 0.856e9, nchan)
+    got = b200.model.spectral_model(stokes, spi, ref_freq, freq, base=base)
+    assert got.flags.c_contiguous
+    assert_c128_close(got, oracle.spectral_model(stokes, spi, ref_freq, freq, base=base))
