@@ -388,6 +388,52 @@ def gen_feeds():
     save("feeds", **out)
 
 
+def gen_corrupt_vis():
+    """The reference's INDEPENDENT implementation of the DDE chain,
+    africanus.calibration.utils.corrupt_vis (calibration/utils/corrupt_vis.py:58-103), on the inputs
+    of its own cross-check against predict_vis (calibration/utils/tests/test_utils.py:21-80,
+    conftest.py:30-115): int16 antenna columns with antenna1 > antenna2, (time, ant, chan, dir, corr)
+    Jones and (row, chan, dir, corr) model layouts that the test transposes into predict_vis order."""
+    from africanus.averaging.support import unique_time
+    from africanus.calibration.utils import corrupt_vis
+
+    out = {}
+    rs = np.random.RandomState(42)
+    n_dir, n_time, n_chan, n_ant = 3, 8, 6, 7
+    n_bl = n_ant * (n_ant - 1) // 2
+    n_row = n_bl * n_time
+    antenna1 = np.zeros(n_row, dtype=np.int16)
+    antenna2 = np.zeros(n_row, dtype=np.int16)
+    time = np.zeros(n_row, dtype=np.float64)
+    time_values = np.linspace(0, 1, n_time)
+    for i in range(n_time):
+        row = 0
+        for p in range(n_ant):
+            for q in range(p):
+                time[i * n_bl + row] = time_values[i]
+                antenna1[i * n_bl + row] = p
+                antenna2[i * n_bl + row] = q
+                row += 1
+    uvw = rs.randn(n_row, 3)
+    freq = np.linspace(1e9, 2e9, n_chan)
+    lm = 0.1 * rs.randn(n_dir, 2)
+    _, time_bin_indices, _, time_bin_counts = unique_time(time)
+    out.update(antenna1=antenna1, antenna2=antenna2, time=time, uvw=uvw, freq=freq, lm=lm)
+    for tag, corr_shape, jones_shape in (("c1", (1,), (1,)), ("c2", (2,), (2,)), ("d22", (2, 2), (2,)),
+                                         ("f22", (2, 2), (2, 2))):
+        flux = np.abs(rs.normal(size=(n_dir, 1) + corr_shape)) * (freq / freq[n_chan // 2])[None, :, None].reshape(
+            (1, n_chan) + (1,) * len(corr_shape)) ** -0.7
+        model = np.zeros((n_row, n_chan, n_dir) + corr_shape, dtype=np.complex128)
+        for d in range(n_dir):
+            tmp = im_to_vis(flux[d].reshape(1, n_chan, -1), uvw, lm[d].reshape(1, 2), freq)
+            model[:, :, d] = tmp.reshape((n_row, n_chan) + corr_shape)
+        jones = np.ones((n_time, n_ant, n_chan, n_dir) + jones_shape, dtype=np.complex128)
+        jones += rs.normal(0.0, 0.05, jones.shape) + 1.0j * rs.normal(0.0, 0.05, jones.shape)
+        vis = corrupt_vis(time_bin_indices.copy(), time_bin_counts, antenna1, antenna2, jones, model)
+        out.update({tag + "_model": model, tag + "_jones": jones, tag + "_vis": vis})
+    save("corrupt_vis", **out)
+
+
 if __name__ == "__main__":
     gen_phase()
     gen_dft()
@@ -397,3 +443,4 @@ if __name__ == "__main__":
     gen_wsclean()
     gen_brightness()
     gen_feeds()
+    gen_corrupt_vis()

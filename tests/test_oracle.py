@@ -559,3 +559,30 @@ def test_conversion_schemas(oracle, input_schema, output_schema, vis_shape):
     ref = ref.reshape(vis_shape + out_shape)
     assert got.dtype == coh._output_dtype(vis.dtype, list(op))
     np.testing.assert_array_equal(got, ref if np.iscomplexobj(got) else ref.real)
+
+
+def _corrupt_vis_case(g, tag):
+    """Inputs of calibration/utils/tests/test_utils.py:21-80 in predict_vis order."""
+    model, jones = g[tag + "_model"], g[tag + "_jones"]
+    if tag == "d22":  # DIAG Jones against 2x2 model: broadcast onto the diagonal (:47-53)
+        tmp = np.zeros(jones.shape[:4] + (2, 2), np.complex128)
+        tmp[..., 0, 0] = jones[..., 0]
+        tmp[..., 1, 1] = jones[..., 1]
+        jones = tmp
+    if model.ndim == 5:
+        jones, model = np.transpose(jones, [3, 0, 1, 2, 4, 5]), np.transpose(model, [2, 0, 1, 3, 4])
+    else:
+        jones, model = np.transpose(jones, [3, 0, 1, 2, 4]), np.transpose(model, [2, 0, 1, 3])
+    time_index = np.unique(g["time"], return_inverse=True)[1]
+    return time_index, g["antenna1"], g["antenna2"], jones, model
+
+
+@pytest.mark.parametrize("tag", ["c1", "c2", "d22", "f22"])
+def test_predict_vis_equals_reference_corrupt_vis(golden, oracle, tag):
+    """predict_vis against the reference's independent corrupt_vis (calibration/utils/
+    corrupt_vis.py:58-103) on its own cross-check inputs -- int16 antenna columns, antenna1 >
+    antenna2, transposed (non-contiguous) Jones and model views -- at the reference's decimal 10."""
+    g = golden("corrupt_vis")
+    ti, a1, a2, jones, model = _corrupt_vis_case(g, tag)
+    got = oracle.predict_vis(ti, a1, a2, dde1_jones=jones, source_coh=model, dde2_jones=jones)
+    assert_array_almost_equal(got, g[tag + "_vis"], decimal=10)
