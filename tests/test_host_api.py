@@ -168,3 +168,25 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, fn
                 assert "afr_oracle" not in txt, fn
+
+
+def test_bench_reference_arm_emits_one_json_line():
+    """bench.py contract: exactly ONE JSON line on stdout (library banners go to stderr), with the
+    keys the driver reads; the reference arm runs on the CPU, so this is checkable without a GPU."""
+    import json
+    import subprocess
+    import sys
+
+    env = dict(os.environ, BENCH_REF_SECONDS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, cwd=ROOT, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:300]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "Gterms/s" and line["higher_is_better"] is True
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data",
+                "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
