@@ -933,6 +933,38 @@ __global__ void lm_to_lmn_kernel(const double *lm, long long nsrc, int mode, int
     lmn[3 * s + 2] = n;
 }
 
+// im_to_vis skips pixels that are exactly zero (dft/kernels.py:64), so a source outside the unit
+// disc (n = NaN, kernels.py:54 has no clamp) contributes NaN to exactly the (chan, corr) entries
+// where its pixel is non-zero and nothing elsewhere -- a zero-padded image grid reaching past
+// l^2 + m^2 = 1 is the usual case, and stays finite -- while NaN * 0 would poison every visibility
+// here.  Such sources get the coordinates (0, 0, 0) (a finite phasor: their zero pixels add zero)
+// and their non-zero pixels are marked in poison[1 + f * ncorr + c] (poison[0] = any), which
+// poison_apply_kernel turns into NaN for every row afterwards -- what the reference computes.
+// Only threads whose n is not finite read their image row.
+template <typename T>
+__global__ void mute_nan_sources_kernel(double *lmn, const T *image, long long nsrc, long long nfc,
+                                        int image_complex, uint8_t *poison) {
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s >= nsrc) return;
+    const double q = lmn[3 * s] + lmn[3 * s + 1] + lmn[3 * s + 2];
+    if (q - q == 0.0) return;  // finite
+    const T *row = image + s * nfc * (image_complex ? 2 : 1);
+    for (long long i = 0; i < nfc; ++i) {
+        const bool lit = image_complex ? (row[2 * i] != T(0) || row[2 * i + 1] != T(0)) : row[i] != T(0);
+        if (lit) poison[1 + i] = 1, poison[0] = 1;
+    }
+    lmn[3 * s] = lmn[3 * s + 1] = lmn[3 * s + 2] = 0.0;
+}
+
+template <typename T>
+__global__ void poison_apply_kernel(T *out, const uint8_t *poison, long long nrow, long long nfc) {
+    if (!poison[0]) return;
+    const T nan = T(NAN);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nrow * nfc;
+         i += (long long)gridDim.x * blockDim.x)
+        if (poison[1 + i % nfc]) out[2 * i] = nan, out[2 * i + 1] = nan;
+}
+
 int ilog2(long long v) {
     int r = 0;
     while ((1LL << (r + 1)) <= v) ++r;
@@ -1225,10 +1257,36 @@ extern "C" int afr_im_to_vis(const void *image, int image_complex, const double 
     int rc = launch_lm_to_lmn(lm, nsrc, kLmnDft, (f32_flags & AFR_F32_LM) != 0,
                               (double *)lmn.ptr, stream);
     if (rc) return rc;
+    const long long nfc = nchan * ncorr;
+    Scratch poison;
+    if (nsrc > 0 && nfc > 0) {
+        AFR_CUDA_OK(poison.alloc((size_t)nfc + 1, stream));
+        AFR_CUDA_OK(cudaMemsetAsync(poison.ptr, 0, (size_t)nfc + 1, stream));
+        const unsigned blocks = (unsigned)((nsrc + 255) / 256);
+        if (out_c64)
+            mute_nan_sources_kernel<float><<<blocks, 256, 0, stream>>>(
+                (double *)lmn.ptr, (const float *)image, nsrc, nfc, image_complex, (uint8_t *)poison.ptr);
+        else
+            mute_nan_sources_kernel<double><<<blocks, 256, 0, stream>>>(
+                (double *)lmn.ptr, (const double *)image, nsrc, nfc, image_complex, (uint8_t *)poison.ptr);
+        AFR_LAUNCH_OK();
+    }
     const bool f32dot = (f32_flags & AFR_F32_LM) && (f32_flags & AFR_F32_UVW);
-    return run_phasor_stream(uvw, nrow, (const double *)lmn.ptr, nsrc, image, image_complex != 0,
-                             nullptr, freq, nchan, ncorr, cst, f32dot, /*adjoint=*/false,
-                             chan_mode == AFR_CHAN_EXACT, out_c64 != 0, out, stream);
+    rc = run_phasor_stream(uvw, nrow, (const double *)lmn.ptr, nsrc, image, image_complex != 0,
+                           nullptr, freq, nchan, ncorr, cst, f32dot, /*adjoint=*/false,
+                           chan_mode == AFR_CHAN_EXACT, out_c64 != 0, out, stream);
+    if (rc) return rc;
+    if (nsrc > 0 && nfc > 0 && nrow > 0) {
+        const unsigned blocks = (unsigned)std::min<long long>((nrow * nfc + 255) / 256, 4LL * sm_count());
+        if (out_c64)
+            poison_apply_kernel<float><<<blocks, 256, 0, stream>>>((float *)out, (const uint8_t *)poison.ptr,
+                                                                   nrow, nfc);
+        else
+            poison_apply_kernel<double><<<blocks, 256, 0, stream>>>((double *)out, (const uint8_t *)poison.ptr,
+                                                                    nrow, nfc);
+        AFR_LAUNCH_OK();
+    }
+    return 0;
 }
 
 extern "C" int afr_vis_to_im(const void *vis, int vis_complex, const double *uvw,

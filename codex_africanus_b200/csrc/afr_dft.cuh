@@ -45,6 +45,7 @@ struct DdeWsParams {
     int arrive_all;  // AFR_SANITIZE=1: every consumer lane arrives on the "empty" barriers
 };
 size_t dde_ws_smem_bytes(int64_t nant, int ft, bool ant);
+int dde_ws_row_tile_channels(int64_t nant);
 // per-timestep antenna coordinates from baseline uvw; ok[0] is cleared when the rows of any
 // timestep are not differences of per-antenna coordinates
 int launch_antenna_uvw(const double *uvw, const int32_t *ant1, const int32_t *ant2,

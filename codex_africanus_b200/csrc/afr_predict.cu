@@ -710,7 +710,7 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
             // the three-stage antenna tile must fit in shared memory
             // (the 2048-row x 1-channel antenna-mode tile is 3.4x smaller per antenna than the
             // 512-row x 4-channel one, so SKA-size arrays still fit in antenna mode)
-            const bool fit4 = dde_ws_smem_bytes(nant, 4, false) <= 220 * 1024;
+            const bool fit4 = dde_ws_row_tile_channels(nant) > 0;  // 4, 2 or 1 channels per 512-row tile
             const bool fit1 = dde_ws_smem_bytes(nant, 1, true) <= 220 * 1024;
             const bool ws_ok = (fit4 || fit1) &&
                                reinterpret_cast<uintptr_t>(dde1) % 16 == 0 &&

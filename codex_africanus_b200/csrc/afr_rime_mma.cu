@@ -1,0 +1,415 @@
+// Full-RIME fused predict with DDEs in antenna-phasor mode as a batched complex FP64 GEMM on the
+// FP64 tensor pipe (DMMA, mma.sync.m8n8k4.f64), sm_100a:
+//
+//   V[t,f][(p,i),(q,j)] = sum_{s,k} P[(p,i),(s,k)] conj(Q[(q,j),(s,k)])
+//   P[(p,i),(s,k)] = k_p(s,f) (E1[s,t,p,f] B[s,f])[i,k]      Q[(q,j),(s,k)] = k_q(s,f) E2[s,t,q,f][j,k]
+//
+// (africanus/rime/predict.py:103-117,193-252 composed with rime/phase.py:20-63, as in
+// rime/examples/predict.py:107-134; the per-row phasor K[s,r,f] factorises as k_p conj(k_q) when
+// the baseline uvw are differences of per-antenna coordinates, which antenna_uvw_kernel of
+// afr_rime_ws.cu checks row by row before this path is allowed.)
+//
+// Why a GEMM here when the brief says "no dense GEMM is pretended": per (time, channel) the source
+// sum IS a rank-2*nsrc update of the (2 nant) x (2 nant) visibility matrix, and the scalar kernel
+// (afr_rime_ws.cu, 32 DFMA + 6 LDS.128 per term) is bound by shared-memory wavefronts, not by the
+// FP64 pipe (ncu: l1tex 78 %, FP64 47 %).  Measured (tools/dmma_microbench.cu): DMMA.8x8x4 issues
+// every 16 cycles per SM sub-partition = 64 FMA lanes/clk/SM = the full 37 TFLOP/s FP64 peak with 4
+// operand registers per 8 FMA per thread, where a DFMA with three distinct operands reaches 2/3 of
+// it.  A 16 x 16 complex warp tile needs 4 LDS.128 per 16 DMMA: shared memory drops to ~25 %.
+//
+// CTA = one (time, channel, pass); 12 consumer warps x 3 tiles of 16 x 16 complex outputs (8 x 8
+// antennas) = 36 tiles = the upper triangle of a 64-antenna array in ONE pass (larger arrays: panels
+// of tiles, one pass each).  4 producer warps stream two sources per stage (= one DMMA k-step of 4
+// complex k) through a three-stage mbarrier pipeline: cp.async of the raw E matrices straight into
+// their final rows, in-place scaling by the antenna phasor, P = (k E1) B.  Complex arithmetic on a
+// real MMA: a thread loads one complex element (LDS.128) of each operand fragment and issues
+//   Re C += Ar Br^T + Ai Bi^T,   Im C += Ai Br^T + (-Ar) Bi^T          (4 DMMA per 8x8x4 complex block).
+// The epilogue scatters each thread's (row i of V_pq: two complex values = 32 contiguous bytes) to the
+// caller's row order through a (time, antenna1, antenna2) -> row map.
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "afr_dft.cuh"
+
+namespace afr {
+namespace {
+
+constexpr int kConsWarps = 12;
+constexpr int kProdWarps = 4;
+constexpr int kNTP = kProdWarps * 32;
+constexpr int kThreads = (kConsWarps + kProdWarps) * 32;
+constexpr int kNS = 3;          // pipeline stages
+constexpr int kSlots = 3;       // tiles per consumer warp
+constexpr int kRowBytes = 64;   // one panel row: 4 complex k (2 sources x 2) of 16 bytes
+constexpr int kConsRegs = 144, kProdRegs = 80;  // 384 x 144 + 128 x 80 = 512 x 128
+
+struct Cd {
+    double re, im;
+};
+__device__ __forceinline__ Cd cmul_(Cd a, Cd b) {
+    return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+__device__ __forceinline__ Cd cadd_(Cd a, Cd b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ Cd lds_c(const unsigned char *p) {
+    const double2 v = *reinterpret_cast<const double2 *>(p);
+    return {v.x, v.y};
+}
+__device__ __forceinline__ void sts_c(unsigned char *p, Cd v) {
+    *reinterpret_cast<double2 *>(p) = make_double2(v.re, v.im);
+}
+__device__ __forceinline__ double neg_(double x) {  // sign flip on the integer pipe
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c[0]), "+d"(c[1])
+        : "d"(a), "d"(b));
+}
+
+// Panel rows are 64 bytes = 4 chunks of one complex value, chunk kc = 2 * (source in stage) + k.
+// The chunk is stored at kc ^ swz(row), swz = bit 2 of the row (= bit 1 of the antenna slot): a
+// consumer quarter-warp (rows r, r+1, all four chunks) still covers 128 contiguous bytes, and the
+// producers' 16-byte stores of 4 consecutive antenna slots x 2 sources (row parity alternating
+// with the slot, see the transform loop) fall into 8 distinct bank groups instead of 2.
+__device__ __forceinline__ unsigned chunk_off(int kc, int slot) { return (unsigned)((kc ^ ((slot >> 1) & 1)) * 16); }
+
+__global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMmaParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x, t = blockIdx.y;
+    const DdeMmaPass &pass = p.passes[blockIdx.z];
+    const int gi0 = pass.gi0, ni = pass.ni, gj0 = pass.gj0, nj = pass.nj;
+    const int nant = (int)p.nant;
+    const size_t p_bytes = (size_t)ni * 16 * kRowBytes, q_bytes = (size_t)nj * 16 * kRowBytes;
+    const size_t stage = p_bytes + q_bytes + 2 * 64;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kNS * stage);  // full, empty, landed [kNS]
+    auto p_of = [&](int st) { return smem + st * stage; };
+    auto q_of = [&](int st) { return smem + st * stage + p_bytes; };
+    auto b_of = [&](int st) { return smem + st * stage + p_bytes + q_bytes; };
+
+    if (tid == 0) {
+        for (int i = 0; i < kNS; ++i) {
+            mbar_init(&bars[i], kNTP);
+            mbar_init(&bars[kNS + i], p.arrive_all ? kConsWarps * 32 : kConsWarps);
+            mbar_init(&bars[2 * kNS + i], kNTP);
+        }
+    }
+    __syncthreads();
+
+    const long long nsrc = p.nsrc;
+    const long long npair = (nsrc + 1) / 2;
+
+    if (warp >= kConsWarps) {
+        // =============================== PRODUCERS ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kProdRegs));
+        const int ptid = tid - kConsWarps * 32;
+        // one E matrix serves both operands when E1 is E2 and the panel is on the diagonal
+        const bool shared = p.same_dde && gi0 == gj0 && ni == nj;
+        const int items_p = ni * 8 * 2, items_q = shared ? 0 : nj * 8 * 2;
+        const double nu = p.freq[f];
+        const double *ant_t = p.ant_uvw + (long long)t * nant * 3;
+        const long long mat_stride_s = (long long)p.ntime * nant * p.nchan * 64;  // bytes between sources
+        const char *e1_tf = reinterpret_cast<const char *>(p.dde1) + ((long long)t * nant * p.nchan + f) * 64;
+        const char *e2_tf = reinterpret_cast<const char *>(p.dde2) + ((long long)t * nant * p.nchan + f) * 64;
+        const long long ant_stride = (long long)p.nchan * 64;
+
+        // raw E matrices of source pair `pr` -> their final panel rows (16-byte cp.async)
+        auto issue = [&](long long pr) {
+            const int st = (int)(pr % kNS);
+            auto copy_items = [&](int nitems, int g0, const char *src_tf, unsigned char *panel) {
+                const unsigned dst0 = smem_addr(panel);
+                for (int idx = ptid; idx < nitems; idx += kNTP) {
+                    const int al = idx >> 1, sl = idx & 1, a = g0 * 8 + al;
+                    const long long s = 2 * pr + sl;
+                    if (a < nant && s < nsrc) {
+                        const char *src = src_tf + s * mat_stride_s + a * ant_stride;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                                                 dst0 + (unsigned)((2 * al + j) * kRowBytes) + chunk_off(2 * sl + k, al)),
+                                             "l"(src + (2 * j + k) * 16));
+                    }
+                }
+            };
+            if (shared) {
+                copy_items(items_p, gj0, e2_tf, q_of(st));
+            } else {
+                copy_items(items_p, gi0, e1_tf, p_of(st));
+                copy_items(items_q, gj0, e2_tf, q_of(st));
+            }
+            if (ptid < 8) {
+                const long long s = 2 * pr + (ptid >> 2);
+                if (s < nsrc)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                                     smem_addr(b_of(st)) + ptid * 16),
+                                 "l"(reinterpret_cast<const char *>(p.bright) + (s * (long long)p.nchan + f) * 64 +
+                                     (ptid & 3) * 16));
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(
+                             smem_addr(&bars[2 * kNS + st]))
+                         : "memory");
+        };
+        for (long long pr = 0; pr < kNS - 1 && pr < npair; ++pr) issue(pr);
+
+        for (long long pr = 0; pr < npair; ++pr) {
+            const int st = (int)(pr % kNS);
+            if (pr >= kNS) mbar_wait(&bars[kNS + st], (unsigned)(((pr - kNS) / kNS) & 1));
+            mbar_wait(&bars[2 * kNS + st], (unsigned)((pr / kNS) & 1));
+            unsigned char *pp = p_of(st), *qq = q_of(st);
+            const unsigned char *bb = b_of(st);
+            // antenna phasor k_a(s, f) = exp(i psi nu_f), psi = cst (l U_a + m V_a + n W_a): the same
+            // operations as the antenna mode of afr_rime_ws.cu
+            auto phasor = [&](int a, long long s) -> Cd {
+                const double psi = __dmul_rn(p.cst, phase_dot(p.lmn[3 * s], p.lmn[3 * s + 1], p.lmn[3 * s + 2],
+                                                              ant_t[3 * a], ant_t[3 * a + 1], ant_t[3 * a + 2], false));
+                const C2<double> kk = cis_fast(__dmul_rn(psi, nu));
+                return {kk.re, kk.im};
+            };
+            for (int idx = ptid; idx < items_p; idx += kNTP) {
+                const int al = idx >> 1, sl = idx & 1, a = gi0 * 8 + al;
+                const long long s = 2 * pr + sl;
+                const bool live = a < nant && s < nsrc;
+                const unsigned c0 = chunk_off(2 * sl, al), c1 = chunk_off(2 * sl + 1, al);
+                Cd k = {0.0, 0.0};
+                if (live) k = phasor(a, s);
+                const unsigned char *bm = bb + sl * 64;
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = jj ^ (al & 1);  // odd slots start with their second row: bank spread
+                    const unsigned row = (unsigned)((2 * al + j) * kRowBytes);
+                    Cd m0 = {0.0, 0.0}, m1 = {0.0, 0.0};
+                    if (live) {
+                        const unsigned char *src = (shared ? qq : pp) + row;
+                        Cd x0 = lds_c(src + c0), x1 = lds_c(src + c1);
+                        if (shared) {
+                            x0 = cmul_(k, x0), x1 = cmul_(k, x1);
+                            sts_c(qq + row + c0, x0);
+                            sts_c(qq + row + c1, x1);
+                        }
+                        const Cd b0 = lds_c(bm), b1 = lds_c(bm + 16), b2 = lds_c(bm + 32), b3 = lds_c(bm + 48);
+                        m0 = cadd_(cmul_(x0, b0), cmul_(x1, b2));
+                        m1 = cadd_(cmul_(x0, b1), cmul_(x1, b3));
+                        if (!shared) m0 = cmul_(k, m0), m1 = cmul_(k, m1);
+                    } else if (shared) {
+                        sts_c(qq + row + c0, m0);
+                        sts_c(qq + row + c1, m0);
+                    }
+                    sts_c(pp + row + c0, m0);
+                    sts_c(pp + row + c1, m1);
+                }
+            }
+            for (int idx = ptid; idx < items_q; idx += kNTP) {
+                const int al = idx >> 1, sl = idx & 1, a = gj0 * 8 + al;
+                const long long s = 2 * pr + sl;
+                const bool live = a < nant && s < nsrc;
+                const unsigned c0 = chunk_off(2 * sl, al), c1 = chunk_off(2 * sl + 1, al);
+                Cd k = {0.0, 0.0};
+                if (live) k = phasor(a, s);
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = jj ^ (al & 1);
+                    unsigned char *row = qq + (2 * al + j) * kRowBytes;
+                    Cd x0 = {0.0, 0.0}, x1 = {0.0, 0.0};
+                    if (live) x0 = cmul_(k, lds_c(row + c0)), x1 = cmul_(k, lds_c(row + c1));
+                    sts_c(row + c0, x0);
+                    sts_c(row + c1, x1);
+                }
+            }
+            mbar_arrive(&bars[st]);  // full: both panels of this source pair are ready
+            if (pr + kNS - 1 < npair) {
+                if (pr >= 1) mbar_wait(&bars[kNS + (int)((pr - 1) % kNS)], (unsigned)(((pr - 1) / kNS) & 1));
+                issue(pr + kNS - 1);
+            }
+        }
+        return;
+    }
+
+    // ================================= CONSUMERS =================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kConsRegs));
+    // tile `slot * 12 + warp` of the pass: (m0, n0) = first complex row in the P / Q panel, mask =
+    // which of its four 8 x 8 blocks (4 x 4 antennas) hold any baseline
+    unsigned moff[kSlots], noff[kSlots], mask[kSlots];
+#pragma unroll
+    for (int sl = 0; sl < kSlots; ++sl) {
+        const int ti = sl * kConsWarps + warp;
+        mask[sl] = ti < pass.ntiles ? pass.mask[ti] : 0u;
+        moff[sl] = (unsigned)(pass.tile_m[ti < pass.ntiles ? ti : 0] * 16 * kRowBytes);
+        noff[sl] = (unsigned)(pass.tile_n[ti < pass.ntiles ? ti : 0] * 16 * kRowBytes);
+    }
+    // fragment element of this lane: row lane / 4 of an 8-row block, chunk lane % 4 (swizzled by
+    // bit 2 of the row = bit 4 of the lane)
+    const unsigned lane_off = (unsigned)((lane >> 2) * kRowBytes + (((lane & 3) ^ ((lane >> 4) & 1)) * 16));
+
+    double cre[kSlots][2][2][2], cim[kSlots][2][2][2];
+#pragma unroll
+    for (int sl = 0; sl < kSlots; ++sl)
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int nn = 0; nn < 2; ++nn)
+                cre[sl][mi][nn][0] = cre[sl][mi][nn][1] = cim[sl][mi][nn][0] = cim[sl][mi][nn][1] = 0.0;
+
+    for (long long pr = 0; pr < npair; ++pr) {
+        const int st = (int)(pr % kNS);
+        mbar_wait(&bars[st], (unsigned)((pr / kNS) & 1));
+        const unsigned char *pb = p_of(st) + lane_off, *qb = q_of(st) + lane_off;
+#pragma unroll
+        for (int sl = 0; sl < kSlots; ++sl) {
+            if (mask[sl] == 0u) continue;  // warp-uniform
+            double2 a[2], b[2];
+            a[0] = *reinterpret_cast<const double2 *>(pb + moff[sl]);
+            a[1] = *reinterpret_cast<const double2 *>(pb + moff[sl] + 8 * kRowBytes);
+            b[0] = *reinterpret_cast<const double2 *>(qb + noff[sl]);
+            b[1] = *reinterpret_cast<const double2 *>(qb + noff[sl] + 8 * kRowBytes);
+            const double na[2] = {neg_(a[0].x), neg_(a[1].x)};
+            // independent accumulators first, their second products afterwards
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int nn = 0; nn < 2; ++nn)
+                    if (mask[sl] & (1u << (2 * mi + nn))) {
+                        dmma(cre[sl][mi][nn], a[mi].x, b[nn].x);
+                        dmma(cim[sl][mi][nn], a[mi].y, b[nn].x);
+                    }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int nn = 0; nn < 2; ++nn)
+                    if (mask[sl] & (1u << (2 * mi + nn))) {
+                        dmma(cre[sl][mi][nn], a[mi].y, b[nn].y);
+                        dmma(cim[sl][mi][nn], na[mi], b[nn].y);
+                    }
+        }
+        __syncwarp();
+        if (p.arrive_all || lane == 0) mbar_arrive(&bars[kNS + st]);
+    }
+
+    // ---- epilogue: this lane holds V_pq[i][0..1] of every block: p = row / 2, i = row % 2,
+    // q = first column / 2 -- 32 contiguous bytes of the caller's row (time, p, q)
+    const int32_t *map_t = p.rowmap + (long long)t * nant * nant;
+#pragma unroll
+    for (int sl = 0; sl < kSlots; ++sl) {
+        const int ti = sl * kConsWarps + warp;
+        if (ti >= pass.ntiles) continue;
+        const int row0 = (gi0 + 0) * 16 + pass.tile_m[ti] * 16, col0 = gj0 * 16 + pass.tile_n[ti] * 16;
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int nn = 0; nn < 2; ++nn) {
+                if (!(mask[sl] & (1u << (2 * mi + nn)))) continue;
+                const int row = row0 + 8 * mi + (lane >> 2), col = col0 + 8 * nn + 2 * (lane & 3);
+                const int pa = row >> 1, i = row & 1, qa = col >> 1;
+                if (pa < nant && qa < nant) {
+                    const int r = map_t[(long long)pa * nant + qa];
+                    if (r >= 0) {
+                        double2 *o = reinterpret_cast<double2 *>(p.out + ((long long)r * p.nchan + f) * 8 + i * 4);
+                        o[0] = make_double2(cre[sl][mi][nn][0], cim[sl][mi][nn][0]);
+                        o[1] = make_double2(cre[sl][mi][nn][1], cim[sl][mi][nn][1]);
+                    }
+                }
+            }
+    }
+}
+
+// rowmap[t][a1][a2] = row (the caller's order), dup[0] set when two rows share (t, a1, a2);
+// used4[(a1 / 4) * n4 + a2 / 4] = 1 where any timestep has a baseline of that 4 x 4 antenna block
+__global__ void baseline_map_kernel(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2,
+                                    long long nrow, long long ntime, long long nant, int n4, int32_t *rowmap,
+                                    uint8_t *used4, int *dup) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= nrow) return;
+    const long long t = time_index[r], a1 = ant1[r], a2 = ant2[r];
+    if (t < 0 || t >= ntime || a1 < 0 || a1 >= nant || a2 < 0 || a2 >= nant) {
+        atomicOr(dup, 2);
+        return;
+    }
+    const int old = atomicCAS(&rowmap[(t * nant + a1) * nant + a2], -1, (int)r);
+    if (old != -1) atomicOr(dup, 1);
+    used4[(a1 >> 2) * n4 + (a2 >> 2)] = 1;
+}
+
+}  // namespace
+
+size_t dde_mma_smem_bytes(int ni, int nj) {
+    return kNS * ((size_t)(ni + nj) * 16 * kRowBytes + 2 * 64) + 3 * kNS * sizeof(uint64_t);
+}
+
+int launch_baseline_map(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2, int64_t nrow,
+                        int64_t ntime, int64_t nant, int32_t *rowmap, uint8_t *used4, int *dup,
+                        cudaStream_t stream) {
+    const int n4 = (int)((nant + 3) / 4);
+    AFR_CUDA_OK(cudaMemsetAsync(rowmap, 0xFF, sizeof(int32_t) * (size_t)(ntime * nant * nant), stream));
+    AFR_CUDA_OK(cudaMemsetAsync(used4, 0, (size_t)n4 * n4, stream));
+    AFR_CUDA_OK(cudaMemsetAsync(dup, 0, sizeof(int), stream));
+    if (nrow <= 0) return 0;
+    baseline_map_kernel<<<(unsigned)((nrow + 255) / 256), 256, 0, stream>>>(time_index, ant1, ant2, nrow, ntime,
+                                                                            nant, n4, rowmap, used4, dup);
+    AFR_LAUNCH_OK();
+    return 0;
+}
+
+// Passes from the used 4 x 4-antenna blocks (host copy): panels of `ps` tile rows x `ps` tile
+// columns (a tile = 8 x 8 antennas); every panel pair with a used tile becomes one pass per 36 of
+// its used tiles.  64 antennas, a1 < a2: one pass of 36 tiles.
+std::vector<DdeMmaPass> dde_mma_passes(const std::vector<uint8_t> &used4, int64_t nant) {
+    const int n4 = (int)((nant + 3) / 4), n8 = (int)((nant + 7) / 8);
+    const int ps = n8 <= 8 ? 8 : 6;
+    std::vector<DdeMmaPass> passes;
+    auto u4 = [&](int i, int j) { return i < n4 && j < n4 && used4[(size_t)i * n4 + j] != 0; };
+    for (int pi = 0; pi < n8; pi += ps)
+        for (int pj = 0; pj < n8; pj += ps) {
+            DdeMmaPass cur{};
+            auto start = [&]() {
+                cur = DdeMmaPass{};
+                cur.gi0 = pi, cur.ni = std::min(ps, n8 - pi);
+                cur.gj0 = pj, cur.nj = std::min(ps, n8 - pj);
+            };
+            start();
+            for (int mt = 0; mt < std::min(ps, n8 - pi); ++mt)
+                for (int nt = 0; nt < std::min(ps, n8 - pj); ++nt) {
+                    unsigned m = 0;
+                    for (int mi = 0; mi < 2; ++mi)
+                        for (int nn = 0; nn < 2; ++nn)
+                            if (u4(2 * (pi + mt) + mi, 2 * (pj + nt) + nn)) m |= 1u << (2 * mi + nn);
+                    if (!m) continue;
+                    if (cur.ntiles == kConsWarps * kSlots) {
+                        passes.push_back(cur);
+                        start();
+                    }
+                    cur.tile_m[cur.ntiles] = (uint8_t)mt;
+                    cur.tile_n[cur.ntiles] = (uint8_t)nt;
+                    cur.mask[cur.ntiles] = (uint8_t)m;
+                    ++cur.ntiles;
+                }
+            if (cur.ntiles) passes.push_back(cur);
+        }
+    return passes;
+}
+
+int launch_fused_dde_mma(DdeMmaParams p, const std::vector<DdeMmaPass> &passes, cudaStream_t stream) {
+    if (passes.empty() || p.nsrc <= 0) return 0;
+    Scratch dpass;
+    AFR_CUDA_OK(dpass.alloc(sizeof(DdeMmaPass) * passes.size(), stream));
+    AFR_CUDA_OK(cudaMemcpyAsync(dpass.ptr, passes.data(), sizeof(DdeMmaPass) * passes.size(),
+                                cudaMemcpyHostToDevice, stream));
+    p.passes = (const DdeMmaPass *)dpass.ptr;
+    p.arrive_all = (getenv("AFR_SANITIZE") && atoi(getenv("AFR_SANITIZE")) != 0) ? 1 : 0;
+    int nmax = 0;
+    for (const auto &q : passes) nmax = std::max(nmax, q.ni + q.nj);
+    const size_t smem = dde_mma_smem_bytes(nmax, 0);
+    AFR_REQUIRE(p.ntime <= 65535 && passes.size() <= 65535, "afr_predict_fused: grid too large");
+    cudaFuncAttributes attr;
+    AFR_CUDA_OK(cudaFuncGetAttributes(&attr, fused_dde_mma_kernel));
+    AFR_REQUIRE(kThreads * attr.numRegs >= kConsWarps * 32 * kConsRegs + kProdWarps * 32 * kProdRegs,
+                "fused_dde_mma: launch-time register pool too small for setmaxnreg");
+    AFR_CUDA_OK(cudaFuncSetAttribute(fused_dde_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)p.nchan, (unsigned)p.ntime, (unsigned)passes.size());
+    fused_dde_mma_kernel<<<grid, kThreads, smem, stream>>>(p);
+    AFR_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace afr

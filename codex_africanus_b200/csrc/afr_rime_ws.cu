@@ -534,11 +534,20 @@ int launch_antenna_uvw(const double *uvw, const int32_t *ant1, const int32_t *an
     return 0;
 }
 
+// channels per CTA of the 512-row tile: the most of 4, 2, 1 whose three-stage antenna tile fits
+// in shared memory (4 up to 138 antennas, 2 up to 258, 1 up to 469); 0 = none fits
+int dde_ws_row_tile_channels(int64_t nant) {
+    for (int ft = 4; ft >= 1; ft /= 2)
+        if (dde_ws_smem_bytes(nant, ft, false) <= 220 * 1024) return ft;
+    return 0;
+}
+
 int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact, bool ant_mode,
                         cudaStream_t stream) {
     // antenna mode with more than one 512-row tile per timestep: 2048 rows x 1 channel per CTA
     const bool wide_rows = ant_mode && max_rows_per_time > kConsThreads;
-    const int ft = wide_rows ? 1 : 4, rpt = wide_rows ? 4 : 1;
+    const int ft = wide_rows ? 1 : dde_ws_row_tile_channels(p.nant), rpt = wide_rows ? 4 : 1;
+    AFR_REQUIRE(ft > 0, "afr_predict_fused: antenna tile does not fit in shared memory");
     const size_t smem = dde_ws_smem_bytes(p.nant, ft, ant_mode);
     const int rows = kConsThreads * rpt;
     dim3 grid((unsigned)((max_rows_per_time + rows - 1) / rows), (unsigned)p.ntime,
@@ -559,12 +568,20 @@ int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact,
         return 0;
     };
     int rc;
-    if (ant_mode)  // antenna phasors are evaluated per channel: any frequency array
-        rc = wide_rows ? go(fused_dde_ws_kernel<false, true, 1, 4>) : go(fused_dde_ws_kernel<false, true, 4, 1>);
+    if (wide_rows)  // antenna phasors are evaluated per channel: any frequency array
+        rc = go(fused_dde_ws_kernel<false, true, 1, 4>);
+    else if (ant_mode)
+        rc = ft == 4 ? go(fused_dde_ws_kernel<false, true, 4, 1>)
+                     : (ft == 2 ? go(fused_dde_ws_kernel<false, true, 2, 1>)
+                                : go(fused_dde_ws_kernel<false, true, 1, 1>));
     else if (exact)
-        rc = go(fused_dde_ws_kernel<true, false, 4, 1>);
+        rc = ft == 4 ? go(fused_dde_ws_kernel<true, false, 4, 1>)
+                     : (ft == 2 ? go(fused_dde_ws_kernel<true, false, 2, 1>)
+                                : go(fused_dde_ws_kernel<true, false, 1, 1>));
     else
-        rc = go(fused_dde_ws_kernel<false, false, 4, 1>);
+        rc = ft == 4 ? go(fused_dde_ws_kernel<false, false, 4, 1>)
+                     : (ft == 2 ? go(fused_dde_ws_kernel<false, false, 2, 1>)
+                                : go(fused_dde_ws_kernel<false, false, 1, 1>));
     if (rc) return rc;
     AFR_LAUNCH_OK();
     return 0;

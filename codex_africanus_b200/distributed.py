@@ -23,7 +23,7 @@ def row_shards(time_index, world_size):
     boundaries so that every rank needs only its own (time, ...) slices of the DDE/DIE
     arrays and ``time_index - min`` stays local (the rule the reference's dask wrapper
     imposes, africanus/rime/dask_predict.py:667-726).  Rows must be ordered by time."""
-    ti = np.asarray(time_index)
+    ti = _host_index(time_index)
     nrow = ti.shape[0]
     if nrow == 0:
         return [(0, 0)] * world_size
@@ -38,6 +38,14 @@ def row_shards(time_index, world_size):
         t1 = (ntime * (r + 1)) // world_size
         shards.append((int(bounds[t0]), int(bounds[t1])))
     return shards
+
+
+def _host_index(time_index):
+    """time_index as a host numpy array (CUDA tensors, lists and any integer dtype accepted, like
+    the single-GPU entry points)."""
+    if isinstance(time_index, torch.Tensor):
+        return time_index.detach().cpu().numpy()
+    return np.asarray(time_index)
 
 
 def _rank_world(group=None):
@@ -59,11 +67,12 @@ def sharded_im_to_vis(image, uvw, lm, frequency, time_index, convention="fourier
     if local_fn is None:
         from .dft import im_to_vis as local_fn
     rank, world = _rank_world(group)
-    r0, r1 = row_shards(time_index, world)[rank]
+    shards = row_shards(time_index, world)
+    r0, r1 = shards[rank]
     vis = local_fn(image, uvw[r0:r1], lm, frequency, convention=convention, dtype=dtype)
     if not gather or world == 1:
         return vis, (r0, r1)
-    return _gather_rows(vis, row_shards(time_index, world), group), (0, len(time_index))
+    return _gather_rows(vis, shards, group), (0, shards[-1][1])
 
 
 def sharded_fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
@@ -76,7 +85,7 @@ def sharded_fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenn
     rank, world = _rank_world(group)
     shards = row_shards(time_index, world)
     r0, r1 = shards[rank]
-    ti = np.asarray(time_index)
+    ti = _host_index(time_index)
     tmin = int(ti.min()) if ti.size else 0
     if r1 > r0:
         t_lo, t_hi = int(ti[r0]) - tmin, int(ti[r1 - 1]) - tmin + 1
@@ -86,6 +95,8 @@ def sharded_fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenn
     def tslice(a, axis):
         if a is None:
             return None
+        if not hasattr(a, "ndim"):
+            a = np.asarray(a)
         idx = [slice(None)] * a.ndim
         idx[axis] = slice(t_lo, t_hi)
         return a[tuple(idx)]
@@ -96,7 +107,7 @@ def sharded_fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenn
                    tslice(die2_jones, 0), convention=convention)
     if not gather or world == 1:
         return vis, (r0, r1)
-    return _gather_rows(vis, shards, group), (0, len(time_index))
+    return _gather_rows(vis, shards, group), (0, shards[-1][1])
 
 
 def _gather_rows(block, shards, group):
@@ -158,7 +169,7 @@ def sharded_stream_predict_vis_stokes(lm, uvw, frequency, stokes, spi, ref_freq,
     r0, r1 = row_shards(time_index, world)[rank]
     if r1 <= r0:
         return
-    ti = np.asarray(time_index.cpu() if isinstance(time_index, torch.Tensor) else time_index)
+    ti = _host_index(time_index)
     tmin = int(ti.min())
     t_lo, t_hi = int(ti[r0]) - tmin, int(ti[r1 - 1]) - tmin + 1
 

@@ -99,6 +99,38 @@ def gen_dft():
     save("dft", **out)
 
 
+def gen_dft_padded():
+    """A zero-padded image grid reaching past l^2 + m^2 = 1: n = sqrt(negative) - 1 = NaN there
+    (kernels.py:54 has no clamp), but exactly-zero pixels are skipped (kernels.py:64), so the
+    reference stays finite as long as every pixel outside the unit disc is zero.  Second case: one
+    bright pixel outside the disc poisons (NaN) exactly the channels / correlations where it is
+    non-zero."""
+    rng = np.random.default_rng(212)
+    npix, nrow, nchan, ncorr = 9, 21, 8, 2
+    x = np.linspace(-1.2, 1.2, npix)
+    ll, mm = np.meshgrid(x, x, indexing="ij")
+    lm = np.stack([ll.ravel(), mm.ravel()], axis=1)
+    inside = (lm**2).sum(axis=1) < 1.0
+    uvw = rng.standard_normal((nrow, 3)) * 40.0
+    freq = np.linspace(0.9e9, 1.3e9, nchan)
+    img = rng.standard_normal((npix * npix, nchan, ncorr))
+    img[~inside] = 0.0
+    out = dict(lm=lm, uvw=uvw, freq=freq, image=img)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out["i2v"] = im_to_vis(img, uvw, lm, freq)
+        out["i2v_c64"] = im_to_vis(img, uvw, lm, freq, dtype=np.complex64)
+        assert np.all(np.isfinite(out["i2v"]))
+        bad = img.copy()
+        k = int(np.flatnonzero(~inside)[3])
+        bad[k, 2:5, 1] = 1.5
+        out["image_bad"] = bad
+        out["i2v_bad"] = im_to_vis(bad, uvw, lm, freq)
+        assert np.isnan(out["i2v_bad"][:, 2:5, 1]).all() and np.isfinite(out["i2v_bad"][:, :, 0]).all()
+    save("dft_padded", **out)
+
+
 # --------------------------------------------------------------------------
 def gen_predict():
     """The reference's 27-case matrix (rime/tests/test_predict.py:33-126) with the
@@ -435,8 +467,14 @@ def gen_corrupt_vis():
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only:  # e.g. `python oracle/gen_golden.py gen_dft_padded`: (re)write the named files only
+        for name in only:
+            globals()[name]()
+        sys.exit(0)
     gen_phase()
     gen_dft()
+    gen_dft_padded()
     gen_predict()
     gen_beam()
     gen_fused()

@@ -1,0 +1,188 @@
+"""
+GPU parity at BASELINE configs[3] (SKA-Mid) phase magnitudes: 197 antennas out to 150 km, the
+full L band up to 1.712 GHz, 4096 equispaced AND non-uniform channels, fields of 0.02 and 0.1 rad,
+i.e. phase arguments |p| ~ 1e5 .. 5e5 rad where ulp(p) ~ 1.5e-11 .. 6e-11 -- one order from the
+1e-10 gate.  This is where the channel recurrence and its restarts, cis_fast's three-piece
+Cody-Waite reduction and the antenna-mode admission test of the DDE kernel are exercised.
+
+Every case runs the CUDA path on rows of one SKA-Mid timestep (the longest baselines always
+included) and compares with the CPU oracle on the same rows at the project gate
+(allclose rtol = 1e-10, atol = 1e-10 max|ref|, africanus/rime/phase.py:40-59,
+africanus/dft/kernels.py:48-65,120-144); the worst error relative to max|ref| is recorded in
+gpurun_out/parity_worst.jsonl (copied to profiles/ per round).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_c128_close
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+NA, NCHAN = 197, 4096
+FIELDS = (0.02, 0.1)
+
+
+def _record(name, got, ref):
+    scale = float(np.max(np.abs(ref)))
+    err = float(np.max(np.abs(np.asarray(got) - ref)) / scale)
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_worst.jsonl"), "a") as f:
+            f.write(json.dumps({"case": name, "max_abs_err_over_max_ref": err}) + "\n")
+    except OSError:
+        pass
+    print("%s: worst |got - ref| / max|ref| = %.3e" % (name, err))
+    return err
+
+
+@pytest.fixture(scope="module")
+def ska():
+    """One SKA-Mid timestep (19,306 baselines, 150 km), its 1024 longest + 1024 random rows."""
+    rng = np.random.default_rng(4)
+    uvw, ti, a1, a2 = synth.uvw_tracks(NA, 1, rng, t0=137, ntime_total=1000, max_radius=150e3)
+    ti = ti - ti.min()
+    length = np.linalg.norm(uvw, axis=1)
+    longest = np.argsort(length)[-1024:]
+    rest = rng.choice(np.setdiff1d(np.arange(uvw.shape[0]), longest), 1024, replace=False)
+    sub = np.sort(np.concatenate([longest, rest]))
+    assert length.max() > 100e3
+
+    class P:
+        pass
+
+    p = P()
+    p.uvw, p.ti, p.a1, p.a2, p.sub, p.rng = uvw, ti, a1, a2, sub, rng
+    p.freq_u = synth.frequencies(NCHAN)
+    # non-uniform: equispaced grid with every channel jittered by up to 40 % of the spacing
+    step = p.freq_u[1] - p.freq_u[0]
+    p.freq_n = p.freq_u + rng.uniform(-0.4, 0.4, NCHAN) * step
+    return p
+
+
+def _freq(ska, kind):
+    return ska.freq_u if kind == "uniform" else ska.freq_n
+
+
+@pytest.mark.parametrize("kind", ["uniform", "nonuniform"])
+@pytest.mark.parametrize("field", FIELDS)
+def test_im_to_vis_ska(ska, oracle, field, kind):
+    from codex_africanus_b200 import dft
+
+    rng = np.random.default_rng(41)
+    nsrc = 96
+    lm = synth.sky_lm(nsrc, rng, radius=field)
+    lm[0] = [field, 0.0]  # a source on the field edge
+    freq = _freq(ska, kind)
+    image = synth.stokes_image(nsrc, NCHAN, 1, rng, freq)
+    uvw = ska.uvw[ska.sub]
+    got = dft.im_to_vis(image, uvw, lm, freq)
+    ref = oracle.im_to_vis(image, uvw, lm, freq)
+    _record("im_to_vis field=%g %s" % (field, kind), got, ref)
+    assert_c128_close(got, ref)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "nonuniform"])
+@pytest.mark.parametrize("field", FIELDS)
+def test_vis_to_im_ska(ska, oracle, field, kind):
+    from codex_africanus_b200 import dft
+
+    rng = np.random.default_rng(42)
+    npix = 48
+    lm = synth.sky_lm(npix, rng, radius=field)
+    lm[0] = [0.0, -field]
+    freq = _freq(ska, kind)
+    uvw = ska.uvw[ska.sub[::2]]
+    nrow = uvw.shape[0]
+    vis = rng.standard_normal((nrow, NCHAN, 1)) + 1j * rng.standard_normal((nrow, NCHAN, 1))
+    flags = rng.random((nrow, NCHAN, 1)) < 0.05
+    got = dft.vis_to_im(vis, uvw, lm, freq, flags)
+    ref = oracle.vis_to_im(vis, uvw, lm, freq, flags)
+    _record("vis_to_im field=%g %s" % (field, kind), got, ref)
+    assert_c128_close(got, ref)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "nonuniform"])
+@pytest.mark.parametrize("field", FIELDS)
+def test_fused_point_predict_with_dies_ska(ska, oracle, field, kind):
+    """configs[3] proper is this call: point sources, 2x2 brightness, DIE gains."""
+    from codex_africanus_b200 import _lib, rime
+
+    rng = np.random.default_rng(43)
+    nsrc = 40
+    lm = synth.sky_lm(nsrc, rng, radius=field)
+    freq = _freq(ska, kind)
+    bright = synth.brightness_2x2(nsrc, NCHAN, rng, freq)
+    die = synth.gains(1, NA, NCHAN, rng)
+    sub = ska.sub[::2]
+    args = (lm, ska.uvw[sub], freq, bright, ska.ti[sub], ska.a1[sub], ska.a2[sub], None, None, die, None, die)
+    got = rime.fused_predict_vis(*args)
+    assert _lib.lib().afr_last_fused_path() == 1
+    ref = oracle.fused_predict(*args)
+    _record("fused point+DIE field=%g %s" % (field, kind), got, ref)
+    assert_c128_close(got, ref)
+
+
+def _dde_case(ska, oracle, field, kind, nchan, env, expect_path, monkeypatch, same=True):
+    """Full timestep on the device (the antenna decomposition needs every baseline), torch
+    tensors in and out; the oracle runs on a row subsample with the same Jones arrays."""
+    import torch
+
+    from codex_africanus_b200 import _lib, rime
+
+    rng = np.random.default_rng(44)
+    nsrc = 6
+    lm = synth.sky_lm(nsrc, rng, radius=field)
+    lm[0] = [field * 0.7, field * 0.7]
+    freq = _freq(ska, kind)[:: NCHAN // nchan].copy()
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    bright = synth.brightness_2x2(nsrc, nchan, rng, freq)
+    dde = np.eye(2) + 0.2 * rc((nsrc, 1, NA, nchan, 2, 2))
+    dde2 = dde if same else np.eye(2) + 0.2 * rc((nsrc, 1, NA, nchan, 2, 2))
+    die = synth.gains(1, NA, nchan, rng)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d_dde = t(dde)
+    d_dde2 = d_dde if same else t(dde2)
+    d_die = t(die)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = rime.fused_predict_vis(t(lm), t(ska.uvw), t(freq), t(bright), t(ska.ti), t(ska.a1), t(ska.a2),
+                                 d_dde, d_dde2, d_die, None, d_die)
+    for k in env:
+        monkeypatch.delenv(k)
+    path = _lib.lib().afr_last_fused_path()
+    assert path == expect_path, "fused DDE path %d, expected %d" % (path, expect_path)
+    sub = ska.sub[::16]
+    got = got[torch.from_numpy(sub).to(dev)].cpu().numpy()
+    ref = oracle.fused_predict(lm, ska.uvw[sub], freq, bright, ska.ti[sub], ska.a1[sub], ska.a2[sub], dde, dde2,
+                               die, None, die)
+    _record("fused DIE+DDE path=%d field=%g %s nchan=%d" % (path, field, kind, nchan), got, ref)
+    assert_c128_close(got, ref)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "nonuniform"])
+@pytest.mark.parametrize("field", FIELDS)
+def test_fused_dde_row_mode_ska(ska, oracle, monkeypatch, field, kind):
+    """150 km baselines x these fields fail the antenna-mode admission test (the per-antenna phase
+    could not be guaranteed within 5e-11 rad of the reference's rounded per-row phase), so the
+    warp-specialised kernel must run with per-row phasors (path 3) without being told to."""
+    _dde_case(ska, oracle, field, kind, 512, {}, 3, monkeypatch, same=(kind == "uniform"))
+
+
+@pytest.mark.parametrize("kind", ["uniform", "nonuniform"])
+def test_fused_dde_antenna_mode_ska(ska, oracle, monkeypatch, kind):
+    """A 0.004 rad field passes the admission test at 150 km: antenna-phasor mode (path 2); the
+    same inputs forced into per-row mode must agree too."""
+    _dde_case(ska, oracle, 0.004, kind, 512, {}, 2, monkeypatch)
+    _dde_case(ska, oracle, 0.004, kind, 256, {"AFR_DDE_ANT": "0"}, 3, monkeypatch, same=False)

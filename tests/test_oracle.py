@@ -101,6 +101,22 @@ def test_dft_golden(oracle, golden):
     assert_array_equal(got, g["v2i_c1_in32"])
 
 
+def test_dft_padded_grid_golden(oracle, golden):
+    """zero-padded image grid past the unit disc: n = NaN there (kernels.py:54), zero pixels are
+    skipped (kernels.py:64); a bright pixel out there gives NaN exactly where it is non-zero"""
+    g = golden("dft_padded")
+    lm, uvw, freq = g["lm"], g["uvw"], g["freq"]
+    with np.errstate(invalid="ignore"):
+        got = oracle.im_to_vis(g["image"], uvw, lm, freq)
+        assert np.all(np.isfinite(got))
+        assert_array_equal(got, g["i2v"])
+        assert_array_equal(oracle.im_to_vis(g["image"], uvw, lm, freq, dtype=np.complex64), g["i2v_c64"])
+        bad = oracle.im_to_vis(g["image_bad"], uvw, lm, freq)
+    assert_array_equal(np.isnan(bad), np.isnan(g["i2v_bad"]))
+    ok = ~np.isnan(bad)
+    assert_array_equal(bad[ok], g["i2v_bad"][ok])
+
+
 def test_im_to_vis_phase_centre(oracle):
     # dft/tests/test_dft.py:12-42
     nrow, npix, nchan, ncorr = 100, 35, 11, 2
