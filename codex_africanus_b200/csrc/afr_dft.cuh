@@ -2,6 +2,8 @@
 // by im_to_vis, vis_to_im and the fused point-source predict.
 #pragma once
 
+#include <vector>
+
 #include "afr_common.cuh"
 
 namespace afr {
@@ -57,5 +59,33 @@ int launch_row_tile_order(const int32_t *time_index, const int32_t *ant1, const 
                           cudaStream_t stream);
 int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact, bool ant_mode,
                         cudaStream_t stream);
+
+// ---- antenna-mode DDE predict as a complex FP64 GEMM on the DMMA pipe (afr_rime_mma.cu)
+// One pass: the consumer tiles (8 x 8 antennas each) of a panel of ni x nj antenna groups of 8,
+// starting at groups gi0 (rows, antenna 1) and gj0 (columns, antenna 2).
+struct DdeMmaPass {
+    int gi0, ni, gj0, nj, ntiles;
+    uint8_t tile_m[36], tile_n[36];  // tile position inside the panel
+    uint8_t mask[36];                // which 4 x 4-antenna blocks of the tile hold baselines
+};
+struct DdeMmaParams {
+    const double *lmn, *freq;
+    const double *bright;       // (nsrc,nchan,2,2) complex128
+    const double *dde1, *dde2;  // (nsrc,ntime,nant,nchan,2,2) complex128
+    const double *ant_uvw;      // (ntime,nant,3) per-antenna coordinates
+    const int32_t *rowmap;      // (ntime,nant,nant) row of baseline (t, a1, a2) or -1
+    const DdeMmaPass *passes;
+    double *out;                // (nrow,nchan,2,2) complex128
+    double cst;
+    long long nsrc, ntime, nant;
+    int nchan;
+    int same_dde;
+    int arrive_all;
+};
+int launch_baseline_map(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2, int64_t nrow,
+                        int64_t ntime, int64_t nant, int32_t *rowmap, uint8_t *used4, int *dup,
+                        cudaStream_t stream);
+std::vector<DdeMmaPass> dde_mma_passes(const std::vector<uint8_t> &used4, int64_t nant);
+int launch_fused_dde_mma(DdeMmaParams p, const std::vector<DdeMmaPass> &passes, cudaStream_t stream);
 
 }  // namespace afr

@@ -17,6 +17,7 @@
 //   base_vis and the DIE product are applied by the same epilogue as predict_vis.
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "afr_dft.cuh"
 
@@ -717,7 +718,21 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
                                reinterpret_cast<uintptr_t>(dde2) % 16 == 0 &&
                                reinterpret_cast<uintptr_t>(brightness) % 16 == 0 &&
                                !(getenv("AFR_DDE_WS") && atoi(getenv("AFR_DDE_WS")) == 0);
-            Scratch antuvw, antok;
+            Scratch antuvw, antok, rowmap, used4, dup;
+            // (time, antenna1, antenna2) -> row map of the GEMM path (afr_rime_mma.cu); AFR_DDE_MMA=0
+            // keeps the scalar warp-specialised kernel
+            const int n4 = (int)((nant + 3) / 4);
+            const bool mma_ok = ws_ok && nant <= 1024 && nrow < (1LL << 31) &&
+                                (double)ntime * nant * nant * 4.0 <= 1.0e9 &&
+                                !(getenv("AFR_DDE_MMA") && atoi(getenv("AFR_DDE_MMA")) == 0);
+            if (mma_ok) {
+                AFR_CUDA_OK(rowmap.alloc(sizeof(int32_t) * (size_t)(ntime * nant * nant), stream));
+                AFR_CUDA_OK(used4.alloc((size_t)n4 * n4, stream));
+                AFR_CUDA_OK(dup.alloc(sizeof(int), stream));
+                rc = launch_baseline_map(time_index, antenna1, antenna2, nrow, ntime, nant,
+                                         (int32_t *)rowmap.ptr, (uint8_t *)used4.ptr, (int *)dup.ptr, stream);
+                if (rc) return rc;
+            }
             if (ws_ok) {
                 AFR_CUDA_OK(antuvw.alloc(sizeof(double) * 3 * (size_t)(ntime * nant), stream));
                 AFR_CUDA_OK(antok.alloc(sizeof(int), stream));
@@ -733,11 +748,40 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
             AFR_CUDA_OK(cudaMemcpyAsync(hflags, fl.ptr, sizeof(hflags), cudaMemcpyDeviceToHost, stream));
             if (ws_ok)
                 AFR_CUDA_OK(cudaMemcpyAsync(&hant, antok.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            int hdup = 1;
+            std::vector<uint8_t> hused;
+            if (mma_ok) {
+                hused.resize((size_t)n4 * n4);
+                AFR_CUDA_OK(cudaMemcpyAsync(&hdup, dup.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                AFR_CUDA_OK(cudaMemcpyAsync(hused.data(), used4.ptr, hused.size(), cudaMemcpyDeviceToHost, stream));
+            }
             AFR_CUDA_OK(cudaStreamSynchronize(stream));
             const bool same = dde1 == dde2;
             const char *am_env = getenv("AFR_DDE_ANT");  // 0 forces the per-row phasor mode
             const bool ant_mode = hant != 0 && !(am_env && atoi(am_env) == 0);
-            const bool ws_fits = fit4 || (fit1 && ant_mode && hflags[1] > 512);
+            if (mma_ok && ant_mode && hdup == 0 && hflags[0] == 0 && hflags[1] > 0) {
+                // every baseline (t, a1, a2) names one row: source sum as a GEMM per (time, channel)
+                DdeMmaParams mp{};
+                mp.lmn = (const double *)lmn.ptr;
+                mp.freq = freq;
+                mp.bright = (const double *)brightness;
+                mp.dde1 = (const double *)dde1;
+                mp.dde2 = (const double *)dde2;
+                mp.ant_uvw = (const double *)antuvw.ptr;
+                mp.rowmap = (const int32_t *)rowmap.ptr;
+                mp.out = (double *)out;
+                mp.cst = cst;
+                mp.nsrc = nsrc;
+                mp.ntime = ntime;
+                mp.nant = nant;
+                mp.nchan = (int)nchan;
+                mp.same_dde = same ? 1 : 0;
+                rc = launch_fused_dde_mma(mp, dde_mma_passes(hused, nant), stream);
+                if (rc) return rc;
+                note_fused_path(AFR_PATH_DDE_MMA_ANT);
+                done = true;
+            }
+            const bool ws_fits = !done && (fit4 || (fit1 && ant_mode && hflags[1] > 512));
             if (ws_ok && ws_fits && hflags[0] == 0 && hflags[1] > 0 && nrow < (1LL << 31) && nant <= 1024) {
                 Scratch perm;
                 AFR_CUDA_OK(perm.alloc(sizeof(int32_t) * (size_t)nrow, stream));

@@ -66,6 +66,7 @@ unsigned long long afr_kernel_launches(void);
 #define AFR_PATH_DDE_WS_ROW 3   /* warp-specialised DDE kernel, per-row phasors               */
 #define AFR_PATH_DDE_TILED 4    /* antenna-tiled single-role kernel                           */
 #define AFR_PATH_DDE_GATHER 5   /* gather kernel (unsorted rows, diagonal Jones, complex64)   */
+#define AFR_PATH_DDE_MMA_ANT 6  /* antenna phasors, source sum as a complex GEMM on the FP64 tensor pipe */
 int afr_last_fused_path(void);
 /* Select the CUDA device used by subsequent calls on this host thread.  The library
  * links its own (static) CUDA runtime, whose current-device state is separate from any

@@ -5,7 +5,7 @@ call and with the CPU oracle.  Skipped on a single-GPU box (the driver's round-e
 `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu -q` (log under profiles/).
 
   * sharded_vis_to_im: per-rank partial dirty image + ONE all_reduce(SUM) (africanus/dft/dask.py:71-90)
-  * sharded_fused_predict_vis (DIE + DDE, antenna-consistent uvw -> warp-specialised DDE kernel) and
+  * sharded_fused_predict_vis (DIE + DDE, antenna-consistent uvw -> antenna-mode GEMM kernel) and
     sharded_im_to_vis: no data-path collective, final all_gather of the row blocks
     (africanus/rime/dask_predict.py:667-726)
 """
@@ -102,7 +102,7 @@ def test_nccl_sharded_paths_match_one_gpu_and_oracle(tmp_path, oracle, world):
                                     p["dde"], p["dde"], p["die"], p["bvis"], p["die"])
     for rank in range(world):
         got = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
-        assert int(got["path"]) == 2  # every shard ran the warp-specialised DDE kernel, antenna mode
+        assert int(got["path"]) == 6  # every shard ran the antenna-mode GEMM kernel
         # rows are independent: the gathered blocks are the one-GPU rows (same kernels, same order
         # of the source sum); the image differs by the summation order over row shards only
         assert_c128_close(got["vis"], one_vis, rtol=1e-13)

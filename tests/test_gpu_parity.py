@@ -434,8 +434,9 @@ def test_fused_predict_vs_oracle(b200, oracle):
 
 
 def test_fused_dde_ws_modes_vs_oracle(b200, oracle, monkeypatch):
-    """The warp-specialised DDE kernel: antenna-phasor mode (baseline uvw that are differences
-    of per-antenna coordinates, as in a Measurement Set), per-row phasor mode (forced, and
+    """The DDE kernels: antenna-phasor mode (baseline uvw that are differences of per-antenna
+    coordinates, as in a Measurement Set) as a DMMA GEMM (afr_rime_mma.cu) and as the scalar
+    warp-specialised kernel (AFR_DDE_MMA=0), per-row phasor mode (forced, and
     chosen automatically for uvw that are not antenna-consistent), and the previous tiled
     kernel must all match the oracle.  Ragged timesteps, channel tail, E1 != E2."""
     rng = np.random.default_rng(2024)
@@ -468,7 +469,7 @@ def test_fused_dde_ws_modes_vs_oracle(b200, oracle, monkeypatch):
         for uvw in (uvw_ant, uvw_rnd):
             for d1, d2 in ((dde, dde), (dde, dde_b)):
                 ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, d1, d2, die, None, die)
-                for env in ({}, {"AFR_DDE_ANT": "0"}, {"AFR_DDE_WS": "0"}):
+                for env in ({}, {"AFR_DDE_MMA": "0"}, {"AFR_DDE_ANT": "0"}, {"AFR_DDE_WS": "0"}):
                     for k, v in env.items():
                         monkeypatch.setenv(k, v)
                     got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, d1, d2,
@@ -483,8 +484,10 @@ def test_fused_dde_ws_modes_vs_oracle(b200, oracle, monkeypatch):
                         assert path == 4
                     elif "AFR_DDE_ANT" in env or uvw is uvw_rnd:
                         assert path == 3
-                    else:
+                    elif "AFR_DDE_MMA" in env:
                         assert path == 2
+                    else:
+                        assert path == 6  # source sum as a GEMM on the FP64 tensor pipe
 
 
 
@@ -595,7 +598,7 @@ def test_fused_predict_vis_beam_chunks(b200, oracle):
 
 
 
-def test_fused_dde_ws_many_antennas(b200, oracle):
+def test_fused_dde_ws_many_antennas(b200, oracle, monkeypatch):
     """140 antennas (9730 baselines): the three-stage antenna tile of the 512-row x 4-channel CTA
     does not fit in shared memory; antenna mode takes the 2048-row x 1-channel tile, random uvw the
     per-row mode with 512 rows x 2 channels per CTA (1 channel from 259 antennas on)."""
@@ -616,6 +619,11 @@ def test_fused_dde_ws_many_antennas(b200, oracle):
     dde = 1.0 + 0.2 * rc((nsrc, 1, na, nchan, 2, 2))
     ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde)
     got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde)
+    assert _lib.lib().afr_last_fused_path() == 6  # GEMM path: 18 x 18 tiles in 3 x 3 panels of 6
+    assert_c128_close(got, ref)
+    monkeypatch.setenv("AFR_DDE_MMA", "0")
+    got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde)
+    monkeypatch.delenv("AFR_DDE_MMA")
     assert _lib.lib().afr_last_fused_path() == 2
     assert_c128_close(got, ref)
     uvw_r = rng.standard_normal(uvw.shape) * 3000.0
@@ -663,8 +671,9 @@ def test_fused_equals_unfused_composition_on_gpu(b200):
         ref = b200.rime.predict_vis(tiT, a1T, a2T, d1, coh, d2, die, bvis, die)
         got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, tiT, a1T, a2T, d1, d2, die, bvis, die)
         assert_c128_close(got.cpu().numpy(), ref.cpu().numpy())
-    # Measurement-Set-like uvw (differences of per-antenna coordinates, 8 km array): the DDE
-    # kernel folds the phasor into the antenna Jones (2048-row x 1-channel tiles)
+    # Measurement-Set-like uvw (differences of per-antenna coordinates, 8 km array): the phasor
+    # folds into the antenna Jones and the source sum runs as a GEMM per (time, channel): one
+    # pass of 36 tiles for 64 antennas
     from codex_africanus_b200 import _lib
     antpos = rng.standard_normal((ntime, na, 3)) * 2500.0
     uvw_a = T(antpos[ti, ant1] - antpos[ti, ant2])
@@ -673,7 +682,7 @@ def test_fused_equals_unfused_composition_on_gpu(b200):
     for d1, d2 in ((dde, dde), (dde, dde_b)):
         ref = b200.rime.predict_vis(tiT, a1T, a2T, d1, coh_a, d2, die, bvis, die)
         got = b200.rime.fused_predict_vis(lm, uvw_a, freq, bright, tiT, a1T, a2T, d1, d2, die, bvis, die)
-        assert _lib.lib().afr_last_fused_path() == 2
+        assert _lib.lib().afr_last_fused_path() == 6
         assert_c128_close(got.cpu().numpy(), ref.cpu().numpy())
     # rows not ordered by time take the gather kernel; same answer
     perm = torch.from_numpy(rng.permutation(nrow)).to(dev)

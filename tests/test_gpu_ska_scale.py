@@ -182,7 +182,10 @@ def test_fused_dde_row_mode_ska(ska, oracle, monkeypatch, field, kind):
 
 @pytest.mark.parametrize("kind", ["uniform", "nonuniform"])
 def test_fused_dde_antenna_mode_ska(ska, oracle, monkeypatch, kind):
-    """A 0.004 rad field passes the admission test at 150 km: antenna-phasor mode (path 2); the
-    same inputs forced into per-row mode must agree too."""
-    _dde_case(ska, oracle, 0.004, kind, 512, {}, 2, monkeypatch)
+    """A 0.004 rad field passes the admission test at 150 km: antenna-phasor mode, as a GEMM on the
+    FP64 tensor pipe (path 6: 25 x 25 tiles in panels of 6 x 6, 15 + passes) and as the scalar
+    warp-specialised kernel (path 2); the same inputs forced into per-row mode must agree too."""
+    _dde_case(ska, oracle, 0.004, kind, 512, {}, 6, monkeypatch)
+    _dde_case(ska, oracle, 0.004, kind, 256, {}, 6, monkeypatch, same=False)
+    _dde_case(ska, oracle, 0.004, kind, 256, {"AFR_DDE_MMA": "0"}, 2, monkeypatch)
     _dde_case(ska, oracle, 0.004, kind, 256, {"AFR_DDE_ANT": "0"}, 3, monkeypatch, same=False)

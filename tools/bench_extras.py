@@ -253,7 +253,8 @@ def run(dev, fp64_peak):
     from codex_africanus_b200 import _lib as _l
     e["kernel"] = {2: "fused_dde_ws_kernel, antenna-phasor mode (2048 rows x 1 chan per CTA)",
                    3: "fused_dde_ws_kernel, per-row phasor mode", 4: "fused_dde_tiled_kernel",
-                   5: "fused_dde_kernel (gather)"}.get(_l.lib().afr_last_fused_path(), "?")
+                   5: "fused_dde_kernel (gather)",
+                   6: "fused_dde_mma_kernel, antenna-phasor mode as a DMMA GEMM per (time, chan)"}.get(_l.lib().afr_last_fused_path(), "?")
     res["fused_dde_predict_c128_cfg3_slice"] = e
     # ---- configs[2] proper: 1000 sources x 4 timesteps x 4096 chan, DDEs from the beam cube in
     # source chunks (the full DDE array would be 67 GB; device memory holds one 4 GiB chunk)
