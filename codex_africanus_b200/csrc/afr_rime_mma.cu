@@ -17,9 +17,9 @@
 // operand registers per 8 FMA per thread, where a DFMA with three distinct operands reaches 2/3 of
 // it.  A 16 x 16 complex warp tile needs 4 LDS.128 per 16 DMMA: shared memory drops to ~25 %.
 //
-// CTA = one (time, channel, pass); 12 consumer warps x 3 tiles of 16 x 16 complex outputs (8 x 8
-// antennas) = 36 tiles = the upper triangle of a 64-antenna array in ONE pass (larger arrays: panels
-// of tiles, one pass each).  4 producer warps stream two sources per stage (= one DMMA k-step of 4
+// CTA = one (time, channel, pass); 8 consumer warps x 5 tiles of 16 x 16 complex outputs (8 x 8
+// antennas) = 40 tiles >= the 36 of the upper triangle of a 64-antenna array: ONE pass (larger arrays:
+// panels of tiles, one pass each).  8 producer warps stream four sources per stage (= two DMMA k-steps of 4
 // complex k) through a three-stage mbarrier pipeline: cp.async of the raw E matrices straight into
 // their final rows, in-place scaling by the antenna phasor, P = (k E1) B.  Complex arithmetic on a
 // real MMA: a thread loads one complex element (LDS.128) of each operand fragment and issues
@@ -28,6 +28,7 @@
 // caller's row order through a (time, antenna1, antenna2) -> row map.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "afr_dft.cuh"
@@ -35,14 +36,16 @@
 namespace afr {
 namespace {
 
-constexpr int kConsWarps = 12;
-constexpr int kProdWarps = 4;
+constexpr int kConsWarps = 8;
+constexpr int kProdWarps = 8;
 constexpr int kNTP = kProdWarps * 32;
 constexpr int kThreads = (kConsWarps + kProdWarps) * 32;
 constexpr int kNS = 3;          // pipeline stages
-constexpr int kSlots = 3;       // tiles per consumer warp
+constexpr int kSlots = 5;       // tiles per consumer warp
 constexpr int kRowBytes = 64;   // one panel row: 4 complex k (2 sources x 2) of 16 bytes
-constexpr int kConsRegs = 144, kProdRegs = 80;  // 384 x 144 + 128 x 80 = 512 x 128
+constexpr int kKSteps = 2;      // DMMA k-steps (source pairs) per stage
+constexpr int kConsRegs = 192, kProdRegs = 64;  // 256 x 192 + 256 x 64 = 512 x 128
+static_assert(kConsWarps * kSlots == kDdeMmaMaxTiles, "tiles per pass");
 
 struct Cd {
     double re, im;
@@ -81,12 +84,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
     const DdeMmaPass &pass = p.passes[blockIdx.z];
     const int gi0 = pass.gi0, ni = pass.ni, gj0 = pass.gj0, nj = pass.nj;
     const int nant = (int)p.nant;
-    const size_t p_bytes = (size_t)ni * 16 * kRowBytes, q_bytes = (size_t)nj * 16 * kRowBytes;
-    const size_t stage = p_bytes + q_bytes + 2 * 64;
+    // stage = kKSteps x { P panel | Q panel } | B of the stage's 2 kKSteps sources
+    const unsigned p_bytes = (unsigned)ni * 16 * kRowBytes, q_bytes = (unsigned)nj * 16 * kRowBytes;
+    const unsigned kstep_bytes = p_bytes + q_bytes;
+    const unsigned stage = kKSteps * kstep_bytes + kKSteps * 2 * 64;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kNS * stage);  // full, empty, landed [kNS]
-    auto p_of = [&](int st) { return smem + st * stage; };
-    auto q_of = [&](int st) { return smem + st * stage + p_bytes; };
-    auto b_of = [&](int st) { return smem + st * stage + p_bytes + q_bytes; };
+    auto p_of = [&](int st, int ks) { return smem + st * stage + ks * kstep_bytes; };
+    auto q_of = [&](int st, int ks) { return smem + st * stage + ks * kstep_bytes + p_bytes; };
+    auto b_of = [&](int st) { return smem + st * stage + kKSteps * kstep_bytes; };
 
     if (tid == 0) {
         for (int i = 0; i < kNS; ++i) {
@@ -98,15 +103,26 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
     __syncthreads();
 
     const long long nsrc = p.nsrc;
-    const long long npair = (nsrc + 1) / 2;
+    constexpr int kSrcPerStage = 2 * kKSteps;
+    const long long nstage = (nsrc + kSrcPerStage - 1) / kSrcPerStage;
 
     if (warp >= kConsWarps) {
         // =============================== PRODUCERS ===============================
+        // The FP64 pipe of every SM sub-partition is kept busy by the consumers' DMMAs (16 cycles
+        // each), and the warp scheduler hands the pipe round in turn: a producer warp gets ONE FP64
+        // instruction in per rotation (~50 cycles with three DMMA warps beside it), whatever its
+        // instruction-level parallelism.  Measured with 12 consumer + 4 producer warps: 182 FP64
+        // instructions per producer warp and stage -> 8000 cycles per stage against 4600 of DMMA,
+        // consumers waiting on "full" 26 % of the time.  What counts is FP64 instructions per
+        // producer WARP: so 8 producer warps (one item per thread and stage at 64 antennas) beside
+        // 8 consumer warps with 5 / 4 tiles each (two DMMA warps per sub-partition still saturate the
+        // pipe), the phasors computed before waiting for the stage's copies, no branches in an item.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kProdRegs));
         const int ptid = tid - kConsWarps * 32;
         // one E matrix serves both operands when E1 is E2 and the panel is on the diagonal
         const bool shared = p.same_dde && gi0 == gj0 && ni == nj;
-        const int items_p = ni * 8 * 2, items_q = shared ? 0 : nj * 8 * 2;
+        const int per_p = ni * 16, per_q = nj * 16;  // items of one k-step: 8 antennas x 2 sources per group
+        const int items_p = kKSteps * per_p, items_q = shared ? 0 : kKSteps * per_q;
         const double nu = p.freq[f];
         const double *ant_t = p.ant_uvw + (long long)t * nant * 3;
         const long long mat_stride_s = (long long)p.ntime * nant * p.nchan * 64;  // bytes between sources
@@ -114,34 +130,36 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
         const char *e2_tf = reinterpret_cast<const char *>(p.dde2) + ((long long)t * nant * p.nchan + f) * 64;
         const long long ant_stride = (long long)p.nchan * 64;
 
-        // raw E matrices of source pair `pr` -> their final panel rows (16-byte cp.async)
-        auto issue = [&](long long pr) {
-            const int st = (int)(pr % kNS);
-            auto copy_items = [&](int nitems, int g0, const char *src_tf, unsigned char *panel) {
-                const unsigned dst0 = smem_addr(panel);
+        // raw E matrices of stage `sg` -> their final panel rows (16-byte cp.async)
+        auto issue = [&](long long sg) {
+            const int st = (int)(sg % kNS);
+            auto copy_items = [&](int nitems, int per, int g0, const char *src_tf, unsigned panel_off) {
+                const unsigned dst0 = smem_addr(smem + st * stage) + panel_off;
                 for (int idx = ptid; idx < nitems; idx += kNTP) {
-                    const int al = idx >> 1, sl = idx & 1, a = g0 * 8 + al;
-                    const long long s = 2 * pr + sl;
+                    const int ks = idx / per, rem = idx - ks * per;
+                    const int al = rem >> 1, sl = rem & 1, a = g0 * 8 + al;
+                    const long long s = sg * kSrcPerStage + 2 * ks + sl;
                     if (a < nant && s < nsrc) {
                         const char *src = src_tf + s * mat_stride_s + a * ant_stride;
+                        const unsigned dst = dst0 + ks * kstep_bytes + (unsigned)(2 * al * kRowBytes);
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
 #pragma unroll
                             for (int k = 0; k < 2; ++k)
                                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
-                                                 dst0 + (unsigned)((2 * al + j) * kRowBytes) + chunk_off(2 * sl + k, al)),
+                                                 dst + j * kRowBytes + chunk_off(2 * sl + k, al)),
                                              "l"(src + (2 * j + k) * 16));
                     }
                 }
             };
             if (shared) {
-                copy_items(items_p, gj0, e2_tf, q_of(st));
+                copy_items(items_p, per_p, gj0, e2_tf, p_bytes);
             } else {
-                copy_items(items_p, gi0, e1_tf, p_of(st));
-                copy_items(items_q, gj0, e2_tf, q_of(st));
+                copy_items(items_p, per_p, gi0, e1_tf, 0u);
+                copy_items(items_q, per_q, gj0, e2_tf, p_bytes);
             }
-            if (ptid < 8) {
-                const long long s = 2 * pr + (ptid >> 2);
+            if (ptid < kSrcPerStage * 4) {
+                const long long s = sg * kSrcPerStage + (ptid >> 2);
                 if (s < nsrc)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
                                      smem_addr(b_of(st)) + ptid * 16),
@@ -152,76 +170,96 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
                              smem_addr(&bars[2 * kNS + st]))
                          : "memory");
         };
-        for (long long pr = 0; pr < kNS - 1 && pr < npair; ++pr) issue(pr);
+        for (long long sg = 0; sg < kNS - 1 && sg < nstage; ++sg) issue(sg);
 
-        for (long long pr = 0; pr < npair; ++pr) {
-            const int st = (int)(pr % kNS);
-            if (pr >= kNS) mbar_wait(&bars[kNS + st], (unsigned)(((pr - kNS) / kNS) & 1));
-            mbar_wait(&bars[2 * kNS + st], (unsigned)((pr / kNS) & 1));
-            unsigned char *pp = p_of(st), *qq = q_of(st);
-            const unsigned char *bb = b_of(st);
+        // Item idx of a panel: k-step idx / per, antenna slot (idx % per) / 2, source parity idx % 2.
+        struct Item {
+            Cd k;            // antenna phasor, zero for a dead antenna / source
+            unsigned row;    // byte offset of the item's first row inside its k-step
+            unsigned c0, c1; // its two chunks
+            unsigned boff;   // brightness matrix of its source inside the stage's B block
+            int odd;         // odd antenna slot: rows in the order 1, 0 (bank spread)
+        };
+        auto setup = [&](int idx, int nitems, int per, int g0, long long sg) -> Item {
+            Item it;
+            (void)nitems;
+            const int ks = idx / per, rem = idx - ks * per;
+            const int al = rem >> 1, sl = rem & 1, a = g0 * 8 + al;
+            const long long s = sg * kSrcPerStage + 2 * ks + sl;
+            const bool live = a < nant && s < nsrc;
+            const int ac = min(a, nant - 1);
+            const long long sc = min(s, nsrc - 1);
             // antenna phasor k_a(s, f) = exp(i psi nu_f), psi = cst (l U_a + m V_a + n W_a): the same
             // operations as the antenna mode of afr_rime_ws.cu
-            auto phasor = [&](int a, long long s) -> Cd {
-                const double psi = __dmul_rn(p.cst, phase_dot(p.lmn[3 * s], p.lmn[3 * s + 1], p.lmn[3 * s + 2],
-                                                              ant_t[3 * a], ant_t[3 * a + 1], ant_t[3 * a + 2], false));
-                const C2<double> kk = cis_fast(__dmul_rn(psi, nu));
-                return {kk.re, kk.im};
+            const double psi = __dmul_rn(p.cst, phase_dot(p.lmn[3 * sc], p.lmn[3 * sc + 1], p.lmn[3 * sc + 2],
+                                                          ant_t[3 * ac], ant_t[3 * ac + 1], ant_t[3 * ac + 2], false));
+            const C2<double> kk = cis_fast(__dmul_rn(psi, nu));
+            it.k = {live ? kk.re : 0.0, live ? kk.im : 0.0};
+            it.row = ks * kstep_bytes + (unsigned)(2 * al * kRowBytes);
+            it.c0 = chunk_off(2 * sl, al), it.c1 = chunk_off(2 * sl + 1, al);
+            it.boff = (unsigned)((2 * ks + sl) * 64);
+            it.odd = al & 1;
+            return it;
+        };
+        auto zero_if_dead = [](Cd x, const Item &it) -> Cd {
+            // a dead item never had its rows copied: whatever the stage holds must not reach 0 * x
+            const bool live = it.k.re != 0.0 || it.k.im != 0.0;
+            return {live ? x.re : 0.0, live ? x.im : 0.0};
+        };
+
+        for (long long sg = 0; sg < nstage; ++sg) {
+            const int st = (int)(sg % kNS);
+            unsigned char *sbase = smem + st * stage;
+            const unsigned char *bb = b_of(st);
+            bool waited = false;
+            auto wait_landed = [&]() {
+                if (!waited) {
+                    if (sg >= kNS) mbar_wait(&bars[kNS + st], (unsigned)(((sg - kNS) / kNS) & 1));
+                    mbar_wait(&bars[2 * kNS + st], (unsigned)((sg / kNS) & 1));
+                    waited = true;
+                }
             };
+            // ---- P items: P = k (E1 B); shared: also Q = k E in place
             for (int idx = ptid; idx < items_p; idx += kNTP) {
-                const int al = idx >> 1, sl = idx & 1, a = gi0 * 8 + al;
-                const long long s = 2 * pr + sl;
-                const bool live = a < nant && s < nsrc;
-                const unsigned c0 = chunk_off(2 * sl, al), c1 = chunk_off(2 * sl + 1, al);
-                Cd k = {0.0, 0.0};
-                if (live) k = phasor(a, s);
-                const unsigned char *bm = bb + sl * 64;
+                const Item it = setup(idx, items_p, per_p, gi0, sg);
+                wait_landed();
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    const int j = jj ^ (al & 1);  // odd slots start with their second row: bank spread
-                    const unsigned row = (unsigned)((2 * al + j) * kRowBytes);
-                    Cd m0 = {0.0, 0.0}, m1 = {0.0, 0.0};
-                    if (live) {
-                        const unsigned char *src = (shared ? qq : pp) + row;
-                        Cd x0 = lds_c(src + c0), x1 = lds_c(src + c1);
-                        if (shared) {
-                            x0 = cmul_(k, x0), x1 = cmul_(k, x1);
-                            sts_c(qq + row + c0, x0);
-                            sts_c(qq + row + c1, x1);
-                        }
-                        const Cd b0 = lds_c(bm), b1 = lds_c(bm + 16), b2 = lds_c(bm + 32), b3 = lds_c(bm + 48);
-                        m0 = cadd_(cmul_(x0, b0), cmul_(x1, b2));
-                        m1 = cadd_(cmul_(x0, b1), cmul_(x1, b3));
-                        if (!shared) m0 = cmul_(k, m0), m1 = cmul_(k, m1);
-                    } else if (shared) {
-                        sts_c(qq + row + c0, m0);
-                        sts_c(qq + row + c1, m0);
+                    const unsigned row = it.row + (unsigned)((jj ^ it.odd) * kRowBytes);
+                    const unsigned char *src = sbase + (shared ? p_bytes : 0u) + row;
+                    Cd x0 = zero_if_dead(lds_c(src + it.c0), it), x1 = zero_if_dead(lds_c(src + it.c1), it);
+                    const unsigned char *bm = bb + it.boff;
+                    const Cd b0 = lds_c(bm), b1 = lds_c(bm + 16), b2 = lds_c(bm + 32), b3 = lds_c(bm + 48);
+                    if (shared) {
+                        x0 = cmul_(it.k, x0), x1 = cmul_(it.k, x1);
+                        sts_c(sbase + p_bytes + row + it.c0, x0);
+                        sts_c(sbase + p_bytes + row + it.c1, x1);
                     }
-                    sts_c(pp + row + c0, m0);
-                    sts_c(pp + row + c1, m1);
+                    Cd m0 = cadd_(cmul_(x0, b0), cmul_(x1, b2));
+                    Cd m1 = cadd_(cmul_(x0, b1), cmul_(x1, b3));
+                    if (!shared) m0 = cmul_(it.k, m0), m1 = cmul_(it.k, m1);
+                    sts_c(sbase + row + it.c0, m0);
+                    sts_c(sbase + row + it.c1, m1);
                 }
             }
+            // ---- Q items (off-diagonal panels, or E1 != E2): Q = k E2 in place
             for (int idx = ptid; idx < items_q; idx += kNTP) {
-                const int al = idx >> 1, sl = idx & 1, a = gj0 * 8 + al;
-                const long long s = 2 * pr + sl;
-                const bool live = a < nant && s < nsrc;
-                const unsigned c0 = chunk_off(2 * sl, al), c1 = chunk_off(2 * sl + 1, al);
-                Cd k = {0.0, 0.0};
-                if (live) k = phasor(a, s);
+                const Item it = setup(idx, items_q, per_q, gj0, sg);
+                wait_landed();
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    const int j = jj ^ (al & 1);
-                    unsigned char *row = qq + (2 * al + j) * kRowBytes;
-                    Cd x0 = {0.0, 0.0}, x1 = {0.0, 0.0};
-                    if (live) x0 = cmul_(k, lds_c(row + c0)), x1 = cmul_(k, lds_c(row + c1));
-                    sts_c(row + c0, x0);
-                    sts_c(row + c1, x1);
+                    unsigned char *row = sbase + p_bytes + it.row + (unsigned)((jj ^ it.odd) * kRowBytes);
+                    const Cd x0 = cmul_(it.k, zero_if_dead(lds_c(row + it.c0), it));
+                    const Cd x1 = cmul_(it.k, zero_if_dead(lds_c(row + it.c1), it));
+                    sts_c(row + it.c0, x0);
+                    sts_c(row + it.c1, x1);
                 }
             }
-            mbar_arrive(&bars[st]);  // full: both panels of this source pair are ready
-            if (pr + kNS - 1 < npair) {
-                if (pr >= 1) mbar_wait(&bars[kNS + (int)((pr - 1) % kNS)], (unsigned)(((pr - 1) / kNS) & 1));
-                issue(pr + kNS - 1);
+            wait_landed();
+            mbar_arrive(&bars[st]);  // full: the panels of this stage are ready
+            if (sg + kNS - 1 < nstage) {
+                if (sg >= 1) mbar_wait(&bars[kNS + (int)((sg - 1) % kNS)], (unsigned)(((sg - 1) / kNS) & 1));
+                issue(sg + kNS - 1);
             }
         }
         return;
@@ -229,16 +267,20 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
 
     // ================================= CONSUMERS =================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kConsRegs));
-    // tile `slot * 12 + warp` of the pass: (m0, n0) = first complex row in the P / Q panel, mask =
+    // tile `slot * 8 + warp` of the pass: (m0, n0) = first complex row in the P / Q panel, mask =
     // which of its four 8 x 8 blocks (4 x 4 antennas) hold any baseline
-    unsigned moff[kSlots], noff[kSlots], mask[kSlots];
+    // (packed: the 160 accumulator registers leave little room) desc = mask | tile_m << 8 | tile_n << 16
+    unsigned desc[kSlots];
 #pragma unroll
     for (int sl = 0; sl < kSlots; ++sl) {
         const int ti = sl * kConsWarps + warp;
-        mask[sl] = ti < pass.ntiles ? pass.mask[ti] : 0u;
-        moff[sl] = (unsigned)(pass.tile_m[ti < pass.ntiles ? ti : 0] * 16 * kRowBytes);
-        noff[sl] = (unsigned)(pass.tile_n[ti < pass.ntiles ? ti : 0] * 16 * kRowBytes);
+        desc[sl] = ti < pass.ntiles ? (unsigned)pass.mask[ti] | ((unsigned)pass.tile_m[ti] << 8) |
+                                          ((unsigned)pass.tile_n[ti] << 16)
+                                    : 0u;
     }
+    auto mask_of = [&](int sl) { return desc[sl] & 0xFu; };
+    auto moff_of = [&](int sl) { return ((desc[sl] >> 8) & 0xFFu) * (16u * kRowBytes); };
+    auto noff_of = [&](int sl) { return (desc[sl] >> 16) * (16u * kRowBytes); };
     // fragment element of this lane: row lane / 4 of an 8-row block, chunk lane % 4 (swizzled by
     // bit 2 of the row = bit 4 of the lane)
     const unsigned lane_off = (unsigned)((lane >> 2) * kRowBytes + (((lane & 3) ^ ((lane >> 4) & 1)) * 16));
@@ -252,36 +294,48 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
             for (int nn = 0; nn < 2; ++nn)
                 cre[sl][mi][nn][0] = cre[sl][mi][nn][1] = cim[sl][mi][nn][0] = cim[sl][mi][nn][1] = 0.0;
 
-    for (long long pr = 0; pr < npair; ++pr) {
-        const int st = (int)(pr % kNS);
-        mbar_wait(&bars[st], (unsigned)((pr / kNS) & 1));
-        const unsigned char *pb = p_of(st) + lane_off, *qb = q_of(st) + lane_off;
+    // one tile, one k-step: 4 LDS.128, 16 DMMA (FULL: all four blocks, no predicates)
+    auto tile_step = [&](auto full_tag, int sl, const unsigned char *pb, const unsigned char *qb) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        double2 a[2], b[2];
+        const unsigned char *pa = pb + moff_of(sl), *qa = qb + noff_of(sl);
+        a[0] = *reinterpret_cast<const double2 *>(pa);
+        a[1] = *reinterpret_cast<const double2 *>(pa + 8 * kRowBytes);
+        b[0] = *reinterpret_cast<const double2 *>(qa);
+        b[1] = *reinterpret_cast<const double2 *>(qa + 8 * kRowBytes);
+        const double na[2] = {neg_(a[0].x), neg_(a[1].x)};
+        // independent accumulators first, their second products afterwards
 #pragma unroll
-        for (int sl = 0; sl < kSlots; ++sl) {
-            if (mask[sl] == 0u) continue;  // warp-uniform
-            double2 a[2], b[2];
-            a[0] = *reinterpret_cast<const double2 *>(pb + moff[sl]);
-            a[1] = *reinterpret_cast<const double2 *>(pb + moff[sl] + 8 * kRowBytes);
-            b[0] = *reinterpret_cast<const double2 *>(qb + noff[sl]);
-            b[1] = *reinterpret_cast<const double2 *>(qb + noff[sl] + 8 * kRowBytes);
-            const double na[2] = {neg_(a[0].x), neg_(a[1].x)};
-            // independent accumulators first, their second products afterwards
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
+            for (int nn = 0; nn < 2; ++nn)
+                if (FULL || (mask_of(sl) & (1u << (2 * mi + nn)))) {
+                    dmma(cre[sl][mi][nn], a[mi].x, b[nn].x);
+                    dmma(cim[sl][mi][nn], a[mi].y, b[nn].x);
+                }
 #pragma unroll
-                for (int nn = 0; nn < 2; ++nn)
-                    if (mask[sl] & (1u << (2 * mi + nn))) {
-                        dmma(cre[sl][mi][nn], a[mi].x, b[nn].x);
-                        dmma(cim[sl][mi][nn], a[mi].y, b[nn].x);
-                    }
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
+            for (int nn = 0; nn < 2; ++nn)
+                if (FULL || (mask_of(sl) & (1u << (2 * mi + nn)))) {
+                    dmma(cre[sl][mi][nn], a[mi].y, b[nn].y);
+                    dmma(cim[sl][mi][nn], na[mi], b[nn].y);
+                }
+    };
+
+    for (long long sg = 0; sg < nstage; ++sg) {
+        const int st = (int)(sg % kNS);
+        mbar_wait(&bars[st], (unsigned)((sg / kNS) & 1));
 #pragma unroll
-                for (int nn = 0; nn < 2; ++nn)
-                    if (mask[sl] & (1u << (2 * mi + nn))) {
-                        dmma(cre[sl][mi][nn], a[mi].y, b[nn].y);
-                        dmma(cim[sl][mi][nn], na[mi], b[nn].y);
-                    }
+        for (int ks = 0; ks < kKSteps; ++ks) {
+            const unsigned char *pb = p_of(st, ks) + lane_off, *qb = q_of(st, ks) + lane_off;
+#pragma unroll
+            for (int sl = 0; sl < kSlots; ++sl) {
+                if (mask_of(sl) == 0xFu)  // warp-uniform
+                    tile_step(std::true_type{}, sl, pb, qb);
+                else if (mask_of(sl) != 0u)
+                    tile_step(std::false_type{}, sl, pb, qb);
+            }
         }
         __syncwarp();
         if (p.arrive_all || lane == 0) mbar_arrive(&bars[kNS + st]);
@@ -294,12 +348,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
     for (int sl = 0; sl < kSlots; ++sl) {
         const int ti = sl * kConsWarps + warp;
         if (ti >= pass.ntiles) continue;
-        const int row0 = (gi0 + 0) * 16 + pass.tile_m[ti] * 16, col0 = gj0 * 16 + pass.tile_n[ti] * 16;
+        const int row0 = gi0 * 16 + pass.tile_m[ti] * 16, col0 = gj0 * 16 + pass.tile_n[ti] * 16;
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int nn = 0; nn < 2; ++nn) {
-                if (!(mask[sl] & (1u << (2 * mi + nn)))) continue;
+                if (!(mask_of(sl) & (1u << (2 * mi + nn)))) continue;
                 const int row = row0 + 8 * mi + (lane >> 2), col = col0 + 8 * nn + 2 * (lane & 3);
                 const int pa = row >> 1, i = row & 1, qa = col >> 1;
                 if (pa < nant && qa < nant) {
@@ -334,7 +388,7 @@ __global__ void baseline_map_kernel(const int32_t *time_index, const int32_t *an
 }  // namespace
 
 size_t dde_mma_smem_bytes(int ni, int nj) {
-    return kNS * ((size_t)(ni + nj) * 16 * kRowBytes + 2 * 64) + 3 * kNS * sizeof(uint64_t);
+    return kNS * kKSteps * ((size_t)(ni + nj) * 16 * kRowBytes + 2 * 64) + 3 * kNS * sizeof(uint64_t);
 }
 
 int launch_baseline_map(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2, int64_t nrow,
@@ -375,7 +429,7 @@ std::vector<DdeMmaPass> dde_mma_passes(const std::vector<uint8_t> &used4, int64_
                         for (int nn = 0; nn < 2; ++nn)
                             if (u4(2 * (pi + mt) + mi, 2 * (pj + nt) + nn)) m |= 1u << (2 * mi + nn);
                     if (!m) continue;
-                    if (cur.ntiles == kConsWarps * kSlots) {
+                    if (cur.ntiles == kDdeMmaMaxTiles) {
                         passes.push_back(cur);
                         start();
                     }
