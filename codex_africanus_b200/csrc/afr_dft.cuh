@@ -63,7 +63,7 @@ int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact,
 // ---- antenna-mode DDE predict as a complex FP64 GEMM on the DMMA pipe (afr_rime_mma.cu)
 // One pass: the consumer tiles (8 x 8 antennas each) of a panel of ni x nj antenna groups of 8,
 // starting at groups gi0 (rows, antenna 1) and gj0 (columns, antenna 2).
-constexpr int kDdeMmaMaxTiles = 40;
+constexpr int kDdeMmaMaxTiles = 36;
 struct DdeMmaPass {
     int gi0, ni, gj0, nj, ntiles;
     uint8_t tile_m[kDdeMmaMaxTiles], tile_n[kDdeMmaMaxTiles];  // tile position inside the panel

@@ -17,11 +17,11 @@
 // operand registers per 8 FMA per thread, where a DFMA with three distinct operands reaches 2/3 of
 // it.  A 16 x 16 complex warp tile needs 4 LDS.128 per 16 DMMA: shared memory drops to ~25 %.
 //
-// CTA = one (time, channel, pass); 8 consumer warps x 5 tiles of 16 x 16 complex outputs (8 x 8
-// antennas) = 40 tiles >= the 36 of the upper triangle of a 64-antenna array: ONE pass (larger arrays:
-// panels of tiles, one pass each).  8 producer warps stream four sources per stage (= two DMMA k-steps of 4
-// complex k) through a three-stage mbarrier pipeline: cp.async of the raw E matrices straight into
-// their final rows, in-place scaling by the antenna phasor, P = (k E1) B.  Complex arithmetic on a
+// CTA = one (time, channel, pass); 12 warps x 3 tiles of 16 x 16 complex outputs (8 x 8 antennas) =
+// 36 tiles = the upper triangle of a 64-antenna array in ONE pass (larger arrays: panels of tiles,
+// one pass each).  Four sources per stage (= two DMMA k-steps of 4 complex k), five shared-memory
+// stages: cp.async of the raw E matrices straight into their final rows three stages ahead, in-place
+// scaling by the antenna phasor and P = (k E1) B two stages ahead.  Complex arithmetic on a
 // real MMA: a thread loads one complex element (LDS.128) of each operand fragment and issues
 //   Re C += Ar Br^T + Ai Bi^T,   Im C += Ai Br^T + (-Ar) Bi^T          (4 DMMA per 8x8x4 complex block).
 // The epilogue scatters each thread's (row i of V_pq: two complex values = 32 contiguous bytes) to the
@@ -36,16 +36,14 @@
 namespace afr {
 namespace {
 
-constexpr int kConsWarps = 8;
-constexpr int kProdWarps = 8;
-constexpr int kNTP = kProdWarps * 32;
-constexpr int kThreads = (kConsWarps + kProdWarps) * 32;
-constexpr int kNS = 3;          // pipeline stages
-constexpr int kSlots = 5;       // tiles per consumer warp
+constexpr int kWarps = 12;      // every warp transforms AND multiplies (see the kernel)
+constexpr int kThreads = kWarps * 32;
+constexpr int kNS = 5;          // shared-memory stages: consumed | 2 transformed | landing | spare
+constexpr int kSlots = 3;       // tiles per warp
 constexpr int kRowBytes = 64;   // one panel row: 4 complex k (2 sources x 2) of 16 bytes
 constexpr int kKSteps = 2;      // DMMA k-steps (source pairs) per stage
-constexpr int kConsRegs = 192, kProdRegs = 64;  // 256 x 192 + 256 x 64 = 512 x 128
-static_assert(kConsWarps * kSlots == kDdeMmaMaxTiles, "tiles per pass");
+constexpr int kSrcPerStage = 2 * kKSteps;
+static_assert(kWarps * kSlots == kDdeMmaMaxTiles, "tiles per pass");
 
 struct Cd {
     double re, im;
@@ -53,7 +51,13 @@ struct Cd {
 __device__ __forceinline__ Cd cmul_(Cd a, Cd b) {
     return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
 }
-__device__ __forceinline__ Cd cadd_(Cd a, Cd b) { return {a.re + b.re, a.im + b.im}; }
+// a * b + c * d with one DMUL + three DFMA per component
+__device__ __forceinline__ Cd cmul2_(Cd a, Cd b, Cd c, Cd d) {
+    Cd r;
+    r.re = fma(-c.im, d.im, fma(c.re, d.re, fma(-a.im, b.im, a.re * b.re)));
+    r.im = fma(c.im, d.re, fma(c.re, d.im, fma(a.im, b.re, a.re * b.im)));
+    return r;
+}
 __device__ __forceinline__ Cd lds_c(const unsigned char *p) {
     const double2 v = *reinterpret_cast<const double2 *>(p);
     return {v.x, v.y};
@@ -70,13 +74,23 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
         : "d"(a), "d"(b));
 }
 
-// Panel rows are 64 bytes = 4 chunks of one complex value, chunk kc = 2 * (source in stage) + k.
+// Panel rows are 64 bytes = 4 chunks of one complex value, chunk kc = 2 * (source in k-step) + k.
 // The chunk is stored at kc ^ swz(row), swz = bit 2 of the row (= bit 1 of the antenna slot): a
-// consumer quarter-warp (rows r, r+1, all four chunks) still covers 128 contiguous bytes, and the
-// producers' 16-byte stores of 4 consecutive antenna slots x 2 sources (row parity alternating
-// with the slot, see the transform loop) fall into 8 distinct bank groups instead of 2.
+// quarter-warp of a fragment load (rows r, r+1, all four chunks) still covers 128 contiguous
+// bytes, and the transform's 16-byte stores of 4 consecutive antenna slots x 2 sources (row parity
+// alternating with the slot, see the transform loop) fall into 8 distinct bank groups instead of 2.
 __device__ __forceinline__ unsigned chunk_off(int kc, int slot) { return (unsigned)((kc ^ ((slot >> 1) & 1)) * 16); }
 
+// Schedule.  The first two versions had dedicated producer warps (4, then 8) preparing the panels
+// while consumer warps multiplied; both stopped at 61 % DMMA-pipe utilisation with the consumers
+// waiting on "panel ready" 16-26 % of the time (profiles/ncu_full_fused_dde_mma_r2{a,c}.txt).  Cause:
+// the DMMAs keep the FP64 pipe of every SM sub-partition busy (16 cycles each) and the scheduler
+// hands the pipe round in turn, so a warp issuing scalar FP64 gets ONE instruction in per rotation
+// (~36-50 cycles).  The ~90 FP64 instructions per warp and stage of the phasor + Jones products then
+// take longer than the stage's DMMAs -- a latency problem that extra parallelism inside a producer
+// warp cannot fix.  So there are no producers: every warp alternates between transforming its share
+// of stage s+1 (while its two neighbours on the sub-partition keep the pipe full of DMMAs) and
+// multiplying stage s, five shared-memory stages deep so that warps may drift a whole phase apart.
 __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMmaParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -84,196 +98,150 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
     const DdeMmaPass &pass = p.passes[blockIdx.z];
     const int gi0 = pass.gi0, ni = pass.ni, gj0 = pass.gj0, nj = pass.nj;
     const int nant = (int)p.nant;
-    // stage = kKSteps x { P panel | Q panel } | B of the stage's 2 kKSteps sources
+    // stage = kKSteps x { P panel | Q panel } | B of the stage's sources
     const unsigned p_bytes = (unsigned)ni * 16 * kRowBytes, q_bytes = (unsigned)nj * 16 * kRowBytes;
     const unsigned kstep_bytes = p_bytes + q_bytes;
-    const unsigned stage = kKSteps * kstep_bytes + kKSteps * 2 * 64;
+    const unsigned stage = kKSteps * kstep_bytes + kSrcPerStage * 64;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kNS * stage);  // full, empty, landed [kNS]
-    auto p_of = [&](int st, int ks) { return smem + st * stage + ks * kstep_bytes; };
-    auto q_of = [&](int st, int ks) { return smem + st * stage + ks * kstep_bytes + p_bytes; };
     auto b_of = [&](int st) { return smem + st * stage + kKSteps * kstep_bytes; };
 
     if (tid == 0) {
         for (int i = 0; i < kNS; ++i) {
-            mbar_init(&bars[i], kNTP);
-            mbar_init(&bars[kNS + i], p.arrive_all ? kConsWarps * 32 : kConsWarps);
-            mbar_init(&bars[2 * kNS + i], kNTP);
+            // full / empty: one elected lane per warp (after __syncwarp); AFR_SANITIZE=1: every lane
+            mbar_init(&bars[i], p.arrive_all ? kThreads : kWarps);
+            mbar_init(&bars[kNS + i], p.arrive_all ? kThreads : kWarps);
+            mbar_init(&bars[2 * kNS + i], kThreads);  // landed: the cp.async of every thread
         }
     }
     __syncthreads();
 
     const long long nsrc = p.nsrc;
-    constexpr int kSrcPerStage = 2 * kKSteps;
     const long long nstage = (nsrc + kSrcPerStage - 1) / kSrcPerStage;
+    // one E matrix serves both operands when E1 is E2 and the panel is on the diagonal
+    const bool shared = p.same_dde && gi0 == gj0 && ni == nj;
+    const int per_p = ni * 16, per_q = nj * 16;  // items of one k-step: 8 antennas x 2 sources per group
+    const int items_p = kKSteps * per_p, items_q = shared ? 0 : kKSteps * per_q;
+    const double nu = p.freq[f];
+    const double *ant_t = p.ant_uvw + (long long)t * nant * 3;
+    const long long mat_stride_s = (long long)p.ntime * nant * p.nchan * 64;  // bytes between sources
+    const char *e1_tf = reinterpret_cast<const char *>(p.dde1) + ((long long)t * nant * p.nchan + f) * 64;
+    const char *e2_tf = reinterpret_cast<const char *>(p.dde2) + ((long long)t * nant * p.nchan + f) * 64;
+    const long long ant_stride = (long long)p.nchan * 64;
 
-    if (warp >= kConsWarps) {
-        // =============================== PRODUCERS ===============================
-        // The FP64 pipe of every SM sub-partition is kept busy by the consumers' DMMAs (16 cycles
-        // each), and the warp scheduler hands the pipe round in turn: a producer warp gets ONE FP64
-        // instruction in per rotation (~50 cycles with three DMMA warps beside it), whatever its
-        // instruction-level parallelism.  Measured with 12 consumer + 4 producer warps: 182 FP64
-        // instructions per producer warp and stage -> 8000 cycles per stage against 4600 of DMMA,
-        // consumers waiting on "full" 26 % of the time.  What counts is FP64 instructions per
-        // producer WARP: so 8 producer warps (one item per thread and stage at 64 antennas) beside
-        // 8 consumer warps with 5 / 4 tiles each (two DMMA warps per sub-partition still saturate the
-        // pipe), the phasors computed before waiting for the stage's copies, no branches in an item.
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kProdRegs));
-        const int ptid = tid - kConsWarps * 32;
-        // one E matrix serves both operands when E1 is E2 and the panel is on the diagonal
-        const bool shared = p.same_dde && gi0 == gj0 && ni == nj;
-        const int per_p = ni * 16, per_q = nj * 16;  // items of one k-step: 8 antennas x 2 sources per group
-        const int items_p = kKSteps * per_p, items_q = shared ? 0 : kKSteps * per_q;
-        const double nu = p.freq[f];
-        const double *ant_t = p.ant_uvw + (long long)t * nant * 3;
-        const long long mat_stride_s = (long long)p.ntime * nant * p.nchan * 64;  // bytes between sources
-        const char *e1_tf = reinterpret_cast<const char *>(p.dde1) + ((long long)t * nant * p.nchan + f) * 64;
-        const char *e2_tf = reinterpret_cast<const char *>(p.dde2) + ((long long)t * nant * p.nchan + f) * 64;
-        const long long ant_stride = (long long)p.nchan * 64;
-
-        // raw E matrices of stage `sg` -> their final panel rows (16-byte cp.async)
-        auto issue = [&](long long sg) {
-            const int st = (int)(sg % kNS);
-            auto copy_items = [&](int nitems, int per, int g0, const char *src_tf, unsigned panel_off) {
-                const unsigned dst0 = smem_addr(smem + st * stage) + panel_off;
-                for (int idx = ptid; idx < nitems; idx += kNTP) {
-                    const int ks = idx / per, rem = idx - ks * per;
-                    const int al = rem >> 1, sl = rem & 1, a = g0 * 8 + al;
-                    const long long s = sg * kSrcPerStage + 2 * ks + sl;
-                    if (a < nant && s < nsrc) {
-                        const char *src = src_tf + s * mat_stride_s + a * ant_stride;
-                        const unsigned dst = dst0 + ks * kstep_bytes + (unsigned)(2 * al * kRowBytes);
+    // ---- raw E matrices of stage `sg` -> their final panel rows (16-byte cp.async), B beside them
+    auto issue = [&](long long sg) {
+        const int st = (int)(sg % kNS);
+        if (sg >= kNS) mbar_wait(&bars[kNS + st], (unsigned)(((sg - kNS) / kNS) & 1));  // buffer released
+        auto copy_items = [&](int nitems, int per, int g0, const char *src_tf, unsigned panel_off) {
+            const unsigned dst0 = smem_addr(smem + st * stage) + panel_off;
+            for (int idx = tid; idx < nitems; idx += kThreads) {
+                const int ks = idx / per, rem = idx - ks * per;
+                const int al = rem >> 1, sl = rem & 1, a = g0 * 8 + al;
+                const long long s = sg * kSrcPerStage + 2 * ks + sl;
+                if (a < nant && s < nsrc) {
+                    const char *src = src_tf + s * mat_stride_s + a * ant_stride;
+                    const unsigned dst = dst0 + ks * kstep_bytes + (unsigned)(2 * al * kRowBytes);
 #pragma unroll
-                        for (int j = 0; j < 2; ++j)
+                    for (int j = 0; j < 2; ++j)
 #pragma unroll
-                            for (int k = 0; k < 2; ++k)
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
-                                                 dst + j * kRowBytes + chunk_off(2 * sl + k, al)),
-                                             "l"(src + (2 * j + k) * 16));
-                    }
+                        for (int k = 0; k < 2; ++k)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                                             dst + j * kRowBytes + chunk_off(2 * sl + k, al)),
+                                         "l"(src + (2 * j + k) * 16));
                 }
-            };
-            if (shared) {
-                copy_items(items_p, per_p, gj0, e2_tf, p_bytes);
-            } else {
-                copy_items(items_p, per_p, gi0, e1_tf, 0u);
-                copy_items(items_q, per_q, gj0, e2_tf, p_bytes);
             }
-            if (ptid < kSrcPerStage * 4) {
-                const long long s = sg * kSrcPerStage + (ptid >> 2);
-                if (s < nsrc)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
-                                     smem_addr(b_of(st)) + ptid * 16),
-                                 "l"(reinterpret_cast<const char *>(p.bright) + (s * (long long)p.nchan + f) * 64 +
-                                     (ptid & 3) * 16));
-            }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(
-                             smem_addr(&bars[2 * kNS + st]))
-                         : "memory");
         };
-        for (long long sg = 0; sg < kNS - 1 && sg < nstage; ++sg) issue(sg);
+        if (shared) {
+            copy_items(items_p, per_p, gj0, e2_tf, p_bytes);
+        } else {
+            copy_items(items_p, per_p, gi0, e1_tf, 0u);
+            copy_items(items_q, per_q, gj0, e2_tf, p_bytes);
+        }
+        if (tid < kSrcPerStage * 4) {
+            const long long s = sg * kSrcPerStage + (tid >> 2);
+            if (s < nsrc)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr(b_of(st)) + tid * 16),
+                             "l"(reinterpret_cast<const char *>(p.bright) + (s * (long long)p.nchan + f) * 64 +
+                                 (tid & 3) * 16));
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_addr(&bars[2 * kNS + st]))
+                     : "memory");
+    };
 
-        // Item idx of a panel: k-step idx / per, antenna slot (idx % per) / 2, source parity idx % 2.
-        struct Item {
-            Cd k;            // antenna phasor, zero for a dead antenna / source
-            unsigned row;    // byte offset of the item's first row inside its k-step
-            unsigned c0, c1; // its two chunks
-            unsigned boff;   // brightness matrix of its source inside the stage's B block
-            int odd;         // odd antenna slot: rows in the order 1, 0 (bank spread)
-        };
-        auto setup = [&](int idx, int nitems, int per, int g0, long long sg) -> Item {
-            Item it;
-            (void)nitems;
-            const int ks = idx / per, rem = idx - ks * per;
-            const int al = rem >> 1, sl = rem & 1, a = g0 * 8 + al;
-            const long long s = sg * kSrcPerStage + 2 * ks + sl;
-            const bool live = a < nant && s < nsrc;
-            const int ac = min(a, nant - 1);
-            const long long sc = min(s, nsrc - 1);
-            // antenna phasor k_a(s, f) = exp(i psi nu_f), psi = cst (l U_a + m V_a + n W_a): the same
-            // operations as the antenna mode of afr_rime_ws.cu
-            const double psi = __dmul_rn(p.cst, phase_dot(p.lmn[3 * sc], p.lmn[3 * sc + 1], p.lmn[3 * sc + 2],
-                                                          ant_t[3 * ac], ant_t[3 * ac + 1], ant_t[3 * ac + 2], false));
-            const C2<double> kk = cis_fast(__dmul_rn(psi, nu));
-            it.k = {live ? kk.re : 0.0, live ? kk.im : 0.0};
-            it.row = ks * kstep_bytes + (unsigned)(2 * al * kRowBytes);
-            it.c0 = chunk_off(2 * sl, al), it.c1 = chunk_off(2 * sl + 1, al);
-            it.boff = (unsigned)((2 * ks + sl) * 64);
-            it.odd = al & 1;
-            return it;
-        };
-        auto zero_if_dead = [](Cd x, const Item &it) -> Cd {
-            // a dead item never had its rows copied: whatever the stage holds must not reach 0 * x
-            const bool live = it.k.re != 0.0 || it.k.im != 0.0;
-            return {live ? x.re : 0.0, live ? x.im : 0.0};
-        };
-
-        for (long long sg = 0; sg < nstage; ++sg) {
-            const int st = (int)(sg % kNS);
-            unsigned char *sbase = smem + st * stage;
-            const unsigned char *bb = b_of(st);
-            bool waited = false;
-            auto wait_landed = [&]() {
+    // ---- transform of stage `sg`: Q = k E2 (in place), P = k (E1 B).  Item idx of a panel: k-step
+    // idx / per, antenna slot (idx % per) / 2, source parity idx % 2.  The thread <-> item map
+    // rotates with the stage so that every warp carries the same share over three stages.
+    auto transform = [&](long long sg) {
+        const int st = (int)(sg % kNS);
+        unsigned char *sbase = smem + st * stage;
+        const unsigned char *bb = b_of(st);
+        int first = tid + 128 * (int)(sg % 3);
+        if (first >= kThreads) first -= kThreads;
+        bool waited = false;
+        auto do_items = [&](int nitems, int per, int g0, bool is_p) {
+            for (int idx = first; idx < nitems; idx += kThreads) {
+                const int ks = idx / per, rem = idx - ks * per;
+                const int al = rem >> 1, sl = rem & 1, a = g0 * 8 + al;
+                const long long s = sg * kSrcPerStage + 2 * ks + sl;
+                const bool live = a < nant && s < nsrc;
+                const int ac = min(a, nant - 1);
+                const long long sc = min(s, nsrc - 1);
+                // antenna phasor k_a(s, f) = exp(i psi nu_f), psi = cst (l U_a + m V_a + n W_a): the
+                // same operations as the antenna mode of afr_rime_ws.cu -- evaluated BEFORE waiting
+                // for the stage's copies
+                const double psi = __dmul_rn(p.cst, phase_dot(p.lmn[3 * sc], p.lmn[3 * sc + 1], p.lmn[3 * sc + 2],
+                                                              ant_t[3 * ac], ant_t[3 * ac + 1], ant_t[3 * ac + 2], false));
+                const C2<double> kk = cis_fast(__dmul_rn(psi, nu));
+                const Cd k = {kk.re, kk.im};
+                const unsigned row0 = ks * kstep_bytes + (unsigned)(2 * al * kRowBytes);
+                const unsigned c0 = chunk_off(2 * sl, al), c1 = chunk_off(2 * sl + 1, al);
                 if (!waited) {
-                    if (sg >= kNS) mbar_wait(&bars[kNS + st], (unsigned)(((sg - kNS) / kNS) & 1));
                     mbar_wait(&bars[2 * kNS + st], (unsigned)((sg / kNS) & 1));
                     waited = true;
                 }
-            };
-            // ---- P items: P = k (E1 B); shared: also Q = k E in place
-            for (int idx = ptid; idx < items_p; idx += kNTP) {
-                const Item it = setup(idx, items_p, per_p, gi0, sg);
-                wait_landed();
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    const unsigned row = it.row + (unsigned)((jj ^ it.odd) * kRowBytes);
-                    const unsigned char *src = sbase + (shared ? p_bytes : 0u) + row;
-                    Cd x0 = zero_if_dead(lds_c(src + it.c0), it), x1 = zero_if_dead(lds_c(src + it.c1), it);
-                    const unsigned char *bm = bb + it.boff;
-                    const Cd b0 = lds_c(bm), b1 = lds_c(bm + 16), b2 = lds_c(bm + 32), b3 = lds_c(bm + 48);
-                    if (shared) {
-                        x0 = cmul_(it.k, x0), x1 = cmul_(it.k, x1);
-                        sts_c(sbase + p_bytes + row + it.c0, x0);
-                        sts_c(sbase + p_bytes + row + it.c1, x1);
+                    // odd antenna slots start with their second row: bank spread of the stores
+                    const unsigned row = row0 + (unsigned)((jj ^ (al & 1)) * kRowBytes);
+                    Cd x0 = {0.0, 0.0}, x1 = {0.0, 0.0}, m0 = {0.0, 0.0}, m1 = {0.0, 0.0};
+                    if (is_p) {
+                        if (live) {  // a dead antenna / source was never copied: its rows become zero
+                            const unsigned char *src = sbase + (shared ? p_bytes : 0u) + row;
+                            x0 = lds_c(src + c0), x1 = lds_c(src + c1);
+                            const unsigned char *bm = bb + (2 * ks + sl) * 64;
+                            const Cd b0 = lds_c(bm), b1 = lds_c(bm + 16), b2 = lds_c(bm + 32), b3 = lds_c(bm + 48);
+                            if (shared) x0 = cmul_(k, x0), x1 = cmul_(k, x1);
+                            m0 = cmul2_(x0, b0, x1, b2);
+                            m1 = cmul2_(x0, b1, x1, b3);
+                            if (!shared) m0 = cmul_(k, m0), m1 = cmul_(k, m1);
+                        }
+                        if (shared) {
+                            sts_c(sbase + p_bytes + row + c0, x0);
+                            sts_c(sbase + p_bytes + row + c1, x1);
+                        }
+                        sts_c(sbase + row + c0, m0);
+                        sts_c(sbase + row + c1, m1);
+                    } else {
+                        unsigned char *q = sbase + p_bytes + row;
+                        if (live) x0 = cmul_(k, lds_c(q + c0)), x1 = cmul_(k, lds_c(q + c1));
+                        sts_c(q + c0, x0);
+                        sts_c(q + c1, x1);
                     }
-                    Cd m0 = cadd_(cmul_(x0, b0), cmul_(x1, b2));
-                    Cd m1 = cadd_(cmul_(x0, b1), cmul_(x1, b3));
-                    if (!shared) m0 = cmul_(it.k, m0), m1 = cmul_(it.k, m1);
-                    sts_c(sbase + row + it.c0, m0);
-                    sts_c(sbase + row + it.c1, m1);
                 }
             }
-            // ---- Q items (off-diagonal panels, or E1 != E2): Q = k E2 in place
-            for (int idx = ptid; idx < items_q; idx += kNTP) {
-                const Item it = setup(idx, items_q, per_q, gj0, sg);
-                wait_landed();
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    unsigned char *row = sbase + p_bytes + it.row + (unsigned)((jj ^ it.odd) * kRowBytes);
-                    const Cd x0 = cmul_(it.k, zero_if_dead(lds_c(row + it.c0), it));
-                    const Cd x1 = cmul_(it.k, zero_if_dead(lds_c(row + it.c1), it));
-                    sts_c(row + it.c0, x0);
-                    sts_c(row + it.c1, x1);
-                }
-            }
-            wait_landed();
-            mbar_arrive(&bars[st]);  // full: the panels of this stage are ready
-            if (sg + kNS - 1 < nstage) {
-                if (sg >= 1) mbar_wait(&bars[kNS + (int)((sg - 1) % kNS)], (unsigned)(((sg - 1) / kNS) & 1));
-                issue(sg + kNS - 1);
-            }
-        }
-        return;
-    }
+        };
+        do_items(items_p, per_p, gi0, true);
+        if (items_q) do_items(items_q, per_q, gj0, false);
+        __syncwarp();
+        if (p.arrive_all || lane == 0) mbar_arrive(&bars[st]);  // full: this warp's share is in place
+    };
 
-    // ================================= CONSUMERS =================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kConsRegs));
-    // tile `slot * 8 + warp` of the pass: (m0, n0) = first complex row in the P / Q panel, mask =
-    // which of its four 8 x 8 blocks (4 x 4 antennas) hold any baseline
-    // (packed: the 160 accumulator registers leave little room) desc = mask | tile_m << 8 | tile_n << 16
+    // ---- tiles of this warp: tile `slot * 12 + warp` of the pass; desc = mask | tile_m << 8 |
+    // tile_n << 16 (mask: which of the four 8 x 8 blocks = 4 x 4 antennas hold any baseline)
     unsigned desc[kSlots];
 #pragma unroll
     for (int sl = 0; sl < kSlots; ++sl) {
-        const int ti = sl * kConsWarps + warp;
+        const int ti = sl * kWarps + warp;
         desc[sl] = ti < pass.ntiles ? (unsigned)pass.mask[ti] | ((unsigned)pass.tile_m[ti] << 8) |
                                           ((unsigned)pass.tile_n[ti] << 16)
                                     : 0u;
@@ -323,12 +291,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
                 }
     };
 
-    for (long long sg = 0; sg < nstage; ++sg) {
+    auto consume = [&](long long sg) {
         const int st = (int)(sg % kNS);
-        mbar_wait(&bars[st], (unsigned)((sg / kNS) & 1));
+        mbar_wait(&bars[st], (unsigned)((sg / kNS) & 1));  // every warp's share of stage sg is in place
 #pragma unroll
         for (int ks = 0; ks < kKSteps; ++ks) {
-            const unsigned char *pb = p_of(st, ks) + lane_off, *qb = q_of(st, ks) + lane_off;
+            const unsigned char *pb = smem + st * stage + ks * kstep_bytes + lane_off, *qb = pb + p_bytes;
 #pragma unroll
             for (int sl = 0; sl < kSlots; ++sl) {
                 if (mask_of(sl) == 0xFu)  // warp-uniform
@@ -338,7 +306,30 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
             }
         }
         __syncwarp();
-        if (p.arrive_all || lane == 0) mbar_arrive(&bars[kNS + st]);
+        if (p.arrive_all || lane == 0) mbar_arrive(&bars[kNS + st]);  // empty: done with the buffer
+    };
+
+    // ---- pipeline: copies three stages ahead, transform TWO stages ahead, and the three warps of
+    // a sub-partition out of step: warps 0-3 multiply first and transform afterwards, warps 4-11
+    // transform first.  A warp in its multiply phase can keep the DMMA pipe ~93 % busy on its own
+    // (tools/dmma_microbench.cu: 17.3 cycles per DMMA with one warp per sub-partition); what must not
+    // happen is all three transforming at once (measured with everyone in the same order: the pipe
+    // idles during the common transform phase, 62 % DMMA utilisation).  Two stages of slack mean
+    // nobody waits for a neighbour's transform.
+    issue(0);
+    if (nstage > 1) issue(1);
+    if (nstage > 2) issue(2);
+    transform(0);
+    if (nstage > 1) transform(1);
+    for (long long sg = 0; sg < nstage; ++sg) {
+        if (sg + 3 < nstage) issue(sg + 3);
+        if (warp < 4) {
+            consume(sg);
+            if (sg + 2 < nstage) transform(sg + 2);
+        } else {
+            if (sg + 2 < nstage) transform(sg + 2);
+            consume(sg);
+        }
     }
 
     // ---- epilogue: this lane holds V_pq[i][0..1] of every block: p = row / 2, i = row % 2,
@@ -346,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
     const int32_t *map_t = p.rowmap + (long long)t * nant * nant;
 #pragma unroll
     for (int sl = 0; sl < kSlots; ++sl) {
-        const int ti = sl * kConsWarps + warp;
+        const int ti = sl * kWarps + warp;
         if (ti >= pass.ntiles) continue;
         const int row0 = gi0 * 16 + pass.tile_m[ti] * 16, col0 = gj0 * 16 + pass.tile_n[ti] * 16;
 #pragma unroll
@@ -388,7 +379,7 @@ __global__ void baseline_map_kernel(const int32_t *time_index, const int32_t *an
 }  // namespace
 
 size_t dde_mma_smem_bytes(int ni, int nj) {
-    return kNS * kKSteps * ((size_t)(ni + nj) * 16 * kRowBytes + 2 * 64) + 3 * kNS * sizeof(uint64_t);
+    return kNS * ((size_t)kKSteps * (ni + nj) * 16 * kRowBytes + kSrcPerStage * 64) + 3 * kNS * sizeof(uint64_t);
 }
 
 int launch_baseline_map(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2, int64_t nrow,
@@ -455,10 +446,6 @@ int launch_fused_dde_mma(DdeMmaParams p, const std::vector<DdeMmaPass> &passes, 
     for (const auto &q : passes) nmax = std::max(nmax, q.ni + q.nj);
     const size_t smem = dde_mma_smem_bytes(nmax, 0);
     AFR_REQUIRE(p.ntime <= 65535 && passes.size() <= 65535, "afr_predict_fused: grid too large");
-    cudaFuncAttributes attr;
-    AFR_CUDA_OK(cudaFuncGetAttributes(&attr, fused_dde_mma_kernel));
-    AFR_REQUIRE(kThreads * attr.numRegs >= kConsWarps * 32 * kConsRegs + kProdWarps * 32 * kProdRegs,
-                "fused_dde_mma: launch-time register pool too small for setmaxnreg");
     AFR_CUDA_OK(cudaFuncSetAttribute(fused_dde_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)p.nchan, (unsigned)p.ntime, (unsigned)passes.size());
     fused_dde_mma_kernel<<<grid, kThreads, smem, stream>>>(p);
