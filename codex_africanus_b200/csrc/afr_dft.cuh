@@ -82,6 +82,7 @@ struct DdeMmaParams {
     int nchan;
     int same_dde;
     int arrive_all;
+    int ablate;  // diagnostics (AFR_MMA_ABLATE): 1 = skip the transform, 2 = skip the DMMAs
 };
 int launch_baseline_map(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2, int64_t nrow,
                         int64_t ntime, int64_t nant, int32_t *rowmap, uint8_t *used4, int *dup,

@@ -80,17 +80,127 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // bytes, and the transform's 16-byte stores of 4 consecutive antenna slots x 2 sources (row parity
 // alternating with the slot, see the transform loop) fall into 8 distinct bank groups instead of 2.
 __device__ __forceinline__ unsigned chunk_off(int kc, int slot) { return (unsigned)((kc ^ ((slot >> 1) & 1)) * 16); }
+__device__ __forceinline__ int st_of(long long sg) { return (int)(sg % kNS); }
 
-// Schedule.  The first two versions had dedicated producer warps (4, then 8) preparing the panels
-// while consumer warps multiplied; both stopped at 61 % DMMA-pipe utilisation with the consumers
-// waiting on "panel ready" 16-26 % of the time (profiles/ncu_full_fused_dde_mma_r2{a,c}.txt).  Cause:
-// the DMMAs keep the FP64 pipe of every SM sub-partition busy (16 cycles each) and the scheduler
-// hands the pipe round in turn, so a warp issuing scalar FP64 gets ONE instruction in per rotation
-// (~36-50 cycles).  The ~90 FP64 instructions per warp and stage of the phasor + Jones products then
-// take longer than the stage's DMMAs -- a latency problem that extra parallelism inside a producer
-// warp cannot fix.  So there are no producers: every warp alternates between transforming its share
-// of stage s+1 (while its two neighbours on the sub-partition keep the pipe full of DMMAs) and
-// multiplying stage s, five shared-memory stages deep so that warps may drift a whole phase apart.
+// ---- the transform of one "shared panel" item (P = (k E) B, Q = k E) cut into 23 pieces of 2-8
+// FP64 instructions, which the multiply phase issues between its groups of four DMMAs.  ptxas does
+// not weave two independent instruction streams together by itself (measured: the whole transform
+// stayed in front of the 96 DMMAs), and a scalar FP64 instruction only progresses reliably on a
+// sub-partition full of DMMAs when it sits in a DMMA warp's own stream.  Same operations, in the same
+// order, as cis_fast / phase_dot / the plain transform_item.
+struct XformCtx {
+    const double *lmn_s, *uvw_a;  // coordinates of the item's source / antenna (clamped indices)
+    unsigned char *prow;          // first row of the item in the P panel; the Q panel is +p_bytes
+    const unsigned char *bm;      // brightness matrix of the item's source
+    double cst, nu;
+    unsigned p_bytes, c0, c1, rowa, rowb;  // chunk offsets, byte offsets of the two rows (bank-spread order)
+    bool live;
+};
+struct XformState {
+    double l, m, n, u, v, w, t0, t1, ph, kd, r, z, ps, pc, zr, zz;
+    int kint;
+    Cd k, x0, x1, m0;
+};
+template <int I>
+__device__ __forceinline__ void xform_piece(XformState &x, const XformCtx &c) {
+    constexpr double kMagic = 6755399441055744.0;
+    auto row_load = [&](unsigned row) {
+        const unsigned char *q = c.prow + c.p_bytes + row;
+        x.x0 = lds_c(q + c.c0), x.x1 = lds_c(q + c.c1);
+        if (!c.live) x.x0 = {0.0, 0.0}, x.x1 = {0.0, 0.0};
+        x.x0 = cmul_(x.k, x.x0);
+    };
+    auto row_q = [&](unsigned row) {
+        x.x1 = cmul_(x.k, x.x1);
+        unsigned char *q = c.prow + c.p_bytes + row;
+        sts_c(q + c.c0, x.x0), sts_c(q + c.c1, x.x1);
+    };
+    auto row_m0 = [&]() { x.m0 = cmul2_(x.x0, lds_c(c.bm), x.x1, lds_c(c.bm + 32)); };
+    auto row_p = [&](unsigned row) {
+        const Cd m1 = cmul2_(x.x0, lds_c(c.bm + 16), x.x1, lds_c(c.bm + 48));
+        sts_c(c.prow + row + c.c0, x.m0), sts_c(c.prow + row + c.c1, m1);
+    };
+    if constexpr (I == 0) {
+        x.l = c.lmn_s[0], x.m = c.lmn_s[1], x.n = c.lmn_s[2];
+        x.u = c.uvw_a[0], x.v = c.uvw_a[1], x.w = c.uvw_a[2];
+    } else if constexpr (I == 1) {
+        x.t0 = __dmul_rn(x.l, x.u), x.t1 = __dmul_rn(x.m, x.v);
+    } else if constexpr (I == 2) {
+        x.t0 = __dadd_rn(x.t0, x.t1), x.t1 = __dmul_rn(x.n, x.w);
+    } else if constexpr (I == 3) {
+        x.ph = __dmul_rn(c.cst, __dadd_rn(x.t0, x.t1));
+    } else if constexpr (I == 4) {
+        x.ph = __dmul_rn(x.ph, c.nu);
+        x.kd = fma(x.ph, 6.36619772367581382433e-01, kMagic);
+        x.kint = __double2loint(x.kd);
+    } else if constexpr (I == 5) {
+        x.kd -= kMagic;
+        x.t0 = fma(x.kd, 9.5367431640625e-07, kMagic);
+    } else if constexpr (I == 6) {
+        x.t0 = (x.t0 - kMagic) * 1048576.0;  // kh
+        x.t1 = x.kd - x.t0;                  // kl
+    } else if constexpr (I == 7) {
+        x.r = fma(-x.t0, 1.57079632673412561417e+00, x.ph);
+        x.r = fma(-x.t1, 1.57079632673412561417e+00, x.r);
+    } else if constexpr (I == 8) {
+        x.r = fma(-x.kd, 6.07710050630396597660e-11, x.r);
+        x.r = fma(-x.kd, 2.02226624879595063154e-21, x.r);
+    } else if constexpr (I == 9) {
+        x.z = x.r * x.r;
+        x.ps = fma(x.z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+        x.pc = fma(x.z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    } else if constexpr (I == 10) {
+        x.ps = fma(x.z, x.ps, 2.75573137070700676789e-06);
+        x.pc = fma(x.z, x.pc, -2.75573143513906633035e-07);
+    } else if constexpr (I == 11) {
+        x.ps = fma(x.z, x.ps, -1.98412698298579493134e-04);
+        x.pc = fma(x.z, x.pc, 2.48015872894767294178e-05);
+    } else if constexpr (I == 12) {
+        x.ps = fma(x.z, x.ps, 8.33333333332248946124e-03);
+        x.pc = fma(x.z, x.pc, -1.38888888888741095749e-03);
+    } else if constexpr (I == 13) {
+        x.ps = fma(x.z, x.ps, -1.66666666666666324348e-01);
+        x.pc = fma(x.z, x.pc, 4.16666666666666019037e-02);
+        x.zr = x.z * x.r, x.zz = x.z * x.z;
+    } else if constexpr (I == 14) {
+        const double sn = fma(x.zr, x.ps, x.r);
+        const double cs = fma(x.zz, x.pc, fma(-0.5, x.z, 1.0));
+        const int k = x.kint;
+        const double a = (k & 1) ? cs : sn, b = (k & 1) ? sn : cs;
+        x.k.im = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));
+        x.k.re = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
+        if (!c.live) x.k = {0.0, 0.0};  // a dead antenna / source: its rows become zero
+    } else if constexpr (I == 15) {
+        row_load(c.rowa);
+    } else if constexpr (I == 16) {
+        row_q(c.rowa);
+    } else if constexpr (I == 17) {
+        row_m0();
+    } else if constexpr (I == 18) {
+        row_p(c.rowa);
+    } else if constexpr (I == 19) {
+        row_load(c.rowb);
+    } else if constexpr (I == 20) {
+        row_q(c.rowb);
+    } else if constexpr (I == 21) {
+        row_m0();
+    } else if constexpr (I == 22) {
+        row_p(c.rowb);
+    }
+}
+constexpr int kXformPieces = 23;
+
+// Schedule.  Measured facts behind it (tools/dmma_mix_microbench.cu, profiles/dmma_mix_microbench_r2.txt):
+//   * two or more warps issuing DMMAs on an SM sub-partition keep its FP64 pipe 99.7 % busy -- and
+//     STARVE any other warp's scalar FP64 instructions (58-700 DFMAs got through in 5e5 cycles);
+//   * one DMMA warp alone reaches 81-84 % (19-20 cycles per DMMA);
+//   * scalar FP64 instructions INSIDE a DMMA warp's own instruction stream cost 3-4 pipe cycles each.
+// The first versions had dedicated producer warps (4, then 8) preparing the panels, then symmetric
+// warps alternating whole transform / multiply phases: all stopped at 60-62 % DMMA utilisation
+// because the ~90 scalar FP64 instructions per item (phasor range reduction and polynomials, k E,
+// (k E) B) only progressed while the DMMA warps were idle.  Hence: no producers, and every warp
+// carries its share of the transform of stage s+2 IN ITS OWN STREAM, interleaved with the DMMAs of
+// stage s (in-order issue guarantees the scalar work progresses; the DMMAs hide its latency).
 __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMmaParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -118,9 +228,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
     const long long nsrc = p.nsrc;
     const long long nstage = (nsrc + kSrcPerStage - 1) / kSrcPerStage;
     // one E matrix serves both operands when E1 is E2 and the panel is on the diagonal
-    const bool shared = p.same_dde && gi0 == gj0 && ni == nj;
+    const bool shared_rt = p.same_dde && gi0 == gj0 && ni == nj;
+    const bool shared = shared_rt;
     const int per_p = ni * 16, per_q = nj * 16;  // items of one k-step: 8 antennas x 2 sources per group
     const int items_p = kKSteps * per_p, items_q = shared ? 0 : kKSteps * per_q;
+    const int items = items_p + items_q;
     const double nu = p.freq[f];
     const double *ant_t = p.ant_uvw + (long long)t * nant * 3;
     const long long mat_stride_s = (long long)p.ntime * nant * p.nchan * 64;  // bytes between sources
@@ -145,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
                         for (int k = 0; k < 2; ++k)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                            asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;\n" ::"r"(
                                              dst + j * kRowBytes + chunk_off(2 * sl + k, al)),
                                          "l"(src + (2 * j + k) * 16));
                 }
@@ -160,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
         if (tid < kSrcPerStage * 4) {
             const long long s = sg * kSrcPerStage + (tid >> 2);
             if (s < nsrc)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr(b_of(st)) + tid * 16),
+                asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;\n" ::"r"(smem_addr(b_of(st)) + tid * 16),
                              "l"(reinterpret_cast<const char *>(p.bright) + (s * (long long)p.nchan + f) * 64 +
                                  (tid & 3) * 16));
         }
@@ -168,83 +280,93 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
                      : "memory");
     };
 
-    // ---- transform of stage `sg`: Q = k E2 (in place), P = k (E1 B).  Item idx of a panel: k-step
-    // idx / per, antenna slot (idx % per) / 2, source parity idx % 2.  The thread <-> item map
-    // rotates with the stage so that every warp carries the same share over three stages.
-    auto transform = [&](long long sg) {
+    // ---- one item of the transform of stage `sg`: Q = k E2 (in place) or P = k (E1 B).  Item idx:
+    // [0, items_p) the P panel, then the Q panel; inside a panel: k-step idx / per, antenna slot
+    // (idx % per) / 2, source parity idx % 2.  Branch-free (dead antennas / sources are masked), so
+    // that the compiler can weave it into the DMMA stream of the multiply phase.
+    auto transform_item = [&](auto fast_tag, long long sg, int idx, bool store) {
+        // FAST: the panel is "shared" (every item is a P item whose k E also is the Q panel) -- known at
+        // compile time, so the item is one basic block
+        constexpr bool FAST = decltype(fast_tag)::value;
         const int st = (int)(sg % kNS);
         unsigned char *sbase = smem + st * stage;
-        const unsigned char *bb = b_of(st);
-        int first = tid + 128 * (int)(sg % 3);
-        if (first >= kThreads) first -= kThreads;
-        bool waited = false;
-        auto do_items = [&](int nitems, int per, int g0, bool is_p) {
-            for (int idx = first; idx < nitems; idx += kThreads) {
-                const int ks = idx / per, rem = idx - ks * per;
-                const int al = rem >> 1, sl = rem & 1, a = g0 * 8 + al;
-                const long long s = sg * kSrcPerStage + 2 * ks + sl;
-                const bool live = a < nant && s < nsrc;
-                const int ac = min(a, nant - 1);
-                const long long sc = min(s, nsrc - 1);
-                // antenna phasor k_a(s, f) = exp(i psi nu_f), psi = cst (l U_a + m V_a + n W_a): the
-                // same operations as the antenna mode of afr_rime_ws.cu -- evaluated BEFORE waiting
-                // for the stage's copies
-                const double psi = __dmul_rn(p.cst, phase_dot(p.lmn[3 * sc], p.lmn[3 * sc + 1], p.lmn[3 * sc + 2],
-                                                              ant_t[3 * ac], ant_t[3 * ac + 1], ant_t[3 * ac + 2], false));
-                const C2<double> kk = cis_fast(__dmul_rn(psi, nu));
-                const Cd k = {kk.re, kk.im};
-                const unsigned row0 = ks * kstep_bytes + (unsigned)(2 * al * kRowBytes);
-                const unsigned c0 = chunk_off(2 * sl, al), c1 = chunk_off(2 * sl + 1, al);
-                if (!waited) {
-                    mbar_wait(&bars[2 * kNS + st], (unsigned)((sg / kNS) & 1));
-                    waited = true;
-                }
+        const bool is_p = FAST || idx < items_p;
+        const bool shared = FAST || shared_rt;
+        const int li = is_p ? idx : idx - items_p, per = is_p ? per_p : per_q, g0 = is_p ? gi0 : gj0;
+        const int ks = li / per, rem = li - ks * per;
+        const int al = rem >> 1, sl = rem & 1, a = g0 * 8 + al;
+        const long long s = sg * kSrcPerStage + 2 * ks + sl;
+        const bool live = a < nant && s < nsrc;
+        const int ac = min(a, nant - 1);
+        const long long sc = min(s, nsrc - 1);
+        // antenna phasor k_a(s, f) = exp(i psi nu_f), psi = cst (l U_a + m V_a + n W_a): the same
+        // operations as the antenna mode of afr_rime_ws.cu
+        const double psi = __dmul_rn(p.cst, phase_dot(p.lmn[3 * sc], p.lmn[3 * sc + 1], p.lmn[3 * sc + 2],
+                                                      ant_t[3 * ac], ant_t[3 * ac + 1], ant_t[3 * ac + 2], false));
+        const C2<double> kk = cis_fast(__dmul_rn(psi, nu));
+        const Cd k = {live ? kk.re : 0.0, live ? kk.im : 0.0};  // a dead item's rows become zero
+        const unsigned row0 = ks * kstep_bytes + (unsigned)(2 * al * kRowBytes);
+        const unsigned c0 = chunk_off(2 * sl, al), c1 = chunk_off(2 * sl + 1, al);
+        const unsigned char *bm = b_of(st) + (2 * ks + sl) * 64;
+        // in-place panel of the raw matrix: Q (shared or a Q item) or P
+        unsigned char *raw = sbase + ((shared || !is_p) ? p_bytes : 0u);
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    // odd antenna slots start with their second row: bank spread of the stores
-                    const unsigned row = row0 + (unsigned)((jj ^ (al & 1)) * kRowBytes);
-                    Cd x0 = {0.0, 0.0}, x1 = {0.0, 0.0}, m0 = {0.0, 0.0}, m1 = {0.0, 0.0};
-                    if (is_p) {
-                        if (live) {  // a dead antenna / source was never copied: its rows become zero
-                            const unsigned char *src = sbase + (shared ? p_bytes : 0u) + row;
-                            x0 = lds_c(src + c0), x1 = lds_c(src + c1);
-                            const unsigned char *bm = bb + (2 * ks + sl) * 64;
-                            const Cd b0 = lds_c(bm), b1 = lds_c(bm + 16), b2 = lds_c(bm + 32), b3 = lds_c(bm + 48);
-                            if (shared) x0 = cmul_(k, x0), x1 = cmul_(k, x1);
-                            m0 = cmul2_(x0, b0, x1, b2);
-                            m1 = cmul2_(x0, b1, x1, b3);
-                            if (!shared) m0 = cmul_(k, m0), m1 = cmul_(k, m1);
-                        }
-                        if (shared) {
-                            sts_c(sbase + p_bytes + row + c0, x0);
-                            sts_c(sbase + p_bytes + row + c1, x1);
-                        }
-                        sts_c(sbase + row + c0, m0);
-                        sts_c(sbase + row + c1, m1);
-                    } else {
-                        unsigned char *q = sbase + p_bytes + row;
-                        if (live) x0 = cmul_(k, lds_c(q + c0)), x1 = cmul_(k, lds_c(q + c1));
-                        sts_c(q + c0, x0);
-                        sts_c(q + c1, x1);
-                    }
+        for (int jj = 0; jj < 2; ++jj) {
+            // odd antenna slots start with their second row: bank spread of the stores
+            const unsigned row = row0 + (unsigned)((jj ^ (al & 1)) * kRowBytes);
+            Cd x0 = lds_c(raw + row + c0), x1 = lds_c(raw + row + c1);
+            if (!live) x0 = {0.0, 0.0}, x1 = {0.0, 0.0};  // never copied: whatever the buffer holds
+            if (is_p) {
+                const Cd b0 = lds_c(bm), b1 = lds_c(bm + 16), b2 = lds_c(bm + 32), b3 = lds_c(bm + 48);
+                Cd m0, m1;
+                if (shared) {
+                    x0 = cmul_(k, x0), x1 = cmul_(k, x1);
+                    if (store) sts_c(raw + row + c0, x0), sts_c(raw + row + c1, x1);
+                    m0 = cmul2_(x0, b0, x1, b2);
+                    m1 = cmul2_(x0, b1, x1, b3);
+                } else {
+                    m0 = cmul_(k, cmul2_(x0, b0, x1, b2));
+                    m1 = cmul_(k, cmul2_(x0, b1, x1, b3));
                 }
+                if (store) sts_c(sbase + row + c0, m0), sts_c(sbase + row + c1, m1);
+            } else {
+                x0 = cmul_(k, x0), x1 = cmul_(k, x1);
+                if (store) sts_c(raw + row + c0, x0), sts_c(raw + row + c1, x1);
             }
-        };
-        do_items(items_p, per_p, gi0, true);
-        if (items_q) do_items(items_q, per_q, gj0, false);
+        }
+    };
+    // The thread <-> item map rotates with the stage, so that with 256 items (64 antennas) every
+    // warp carries an item in two stages out of three and every sub-partition two items per stage.
+    auto first_item = [&](long long sg) {
+        int first = tid + 128 * (int)(sg % 3);
+        return first >= kThreads ? first - kThreads : first;
+    };
+    auto wait_landed = [&](long long sg) {
+        mbar_wait(&bars[2 * kNS + (int)(sg % kNS)], (unsigned)((sg / kNS) & 1));
+    };
+    auto publish = [&](long long sg) {  // full: this warp's share of stage sg is in place
         __syncwarp();
-        if (p.arrive_all || lane == 0) mbar_arrive(&bars[st]);  // full: this warp's share is in place
+        if (p.arrive_all || lane == 0) mbar_arrive(&bars[(int)(sg % kNS)]);
+    };
+    auto transform_all = [&](long long sg) {  // prologue only
+        wait_landed(sg);
+        for (int idx = first_item(sg); idx < items; idx += kThreads) transform_item(std::false_type{}, sg, idx, true);
+        publish(sg);
     };
 
-    // ---- tiles of this warp: tile `slot * 12 + warp` of the pass; desc = mask | tile_m << 8 |
-    // tile_n << 16 (mask: which of the four 8 x 8 blocks = 4 x 4 antennas hold any baseline)
+    // ---- tiles of this warp: tile `slot * 12 + warp` of the pass, (m0, n0) = first complex row in
+    // the P / Q panel.  A tile is multiplied whole (all four 8 x 8 blocks) so that the multiply phase
+    // is one basic block; `mask` (which 4 x 4-antenna blocks hold baselines) only gates the epilogue.
     unsigned desc[kSlots];
+    int my_tiles = 0;
 #pragma unroll
     for (int sl = 0; sl < kSlots; ++sl) {
         const int ti = sl * kWarps + warp;
-        desc[sl] = ti < pass.ntiles ? (unsigned)pass.mask[ti] | ((unsigned)pass.tile_m[ti] << 8) |
-                                          ((unsigned)pass.tile_n[ti] << 16)
-                                    : 0u;
+        desc[sl] = 0u;
+        if (ti < pass.ntiles) {
+            desc[sl] = (unsigned)pass.mask[ti] | ((unsigned)pass.tile_m[ti] << 8) | ((unsigned)pass.tile_n[ti] << 16);
+            my_tiles = sl + 1;
+        }
     }
     auto mask_of = [&](int sl) { return desc[sl] & 0xFu; };
     auto moff_of = [&](int sl) { return ((desc[sl] >> 8) & 0xFFu) * (16u * kRowBytes); };
@@ -262,9 +384,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
             for (int nn = 0; nn < 2; ++nn)
                 cre[sl][mi][nn][0] = cre[sl][mi][nn][1] = cim[sl][mi][nn][0] = cim[sl][mi][nn][1] = 0.0;
 
-    // one tile, one k-step: 4 LDS.128, 16 DMMA (FULL: all four blocks, no predicates)
-    auto tile_step = [&](auto full_tag, int sl, const unsigned char *pb, const unsigned char *qb) {
-        constexpr bool FULL = decltype(full_tag)::value;
+    // one tile, one k-step: 4 LDS.128, 16 DMMA
+    auto tile_step = [&](int sl, const unsigned char *pb, const unsigned char *qb) {
         double2 a[2], b[2];
         const unsigned char *pa = pb + moff_of(sl), *qa = qb + noff_of(sl);
         a[0] = *reinterpret_cast<const double2 *>(pa);
@@ -276,60 +397,146 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int nn = 0; nn < 2; ++nn)
-                if (FULL || (mask_of(sl) & (1u << (2 * mi + nn)))) {
-                    dmma(cre[sl][mi][nn], a[mi].x, b[nn].x);
-                    dmma(cim[sl][mi][nn], a[mi].y, b[nn].x);
-                }
+            for (int nn = 0; nn < 2; ++nn) {
+                dmma(cre[sl][mi][nn], a[mi].x, b[nn].x);
+                dmma(cim[sl][mi][nn], a[mi].y, b[nn].x);
+            }
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int nn = 0; nn < 2; ++nn)
-                if (FULL || (mask_of(sl) & (1u << (2 * mi + nn)))) {
-                    dmma(cre[sl][mi][nn], a[mi].y, b[nn].y);
-                    dmma(cim[sl][mi][nn], na[mi], b[nn].y);
-                }
+            for (int nn = 0; nn < 2; ++nn) {
+                dmma(cre[sl][mi][nn], a[mi].y, b[nn].y);
+                dmma(cim[sl][mi][nn], na[mi], b[nn].y);
+            }
     };
 
-    auto consume = [&](long long sg) {
+    // Multiply stage sg (NT tiles of this warp) with the transform of this thread's first item of
+    // stage sg + 2 placed in the middle of the same basic block (HAS: the warp carries items).
+    auto body = [&](auto nt_tag, auto has_tag, long long sg) {
+        constexpr int NT = decltype(nt_tag)::value;
+        constexpr int HAS = decltype(has_tag)::value;  // 0: no item, 1: generic item, 2: shared-panel item
         const int st = (int)(sg % kNS);
-        mbar_wait(&bars[st], (unsigned)((sg / kNS) & 1));  // every warp's share of stage sg is in place
+        const unsigned char *pb0 = smem + st * stage + lane_off;
+        const int idx = first_item(sg + 2);
 #pragma unroll
         for (int ks = 0; ks < kKSteps; ++ks) {
-            const unsigned char *pb = smem + st * stage + ks * kstep_bytes + lane_off, *qb = pb + p_bytes;
+            const unsigned char *pb = pb0 + ks * kstep_bytes, *qb = pb + p_bytes;
 #pragma unroll
-            for (int sl = 0; sl < kSlots; ++sl) {
-                if (mask_of(sl) == 0xFu)  // warp-uniform
-                    tile_step(std::true_type{}, sl, pb, qb);
-                else if (mask_of(sl) != 0u)
-                    tile_step(std::false_type{}, sl, pb, qb);
+            for (int sl = 0; sl < NT; ++sl) {
+                if (HAS == 2 && ks == 0 && sl == 0) transform_item(std::true_type{}, sg + 2, idx < items ? idx : 0, idx < items);
+                tile_step(sl, pb, qb);
+                if (HAS == 1 && ks == 0 && sl == 0) transform_item(std::false_type{}, sg + 2, idx < items ? idx : 0, idx < items);
             }
         }
-        __syncwarp();
-        if (p.arrive_all || lane == 0) mbar_arrive(&bars[kNS + st]);  // empty: done with the buffer
     };
 
-    // ---- pipeline: copies three stages ahead, transform TWO stages ahead, and the three warps of
-    // a sub-partition out of step: warps 0-3 multiply first and transform afterwards, warps 4-11
-    // transform first.  A warp in its multiply phase can keep the DMMA pipe ~93 % busy on its own
-    // (tools/dmma_microbench.cu: 17.3 cycles per DMMA with one warp per sub-partition); what must not
-    // happen is all three transforming at once (measured with everyone in the same order: the pipe
-    // idles during the common transform phase, 62 % DMMA utilisation).  Two stages of slack mean
-    // nobody waits for a neighbour's transform.
-    issue(0);
-    if (nstage > 1) issue(1);
-    if (nstage > 2) issue(2);
-    transform(0);
-    if (nstage > 1) transform(1);
+    // FAST multiply phase: the warp's NT tiles of stage sg as groups of four DMMAs with the pieces
+    // of this thread's shared-panel item of stage sg + 2 in between (one basic block).
+    auto body_fast = [&](auto nt_tag, auto abl_tag, long long sg) {
+        constexpr int NT = decltype(nt_tag)::value;
+        constexpr int ABL = decltype(abl_tag)::value;  // diagnostics: 1 = no transform, 2 = no DMMA
+        constexpr int G = NT * kKSteps * 4;  // groups
+        const unsigned char *pb0 = smem + st_of(sg) * stage + lane_off;
+        const long long sg2 = sg + 2;
+        const int idx = first_item(sg2);  // < items: the panel's item count is a multiple of 32
+        const int ks2 = idx / per_p, rem = idx - ks2 * per_p;
+        const int al = rem >> 1, sl2 = rem & 1, a = gi0 * 8 + al;
+        const long long s = sg2 * kSrcPerStage + 2 * ks2 + sl2;
+        XformCtx xc;
+        xc.live = a < nant && s < nsrc;
+        xc.lmn_s = p.lmn + 3 * min(s, nsrc - 1);
+        xc.uvw_a = ant_t + 3 * min(a, nant - 1);
+        xc.prow = smem + st_of(sg2) * stage + ks2 * kstep_bytes + (unsigned)(2 * al * kRowBytes);
+        xc.bm = b_of(st_of(sg2)) + (2 * ks2 + sl2) * 64;
+        xc.cst = p.cst, xc.nu = nu, xc.p_bytes = p_bytes;
+        xc.c0 = chunk_off(2 * sl2, al), xc.c1 = chunk_off(2 * sl2 + 1, al);
+        xc.rowa = (unsigned)((al & 1) * kRowBytes), xc.rowb = (unsigned)(((al & 1) ^ 1) * kRowBytes);
+        XformState xs;
+        double2 fa[2], fb[2];
+        double na[2];
+        auto pieces = [&](auto self, auto lo_tag, auto hi_tag) {
+            constexpr int LO = decltype(lo_tag)::value, HI = decltype(hi_tag)::value;
+            if constexpr (LO < HI) {
+                xform_piece<LO>(xs, xc);
+                self(self, std::integral_constant<int, LO + 1>{}, hi_tag);
+            }
+        };
+        auto group = [&](auto self, auto g_tag) {
+            constexpr int g = decltype(g_tag)::value;
+            constexpr int ks = g / (NT * 4), sl = (g / 4) % NT, q = g % 4, mi = q & 1;
+            if constexpr (q == 0) {
+                const unsigned char *pa = pb0 + ks * kstep_bytes + moff_of(sl);
+                const unsigned char *qa = pb0 + ks * kstep_bytes + p_bytes + noff_of(sl);
+                fa[0] = *reinterpret_cast<const double2 *>(pa);
+                fa[1] = *reinterpret_cast<const double2 *>(pa + 8 * kRowBytes);
+                fb[0] = *reinterpret_cast<const double2 *>(qa);
+                fb[1] = *reinterpret_cast<const double2 *>(qa + 8 * kRowBytes);
+                na[0] = neg_(fa[0].x), na[1] = neg_(fa[1].x);
+            }
+            if constexpr (ABL >= 2) {
+                cre[sl][mi][0][0] += fa[mi].x * fb[0].x + na[mi];
+            } else if constexpr (q < 2) {
+                dmma(cre[sl][mi][0], fa[mi].x, fb[0].x);
+                dmma(cim[sl][mi][0], fa[mi].y, fb[0].x);
+                dmma(cre[sl][mi][1], fa[mi].x, fb[1].x);
+                dmma(cim[sl][mi][1], fa[mi].y, fb[1].x);
+            } else {
+                dmma(cre[sl][mi][0], fa[mi].y, fb[0].y);
+                dmma(cim[sl][mi][0], na[mi], fb[0].y);
+                dmma(cre[sl][mi][1], fa[mi].y, fb[1].y);
+                dmma(cim[sl][mi][1], na[mi], fb[1].y);
+            }
+            if constexpr (ABL != 1 && ABL != 3)
+                pieces(pieces, std::integral_constant<int, g * kXformPieces / G>{},
+                       std::integral_constant<int, (g + 1) * kXformPieces / G>{});
+            if constexpr (g + 1 < G) self(self, std::integral_constant<int, g + 1>{});
+        };
+        group(group, std::integral_constant<int, 0>{});
+    };
+
+    // ---- pipeline: copies three stages ahead, transform two stages ahead
+    for (int i = 0; i < 3; ++i)
+        if (i < nstage) issue(i);
+    transform_all(0);
+    if (nstage > 1) transform_all(1);
     for (long long sg = 0; sg < nstage; ++sg) {
         if (sg + 3 < nstage) issue(sg + 3);
-        if (warp < 4) {
-            consume(sg);
-            if (sg + 2 < nstage) transform(sg + 2);
-        } else {
-            if (sg + 2 < nstage) transform(sg + 2);
-            consume(sg);
+        const bool ahead = sg + 2 < nstage;
+        // warp-uniform: does this warp carry items of stage sg + 2?  (idx < items for its lane 0 ..
+        // lane 31 range: the map is contiguous in tid, so test the warp's first lane)
+        const int w0 = first_item(sg + 2) - lane;
+        const bool has = ahead && w0 < items;
+        mbar_wait(&bars[st_of(sg)], (unsigned)((sg / kNS) & 1));  // every warp's share of stage sg is in place
+        if (has) wait_landed(sg + 2);
+#define AFR_BODY(NT)                                                                       \
+    if (has && shared && p.ablate == 1)                                                    \
+        body_fast(std::integral_constant<int, NT>{}, std::integral_constant<int, 1>{}, sg); \
+    else if (has && shared && p.ablate == 2)                                               \
+        body_fast(std::integral_constant<int, NT>{}, std::integral_constant<int, 2>{}, sg); \
+    else if (has && shared && p.ablate == 3)                                               \
+        body_fast(std::integral_constant<int, NT>{}, std::integral_constant<int, 3>{}, sg); \
+    else if (has && shared)                                                                \
+        body_fast(std::integral_constant<int, NT>{}, std::integral_constant<int, 0>{}, sg); \
+    else if (has)                                                                          \
+        body(std::integral_constant<int, NT>{}, std::integral_constant<int, 1>{}, sg);     \
+    else                                                                                   \
+        body(std::integral_constant<int, NT>{}, std::integral_constant<int, 0>{}, sg)
+        if (my_tiles == 3) {
+            AFR_BODY(3);
+        } else if (my_tiles == 2) {
+            AFR_BODY(2);
+        } else if (my_tiles == 1) {
+            AFR_BODY(1);
         }
+#undef AFR_BODY
+        if (has) {
+            // further items of a large panel, and every item of a warp without tiles (small arrays)
+            for (int idx = first_item(sg + 2) + (my_tiles ? kThreads : 0); idx < items; idx += kThreads)
+                transform_item(std::false_type{}, sg + 2, idx, true);
+        }
+        __syncwarp();
+        if (p.arrive_all || lane == 0) mbar_arrive(&bars[kNS + st_of(sg)]);  // empty: done with the buffer
+        if (ahead) publish(sg + 2);
     }
 
     // ---- epilogue: this lane holds V_pq[i][0..1] of every block: p = row / 2, i = row % 2,
@@ -442,6 +649,7 @@ int launch_fused_dde_mma(DdeMmaParams p, const std::vector<DdeMmaPass> &passes, 
                                 cudaMemcpyHostToDevice, stream));
     p.passes = (const DdeMmaPass *)dpass.ptr;
     p.arrive_all = (getenv("AFR_SANITIZE") && atoi(getenv("AFR_SANITIZE")) != 0) ? 1 : 0;
+    p.ablate = getenv("AFR_MMA_ABLATE") ? atoi(getenv("AFR_MMA_ABLATE")) : 0;  // diagnostics only: wrong results
     int nmax = 0;
     for (const auto &q : passes) nmax = std::max(nmax, q.ni + q.nj);
     const size_t smem = dde_mma_smem_bytes(nmax, 0);

@@ -5,7 +5,7 @@ import synth
 from codex_africanus_b200 import rime
 rng = np.random.default_rng(3); dev = torch.device("cuda:0")
 T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-na, ntime, nchan, nsrc = 64, 1, 1024, 64
+na, ntime, nchan, nsrc = 64, 1, int(sys.argv[1]) if len(sys.argv) > 1 else 1024, int(sys.argv[2]) if len(sys.argv) > 2 else 64
 uvw, tidx, a1, a2 = synth.uvw_tracks(na, ntime, rng, ntime_total=100)
 freq = synth.frequencies(nchan); lm = synth.sky_lm(nsrc, rng)
 bright = T(synth.brightness_2x2(nsrc, nchan, rng, freq))
