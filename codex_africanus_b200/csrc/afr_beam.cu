@@ -8,6 +8,8 @@
 // coordinate arithmetic uses explicitly rounded operations in the reference's order so the
 // grid cell chosen by floor() is the reference's.
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 #include "afr_common.cuh"
 
@@ -66,6 +68,7 @@ struct BeamParams {
     double lower_l, lower_m, lscale, mscale, lmaxf, mmaxf;
     long long lw, mh, nud, nsrc, ntime, nant, nchan;
     int ncorr, coff;
+    const uint8_t *row_flag;  // (ntime,nant) 1: pointing errors / antenna scaling constant along chan
 };
 
 // |re + i im| as the reference's np.abs (hypot).  hypot's overflow/underflow guards cost
@@ -121,14 +124,34 @@ struct Vec2<float> {
 // rotation L[t,a] -- einsum("stafij,tajk->stafik", beam_dde, feed_rot) of
 // africanus/rime/examples/predict.py:469-472 -- before the one store, so the rotated DDE costs
 // no extra pass over the (source,time,ant,chan,2,2) array.
-template <typename T, int NC, bool ROT = false>
-__global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) {
+// grid coordinates of one output element (fast_beam_cubes.py:130-151), explicitly rounded
+// operations in the reference's order
+__device__ __forceinline__ void beam_coords(const BeamParams &p, long long s, long long t, long long a,
+                                            long long f, double sin_pa, double cos_pa, double &vl,
+                                            double &vm) {
+    const double l = p.lm[2 * s], m = p.lm[2 * s + 1];
+    const double fscale = p.fd[3 * f];
+    const double sl = __dmul_rn(l, fscale), sm = __dmul_rn(m, fscale);
+    const double2 pe = *reinterpret_cast<const double2 *>(p.perr + ((t * p.nant + a) * p.nchan + f) * 2);
+    const double tl = __dadd_rn(sl, pe.x), tm = __dadd_rn(sm, pe.y);
+    vl = __dsub_rn(__dmul_rn(tl, cos_pa), __dmul_rn(tm, sin_pa));
+    vm = __dadd_rn(__dmul_rn(tl, sin_pa), __dmul_rn(tm, cos_pa));
+    const double2 as = *reinterpret_cast<const double2 *>(p.ascale + (a * p.nchan + f) * 2);
+    vl = __dmul_rn(vl, as.x);
+    vm = __dmul_rn(vm, as.y);
+    vl = __dmul_rn(p.lscale, __dsub_rn(vl, p.lower_l));
+    vm = __dmul_rn(p.mscale, __dsub_rn(vm, p.lower_m));
+    vl = fmax(0.0, fmin(vl, p.lmaxf));
+    vm = fmax(0.0, fmin(vm, p.mmaxf));
+}
+
+// one output element, all NC correlations of this launch: 8 corner gathers per element
+template <typename T, int NC, bool ROT>
+__device__ __forceinline__ void beam_element(const BeamParams &p, long long i, T *stage = nullptr) {
     const T *beam = (const T *)p.beam;
     const T *babs = (const T *)p.babs;
     T *out = (T *)p.out;
-    const long long total = p.nsrc * p.ntime * p.nant * p.nchan;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
+    {
         const long long f = i % p.nchan;
         long long rest = i / p.nchan;
         const long long a = rest % p.nant;
@@ -137,24 +160,11 @@ __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) 
         const long long s = rest / p.ntime;
 
         const double sin_pa = p.pa_sc[2 * (t * p.nant + a)], cos_pa = p.pa_sc[2 * (t * p.nant + a) + 1];
-        const double l = p.lm[2 * s], m = p.lm[2 * s + 1];
-        const double fscale = p.fd[3 * f], nudw = p.fd[3 * f + 1];
+        const double nudw = p.fd[3 * f + 1];
         const double inv_nud = __dsub_rn(1.0, nudw);
         const long long gc0 = (long long)(int)p.fd[3 * f + 2], gc1 = gc0 + 1;
-
-        // fast_beam_cubes.py:130-151
-        const double sl = __dmul_rn(l, fscale), sm = __dmul_rn(m, fscale);
-        const double2 pe = *reinterpret_cast<const double2 *>(p.perr + ((t * p.nant + a) * p.nchan + f) * 2);
-        const double tl = __dadd_rn(sl, pe.x), tm = __dadd_rn(sm, pe.y);
-        double vl = __dsub_rn(__dmul_rn(tl, cos_pa), __dmul_rn(tm, sin_pa));
-        double vm = __dadd_rn(__dmul_rn(tl, sin_pa), __dmul_rn(tm, cos_pa));
-        const double2 as = *reinterpret_cast<const double2 *>(p.ascale + (a * p.nchan + f) * 2);
-        vl = __dmul_rn(vl, as.x);
-        vm = __dmul_rn(vm, as.y);
-        vl = __dmul_rn(p.lscale, __dsub_rn(vl, p.lower_l));
-        vm = __dmul_rn(p.mscale, __dsub_rn(vm, p.lower_m));
-        vl = fmax(0.0, fmin(vl, p.lmaxf));
-        vm = fmax(0.0, fmin(vm, p.mmaxf));
+        double vl, vm;
+        beam_coords(p, s, t, a, f, sin_pa, cos_pa, vl, vm);
         // :154-163
         const long long gl0 = (long long)(int)floor(vl), gm0 = (long long)(int)floor(vm);
         const long long gl1 = min(gl0 + 1, p.lw - 1), gm1 = min(gm0 + 1, p.mh - 1);
@@ -199,7 +209,8 @@ __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) 
                 csi[c] = (T)__dadd_rn((double)csi[c], __dmul_rn(wt, (double)bi));
             }
         }
-        T *o = out + (i * p.ncorr + p.coff) * 2;
+        // `stage`: the NC values of this element go there instead of to the output array
+        T *o = stage ? stage : out + (i * p.ncorr + p.coff) * 2;
         T er[NC], ei[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {  // :227-238
@@ -208,10 +219,11 @@ __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) 
             er[c] = csr[c] * k;
             ei[c] = csi[c] * k;
         }
-        if (ROT && NC == 4) {
+        if (ROT && NC >= 2) {
+            // the NC / 2 rows of the 2x2 Jones held by this launch (coff = 0: rows 0, 1 or row 0; 2: row 1)
             const T *L = (const T *)p.feed + (t * p.nant + a) * 8;
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
+            for (int r = 0; r < NC / 2; ++r)
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {  // out[r,k] = E[r,0] L[0,k] + E[r,1] L[1,k]
                     const T l0r = L[2 * k], l0i = L[2 * k + 1], l1r = L[2 * (2 + k)], l1i = L[2 * (2 + k) + 1];
@@ -231,6 +243,154 @@ __global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) 
                 reinterpret_cast<typename Vec2<T>::type *>(o)[c] = w;
             }
         }
+    }
+}
+
+// out-of-line copy for the channels / rows of beam_cube_dde_planes_kernel that have their own grid position
+template <typename T, int NC, bool ROT>
+__device__ __noinline__ void beam_element_call(const BeamParams &p, long long i, T *stage) {
+    beam_element<T, NC, ROT>(p, i, stage);
+}
+
+template <typename T, int NC, bool ROT = false>
+__global__ void __launch_bounds__(256) beam_cube_dde_kernel(const BeamParams p) {
+    const long long total = p.nsrc * p.ntime * p.nant * p.nchan;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x)
+        beam_element<T, NC, ROT>(p, i);
+}
+
+// ---------------------------------------------------------------------------------------
+// Plane-interpolated kernel: one CTA per (source, time, antenna) row of the output.
+//
+// What bounded the one-element-per-thread kernel was the L1 -> register path (ncu: 768 B of corner
+// values ingested per 64 B written, 8 scattered gathers per element) and, behind it, 320 FP64
+// instructions per element.  But for one (source, time, antenna) the grid position (l, m) is the
+// SAME for every in-band channel as long as pointing errors and antenna scaling do not change along
+// the channel axis (they almost never do; out-of-band channels scale lm per channel), so the eight
+// corners of every channel are the same four (l, m) corners at two of the nud frequency planes:
+//   stage 1: S[g] = sum_{k<4} w4[k] beam[corner k][g], A[g] = sum_k w4[k] |beam[corner k][g]| for all
+//            nud planes -- four CONTIGUOUS (nud x ncorr) reads per row instead of 8 gathers per element
+//            (0.1 B ingested per byte written instead of 12);
+//   stage 2: per channel E = nu_w S[g] + (1 - nu_w) S[g+1] (same for A), the amplitude
+//            renormalisation (:227-238), the optional feed rotation, one coalesced store.
+// ~160 FP64 instructions per element: the kernel becomes store-bound.
+// The sum over the 8 corners is re-associated (4 spatial corners per plane first, then the two
+// planes), where the reference accumulates w4[k] nu_w[plane] v over the 8 corners in turn: results
+// differ from the element kernel by a few ulp (tested <= 1e-12 of the largest value; the project
+// gate is 1e-10).  Rows whose pointing errors / antenna scaling change along the channel axis
+// (row_flag, a device pre-pass) and out-of-band channels take the element path.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) beam_row_flag_kernel(const double *perr, const double *ascale,
+                                                            long long nant, long long nchan, uint8_t *flag) {
+    // flag[t * nant + a] = 1: point_errors[t,a,:,:] and antenna_scaling[a,:,:] are constant along chan
+    const long long ta = blockIdx.x, a = ta % nant;
+    const double2 *pe = reinterpret_cast<const double2 *>(perr) + ta * nchan;
+    const double2 *as = reinterpret_cast<const double2 *>(ascale) + a * nchan;
+    const double2 p0 = pe[0], a0 = as[0];
+    bool ok = true;
+    for (long long f = threadIdx.x; f < nchan; f += blockDim.x) {
+        const double2 pv = pe[f], av = as[f];
+        ok = ok && pv.x == p0.x && pv.y == p0.y && av.x == a0.x && av.y == a0.y;
+    }
+    const int all = __syncthreads_and(ok ? 1 : 0);
+    if (threadIdx.x == 0) flag[ta] = (uint8_t)all;
+}
+
+template <typename T, int NC, bool ROT>
+__global__ void __launch_bounds__(256) beam_cube_dde_planes_kernel(const __grid_constant__ BeamParams p) {
+    using V2 = typename Vec2<T>::type;
+    extern __shared__ __align__(16) unsigned char plane_smem[];
+    T *sre = reinterpret_cast<T *>(plane_smem);  // [nud][NC] real part of S, then imaginary part, then A
+    T *sim = sre + p.nud * NC, *sab = sim + p.nud * NC;
+    const T *beam = (const T *)p.beam;
+    const T *babs = (const T *)p.babs;
+    V2 *out = (V2 *)p.out;
+    for (long long sta = blockIdx.x; sta < p.nsrc * p.ntime * p.nant; sta += gridDim.x) {
+        const long long a = sta % p.nant, t = (sta / p.nant) % p.ntime, s = sta / (p.nant * p.ntime);
+        const bool planes = p.row_flag[t * p.nant + a] != 0;  // CTA-uniform
+        if (planes) {
+            const double sin_pa = p.pa_sc[2 * (t * p.nant + a)], cos_pa = p.pa_sc[2 * (t * p.nant + a) + 1];
+            // grid position of an in-band channel (lm scale 1): the row's pointing error / scaling,
+            // the operations of beam_coords (fast_beam_cubes.py:130-151)
+            const double l = p.lm[2 * s], m = p.lm[2 * s + 1];
+            const double2 pe = *reinterpret_cast<const double2 *>(p.perr + ((t * p.nant + a) * p.nchan) * 2);
+            const double2 as = *reinterpret_cast<const double2 *>(p.ascale + (a * p.nchan) * 2);
+            const double tl = __dadd_rn(__dmul_rn(l, 1.0), pe.x), tm = __dadd_rn(__dmul_rn(m, 1.0), pe.y);
+            double vl = __dsub_rn(__dmul_rn(tl, cos_pa), __dmul_rn(tm, sin_pa));
+            double vm = __dadd_rn(__dmul_rn(tl, sin_pa), __dmul_rn(tm, cos_pa));
+            vl = __dmul_rn(vl, as.x), vm = __dmul_rn(vm, as.y);
+            vl = __dmul_rn(p.lscale, __dsub_rn(vl, p.lower_l));
+            vm = __dmul_rn(p.mscale, __dsub_rn(vm, p.lower_m));
+            vl = fmax(0.0, fmin(vl, p.lmaxf)), vm = fmax(0.0, fmin(vm, p.mmaxf));
+            // :154-163
+            const long long gl0 = (long long)(int)floor(vl), gm0 = (long long)(int)floor(vm);
+            const long long gl1 = min(gl0 + 1, p.lw - 1), gm1 = min(gm0 + 1, p.mh - 1);
+            const double ld = __dsub_rn(vl, (double)gl0), md = __dsub_rn(vm, (double)gm0);
+            const double oml = __dsub_rn(1.0, ld), omm = __dsub_rn(1.0, md);
+            const double w4[4] = {__dmul_rn(oml, omm), __dmul_rn(ld, omm), __dmul_rn(oml, md), __dmul_rn(ld, md)};
+            const long long corner[4] = {gl0 * p.mh + gm0, gl1 * p.mh + gm0, gl0 * p.mh + gm1, gl1 * p.mh + gm1};
+            // ---- stage 1: thread <-> (plane, correlation); the (nud x ncorr) block of a corner is contiguous
+            for (int idx = threadIdx.x; idx < (int)p.nud * NC; idx += blockDim.x) {
+                const int g = idx / NC, c = idx - g * NC;
+                double re = 0.0, im = 0.0, ab = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const long long e = (corner[k] * p.nud + g) * p.ncorr + p.coff + c;
+                    const V2 bv = reinterpret_cast<const V2 *>(beam)[e];
+                    re = (double)(T)__dadd_rn(re, __dmul_rn(w4[k], (double)bv.x));
+                    im = (double)(T)__dadd_rn(im, __dmul_rn(w4[k], (double)bv.y));
+                    ab = (double)(T)__dadd_rn(ab, __dmul_rn(w4[k], (double)babs[e]));
+                }
+                sre[idx] = (T)re, sim[idx] = (T)im, sab[idx] = (T)ab;
+            }
+        }
+        __syncthreads();
+        // ---- stage 2: thread <-> channel
+        for (long long f = threadIdx.x; f < p.nchan; f += blockDim.x) {
+            const long long i = sta * p.nchan + f;
+            if (!planes || p.fd[3 * f] != 1.0) {  // per-channel grid position: the element path
+                beam_element_call<T, NC, ROT>(p, i, nullptr);
+                continue;
+            }
+            const double nudw = p.fd[3 * f + 1], inv = __dsub_rn(1.0, nudw);
+            const int g = (int)p.fd[3 * f + 2];
+            T er[NC], ei[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int lo = g * NC + c, hi = lo + NC;
+                const T csr = (T)__dadd_rn(__dmul_rn(nudw, (double)sre[lo]), __dmul_rn(inv, (double)sre[hi]));
+                const T csi = (T)__dadd_rn(__dmul_rn(nudw, (double)sim[lo]), __dmul_rn(inv, (double)sim[hi]));
+                const T asum = (T)__dadd_rn(__dmul_rn(nudw, (double)sab[lo]), __dmul_rn(inv, (double)sab[hi]));
+                const T div = habs(csr, csi);  // :227-238
+                const T kk = (div == T(0)) ? asum : asum / div;
+                er[c] = csr * kk, ei[c] = csi * kk;
+            }
+            V2 *o = out + i * p.ncorr + p.coff;
+            if (ROT && NC == 4) {
+                const T *L = (const T *)p.feed + (t * p.nant + a) * 8;
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {  // out[r,k] = E[r,0] L[0,k] + E[r,1] L[1,k]
+                        const T l0r = L[2 * k], l0i = L[2 * k + 1], l1r = L[2 * (2 + k)], l1i = L[2 * (2 + k) + 1];
+                        const T e0r = er[(2 * r) % NC], e0i = ei[(2 * r) % NC];
+                        const T e1r = er[(2 * r + 1) % NC], e1i = ei[(2 * r + 1) % NC];
+                        V2 w;
+                        w.x = (e0r * l0r - e0i * l0i) + (e1r * l1r - e1i * l1i);
+                        w.y = (e0r * l0i + e0i * l0r) + (e1r * l1i + e1i * l1r);
+                        o[2 * r + k] = w;
+                    }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    V2 w;
+                    w.x = er[c], w.y = ei[c];
+                    o[c] = w;
+                }
+            }
+        }
+        __syncthreads();  // the planes are overwritten by the next row
     }
 }
 
@@ -263,24 +423,35 @@ template <typename T>
 int launch_beam(BeamParams p, cudaStream_t stream) {
     const long long total = p.nsrc * p.ntime * p.nant * p.nchan;
     if (total <= 0) return 0;
-    const int grid = grid_for(total);
+    // AFR_BEAM_PLANES=0 selects the one-element-per-thread kernel (tests compare the two)
+    const size_t plane_bytes = (size_t)p.nud * 4 * 3 * sizeof(T);
+    const bool planes = p.row_flag != nullptr && plane_bytes <= 48 * 1024 && p.nchan >= 64 &&
+                        !(getenv("AFR_BEAM_PLANES") && atoi(getenv("AFR_BEAM_PLANES")) == 0);
+    const long long rows = p.nsrc * p.ntime * p.nant;
+    const int grid = planes ? (int)std::min<long long>(rows, 64LL * sm_count()) : grid_for(total);
     int c = 0;
     while (c < p.ncorr) {  // correlations are independent: blocks of 4, 2, 1
         p.coff = c;
-        if (p.ncorr - c >= 4) {
-            if (p.feed)
-                beam_cube_dde_kernel<T, 4, true><<<grid, 256, 0, stream>>>(p);
-            else
-                beam_cube_dde_kernel<T, 4><<<grid, 256, 0, stream>>>(p);
-            c += 4;
-        } else if (p.ncorr - c >= 2) {
+        const int nc = p.ncorr - c >= 4 ? 4 : (p.ncorr - c >= 2 ? 2 : 1);
+        const size_t sm = (size_t)p.nud * nc * 3 * sizeof(T);
+        if (planes && nc == 4 && p.feed)
+            beam_cube_dde_planes_kernel<T, 4, true><<<grid, 256, sm, stream>>>(p);
+        else if (planes && nc == 4)
+            beam_cube_dde_planes_kernel<T, 4, false><<<grid, 256, sm, stream>>>(p);
+        else if (planes && nc == 2)
+            beam_cube_dde_planes_kernel<T, 2, false><<<grid, 256, sm, stream>>>(p);
+        else if (planes)
+            beam_cube_dde_planes_kernel<T, 1, false><<<grid, 256, sm, stream>>>(p);
+        else if (nc == 4 && p.feed)
+            beam_cube_dde_kernel<T, 4, true><<<grid, 256, 0, stream>>>(p);
+        else if (nc == 4)
+            beam_cube_dde_kernel<T, 4><<<grid, 256, 0, stream>>>(p);
+        else if (nc == 2)
             beam_cube_dde_kernel<T, 2><<<grid, 256, 0, stream>>>(p);
-            c += 2;
-        } else {
+        else
             beam_cube_dde_kernel<T, 1><<<grid, 256, 0, stream>>>(p);
-            c += 1;
-        }
         AFR_LAUNCH_OK();
+        c += nc;
     }
     return 0;
 }
@@ -351,14 +522,20 @@ extern "C" int afr_beam_cube_dde_rot(const void *beam, const double *ext_host_or
     AFR_REQUIRE(lw >= 2 && mh >= 2 && nud >= 2, "beam_lw, beam_mh and beam_nud must be >= 2");
     AFR_REQUIRE(ncorr >= 1 && nsrc >= 0 && ntime >= 0 && nant >= 0 && nchan >= 0, "bad extent");
     if (nsrc == 0 || ntime == 0 || nant == 0 || nchan == 0) return 0;
-    // the four extents are needed on the host to form lscale/mscale (:83-92)
-    double ext[4];
-    AFR_CUDA_OK(cudaMemcpyAsync(ext, ext_host_or_dev, sizeof(ext), cudaMemcpyDefault, stream));
-    AFR_CUDA_OK(cudaStreamSynchronize(stream));
     Scratch fd;
     AFR_CUDA_OK(fd.alloc(sizeof(double) * 3 * (size_t)nchan, stream));
     int rc = afr_freq_grid_interp(freq, beam_freq_map, nchan, nud, (double *)fd.ptr, stream_);
     if (rc) return rc;
+    // the four extents are needed on the host to form lscale/mscale (:83-92)
+    double ext[4];
+    AFR_CUDA_OK(cudaMemcpyAsync(ext, ext_host_or_dev, sizeof(ext), cudaMemcpyDefault, stream));
+    AFR_CUDA_OK(cudaStreamSynchronize(stream));
+    // which (time, antenna) rows keep one grid position along the channel axis
+    Scratch rflag;
+    AFR_CUDA_OK(rflag.alloc((size_t)(ntime * nant), stream));
+    beam_row_flag_kernel<<<(unsigned)(ntime * nant), 256, 0, stream>>>(point_errors, antenna_scaling, nant, nchan,
+                                                                      (uint8_t *)rflag.ptr);
+    AFR_LAUNCH_OK();
     // pre-passes: |beam| and sin/cos of the parallactic angles
     const long long nbeam = lw * mh * nud * ncorr;
     Scratch babs, pasc;
@@ -400,5 +577,6 @@ extern "C" int afr_beam_cube_dde_rot(const void *beam, const double *ext_host_or
     p.nant = nant;
     p.nchan = nchan;
     p.ncorr = (int)ncorr;
+    p.row_flag = (const uint8_t *)rflag.ptr;
     return is_c64 ? launch_beam<float>(p, stream) : launch_beam<double>(p, stream);
 }

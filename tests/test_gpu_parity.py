@@ -364,6 +364,56 @@ def test_beam_cube_dde_vs_oracle(b200, oracle):
         assert_c128_close(got, oracle.beam_cube_dde(beam, ext, bfm, lm, pa, perr, ascale, freq))
 
 
+def test_beam_cube_dde_planes_kernel(b200, oracle, monkeypatch):
+    """The plane-interpolated kernel (four spatial corners reduced per frequency plane once per
+    (source, time, antenna) row, then two planes per channel) re-associates the reference's sum over
+    the 8 corners: it must agree with the element-per-thread kernel to a few ulp and with the oracle
+    at the project gate.  Cases: channel-constant pointing errors (plane path), per-channel pointing
+    errors / scaling (rows fall back to the element path: bit-identical), out-of-band channels (lm
+    scaled per channel: element path inside a plane row), complex64 beams, 1 / 2 / 3 / 4
+    correlations, and the feed-rotation epilogue."""
+    rng = np.random.default_rng(77)
+    lw, mh, nud = 41, 37, 9
+    nsrc, ntime, nant = 13, 2, 5
+    bfm = np.linspace(0.856e9, 1.712e9, nud)
+    ext = np.array([[-0.05, 0.05], [-0.04, 0.06]])
+    lm = rng.uniform(-0.045, 0.045, (nsrc, 2))
+    pa = rng.uniform(-np.pi, np.pi, (ntime, nant))
+
+    def both(fn, *args):
+        got = fn(*args)
+        monkeypatch.setenv("AFR_BEAM_PLANES", "0")
+        elem = fn(*args)
+        monkeypatch.delenv("AFR_BEAM_PLANES")
+        return got, elem
+
+    for nchan, f_lo, f_hi in ((256, 0.856e9, 1.712e9), (77, 0.80e9, 1.80e9)):
+        freq = np.linspace(f_lo, f_hi, nchan)
+        perr_c = np.ascontiguousarray(
+            np.broadcast_to(rng.uniform(-0.004, 0.004, (ntime, nant, 1, 2)), (ntime, nant, nchan, 2)))
+        perr_v = rng.uniform(-0.004, 0.004, (ntime, nant, nchan, 2))
+        perr_v[1] = perr_c[1]  # timestep 1 keeps constant errors: plane rows and element rows in one call
+        asc_c = np.ones((nant, nchan, 2)) * rng.uniform(0.95, 1.05, (nant, 1, 2))
+        asc_v = rng.uniform(0.95, 1.05, (nant, nchan, 2))
+        for corr, dt in (((2, 2), np.complex128), ((2, 2), np.complex64), ((3,), np.complex128), ((1,), np.complex128)):
+            beam = (rng.standard_normal((lw, mh, nud) + corr) + 1j * rng.standard_normal((lw, mh, nud) + corr)).astype(dt)
+            for perr, asc in ((perr_c, asc_c), (perr_v, asc_c), (perr_c, asc_v)):
+                args = (beam, ext, bfm, lm, pa, perr, asc, freq)
+                got, elem = both(b200.rime.beam_cube_dde, *args)
+                if asc is asc_v:
+                    np.testing.assert_array_equal(got, elem)  # no plane rows at all
+                elif dt == np.complex128:
+                    assert_c128_close(got, elem, rtol=1e-12)
+                    assert_c128_close(got, oracle.beam_cube_dde(*args))
+                else:
+                    assert_c64_close(got, elem, tol=2e-6)
+        beam = rng.standard_normal((lw, mh, nud, 2, 2)) + 1j * rng.standard_normal((lw, mh, nud, 2, 2))
+        for feed in ("linear", "circular"):
+            args = (beam, ext, bfm, lm, pa, perr_c, asc_c, freq, b200.rime.feed_rotation(pa, feed))
+            got, elem = both(b200.rime.beam_cube_dde_rotated, *args)
+            assert_c128_close(got, elem, rtol=1e-12)
+
+
 # ----------------------------------------------------------------------------- fused
 def test_fused_predict_golden(b200, golden):
     g = golden("fused_predict")
