@@ -155,30 +155,82 @@ def cpu_im_to_vis_rate(wl, seconds_target, threads=None):
     return rate, threads, sample, t, rows
 
 
+def numba_im_to_vis_rate(wl, seconds_target, threads=None):
+    """The reference's OWN numba kernel (africanus.dft.im_to_vis, dft/kernels.py:23-69, nogil) from
+    baseline/_ref (tools/install_reference.py), threaded over row blocks with a ThreadPoolExecutor --
+    what dask's threaded scheduler does with it.  None when the install or numba is absent."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "africanus")):
+        return None
+    os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(tempfile.gettempdir(), "numba_cache_afr"))
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        from concurrent.futures import ThreadPoolExecutor
+
+        from africanus.dft import im_to_vis as ref_im_to_vis
+    except Exception:
+        return None
+    threads = threads or os.cpu_count() or 1
+    image, lm, freq = wl["image"], wl["lm"], wl["freq"]
+    nsrc, nchan = wl["nsrc"], wl["nchan"]
+    ref_im_to_vis(image[:2], wl["uvw"][:2], lm[:2], freq)  # JIT
+
+    def run(nrows, nthreads):
+        rows = np.linspace(0, wl["uvw"].shape[0] - 1, nrows).astype(np.int64)
+        uvw = np.ascontiguousarray(wl["uvw"][rows])
+        blocks = np.array_split(np.arange(nrows), nthreads)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(nthreads) as ex:
+            list(ex.map(lambda b: ref_im_to_vis(image, uvw[b[0]:b[-1] + 1], lm, freq), [b for b in blocks if b.size]))
+        return time.perf_counter() - t0
+
+    t1 = run(2, 1)  # two rows on one thread: the per-core rate
+    rows = int(max(threads, min(64 * threads, threads * seconds_target / max(t1 / 2, 1e-6))))
+    rows = (rows // threads) * threads
+    t = run(rows, threads)
+    rate = nsrc * float(rows) * nchan / t / 1e9
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "reference",
+            "one_core_Gterms_per_s": nsrc * 2.0 * nchan / t1 / 1e9,
+            "sample": "africanus.dft.im_to_vis (numba, nogil) on %d threads: %d of %d rows x %d chan x %d "
+                      "sources, %.1f s" % (threads, rows, wl["uvw"].shape[0], nchan, nsrc, t),
+            "seconds": t}
+
+
 def run_reference_arm(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0  # rank 0 alone runs the CPU arm
     wl = workload(0, 1)
     per_step = float(os.environ.get("BENCH_REF_STEP_SECONDS", 6.0))
-    rates, secs, rows_used, cores, sample = [], [], 0, 1, ""
+    # the reference's own numba kernel when it is installed (baseline/_ref), else the C port
+    use_numba = numba_im_to_vis_rate(wl, 0.5) is not None
+    rates, secs, cores, sample, kind = [], [], 1, "", "port"
     for i in range(args.warmup + args.steps):
-        rate, cores, sample, t, rows_used = cpu_im_to_vis_rate(wl, per_step)
+        if use_numba:
+            r = numba_im_to_vis_rate(wl, per_step)
+            rate, cores, sample, t, kind = r["value"], r["cores"], r["sample"], r["seconds"], "reference"
+        else:
+            rate, cores, sample, t, _ = cpu_im_to_vis_rate(wl, per_step)
         if i >= args.warmup:
             rates.append(rate)
             secs.append(t)
     value = statistics.mean(rates)
+    port_rate, port_cores, port_sample, _, _ = cpu_im_to_vis_rate(wl, per_step)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": wl["desc"],
-                   "reference_arm": "CPU port of africanus.dft.im_to_vis (oracle/afr_oracle.c, "
-                                    "OpenMP over rows, all host threads); each step is a bounded "
-                                    "row sample of the workload: " + sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
+                   "reference_arm": ("the reference's own numba africanus.dft.im_to_vis (baseline/_ref), threaded "
+                                     "over row blocks on all host threads" if use_numba else
+                                     "CPU port of africanus.dft.im_to_vis (oracle/afr_oracle.c, OpenMP over "
+                                     "rows, all host threads)") + "; each step is a bounded row sample of the "
+                                    "workload: " + sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline_port": {"value": port_rate, "unit": UNIT, "cores": port_cores, "kind": "port",
+                              "sample": port_sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -218,6 +270,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernel timings")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[0]/[2]/[3]/[4] entries")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -302,6 +355,23 @@ def main():
     kernel_s = statistics.mean(a.elapsed_time(b) for a, b in ev) * 1e-3
     value = world * terms * steps / total_s / 1e9
     checksum = float(torch.view_as_real(out[:1024]).abs().sum().item())
+    dft_path = _lib.describe_dft_path()
+    # parity of the timed call's output on a row subsample: 16 rows spread over the
+    # track, all channels and sources, against the oracle (the checker; never the thing measured)
+    parity = None
+    if rank == 0:
+        import oracle
+
+        oracle.build()
+        rows = np.linspace(0, wl["uvw"].shape[0] - 1, 16).astype(np.int64)
+        ref = oracle.im_to_vis(wl["image"], wl["uvw"][rows], wl["lm"], wl["freq"])
+        got = out[torch.from_numpy(rows).to(dev)].cpu().numpy()
+        scale = float(np.max(np.abs(ref)))
+        parity = {"ok": bool(np.allclose(got, ref, rtol=1e-10, atol=1e-10 * scale)),
+                  "max_abs_err_over_max_ref": float(np.max(np.abs(got - ref)) / scale),
+                  "gate": "allclose(rtol=1e-10, atol=1e-10*max|ref|)",
+                  "checked": "16 rows spread over the track x all %d channels x all %d sources vs the oracle"
+                             % (wl["nchan"], wl["nsrc"])}
     out = None
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H timed
@@ -313,7 +383,7 @@ def main():
         res = dft.im_to_vis(h["image"], h["uvw"], h["lm"], h["freq"])  # warm-up (pins buffers)
         d2h = res.nbytes
         res = None
-        n_e2e = max(1, min(steps, 2))
+        n_e2e = max(steps, env_int("BENCH_E2E_STEPS", 5))
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -339,21 +409,37 @@ def main():
                    "no data-path collective" % world,
                    "l2": "256 MiB flush between steps; per-step output (%.2f GB) exceeds L2"
                          % (terms / wl["nsrc"] * 16 / 1e9),
-                   "checksum": checksum},
+                   "checksum": checksum, "kernel_path": dft_path},
         "clocks": clocks, "gpu_launches": launches,
     }
+    if parity:
+        line["parity"] = parity
     if e2e:
         line["e2e"] = e2e
 
     if rank == 0:
         achieved = FLOP_PER_TERM * terms / kernel_s / 1e12
-        traffic = None
+        # DRAM bytes per launch of this kernel from an `ncu --set full` capture (profiles/): a
+        # capture cannot run inside the timed region, so the figure is accepted only while its stamp
+        # -- the sha256 of the kernel's source file it was taken with -- matches the source that
+        # built the library measured here; otherwise traffic is null
+        traffic, traffic_note = None, "no capture"
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("phasor_stream_im_to_vis_cfg2_bytes_per_launch")
-            except Exception:
-                traffic = None
+                import hashlib
+
+                tj = json.load(open(tpath))
+                src = os.path.join(ROOT, "codex_africanus_b200", "csrc", "afr_dft.cu")
+                sha = hashlib.sha256(open(src, "rb").read()).hexdigest()
+                ent = tj.get("phasor_stream_im_to_vis_cfg2")
+                if ent and ent.get("source_sha256") == sha:
+                    traffic = ent.get("dram_bytes_per_launch")
+                    traffic_note = "ncu capture %s, source stamp matches" % ent.get("capture")
+                else:
+                    traffic_note = "capture is stale (kernel source changed since): not reported"
+            except Exception as exc:
+                traffic_note = "unreadable: %r" % (exc,)
         peaks = {}
         ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(ppath):
@@ -370,7 +456,7 @@ def main():
             "kernel_ms": 1e3 * kernel_s,
             "peak_source": "measured in this run: afr_measure_fma_peak (dependent-free DFMA "
                            "chains on all SMs); MEASURED_PEAKS.json has no FP64 entry",
-            "traffic": traffic,
+            "traffic": traffic, "traffic_source": traffic_note,
             "hbm": {"algorithmic_GBps": io_bytes / kernel_s / 1e9,
                     "peak_GBps": peaks.get("hbm_gbs", 6650.0),
                     "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
@@ -382,6 +468,26 @@ def main():
         rate, cores, sample, _, _ = cpu_im_to_vis_rate(wl, float(os.environ.get("BENCH_CPU_SECONDS", 12)))
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": sample}
+        try:
+            nb = numba_im_to_vis_rate(wl, float(os.environ.get("BENCH_NUMBA_SECONDS", 8)))
+        except Exception as exc:
+            nb = {"error": repr(exc)}
+        if nb:
+            nb.pop("seconds", None)
+            line["cpu_baseline_reference"] = nb  # the reference's own numba kernel, same box, same run
+
+    # ---- the other BASELINE configs as first-class entries (tools/bench_configs.py)
+    if not args.no_configs:
+        try:
+            import bench_configs
+
+            cfgs = bench_configs.run(dev, fp64_peak, env_int("BENCH_CFG_STEPS", 5), env_int("BENCH_CFG_WARMUP", 3),
+                                     rank, world)
+            if rank == 0:
+                line["configs"] = cfgs
+        except Exception as exc:
+            if rank == 0:
+                line["configs"] = {"error": repr(exc)}
 
     # ---- secondary kernels (one GPU): every other row of SURVEY.md section 8
     if world == 1 and not args.no_extras:
@@ -390,15 +496,6 @@ def main():
 
             line["extra"] = bench_extras.run(dev, fp64_peak)
         except Exception as exc:  # extras must never sink the headline number
-            line["extra"] = {"error": repr(exc)}
-    elif world > 1 and not args.no_extras:
-        try:
-            import bench_extras
-
-            ex = bench_extras.run_distributed(dev, rank, world)
-            if rank == 0:
-                line["extra"] = ex
-        except Exception as exc:
             line["extra"] = {"error": repr(exc)}
 
     if rank == 0:

@@ -31,6 +31,8 @@ PROTOTYPES = {
     "afr_device_count": (_int, []),
     "afr_kernel_launches": (ctypes.c_ulonglong, []),
     "afr_last_fused_path": (_int, []),
+    "afr_last_dft_path": (_int, []),
+    "afr_trim_scratch": (_int, [_int]),
     "afr_set_device": (_int, [_int]),
     "afr_device_info": (_int, [_int, _pint, _pint, _pint, _pint]),
     "afr_freq_is_uniform": (_int, [_vp, _i64, _dbl]),
@@ -81,6 +83,18 @@ def lib():
             fn.argtypes = argtypes
         _lib = handle
     return _lib
+
+
+def describe_dft_path(code=None):
+    """afr_last_dft_path() as text."""
+    code = lib().afr_last_dft_path() if code is None else code
+    if code == 0:
+        return "none"
+    return "%s, %s, %s W tile, %s accumulators, %d channel runs per CTA, %d slice(s) of the streamed axis" % (
+        "warp-specialised (16 consumer + 4 producer warps)" if code & 1 else "single-role (16 warps)",
+        "one sincos per term" if code & 2 else "three-term / rotation recurrence",
+        "TMA bulk-copied" if code & 4 else "cp.async / staged", "FP32" if code & 8 else "FP64",
+        (code >> 8) & 0xFF, (code >> 16) & 0xFFFF)
 
 
 def last_error():

@@ -5,6 +5,7 @@ memory, CUDA streams.  PyTorch is used for device memory and streams only; all
 arithmetic happens in libafricanus_b200.so.
 """
 import ctypes
+import weakref
 import threading
 
 import numpy as np
@@ -104,10 +105,95 @@ def to_host(t):
     """Device tensor -> numpy array (through pinned memory, synchronised)."""
     if t.numel() == 0:
         return np.empty(tuple(t.shape), dtype=_T2N[t.dtype])
+    if t.dim() >= 1 and t.numel() * t.element_size() > PIN_WHOLE_MAX and t.is_contiguous():
+        sink = RowSink(tuple(t.shape), _T2N[t.dtype], t.device)  # bounded page-locked staging
+        compute = torch.cuda.current_stream(t.device)
+        step = sink.max_block_rows()
+        for r0 in range(0, t.shape[0], step):
+            r1 = min(t.shape[0], r0 + step)
+            sink.push(r0, r1, t[r0:r1], compute)
+        return sink.finish()
     pinned = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     pinned.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
     return pinned.numpy()
+
+
+# A result this large is not pinned whole: PyTorch's caching host allocator rounds page-locked
+# blocks up to a power of two and never returns them to the OS, so an 8 GB visibility array would
+# lock 16 GB for as long as the caller keeps it (and SKA-size outputs could not be returned at all).
+PIN_WHOLE_MAX = 2 << 30
+_STAGE_BYTES = 512 << 20
+
+
+class RowSink:
+    """Host destination of a (row, ...) result produced in row blocks on the device.
+
+    Up to PIN_WHOLE_MAX bytes the result is one page-locked array and every block is copied
+    straight into place.  Above that the result is an ordinary numpy array: blocks travel through
+    two rotating page-locked staging buffers (<= 512 MiB each) on the copy stream and are moved into
+    place by the host while the device computes / copies the following blocks."""
+
+    def __init__(self, shape, np_dtype, device):
+        self.shape = tuple(int(v) for v in shape)
+        self.dtype = np.dtype(np_dtype)
+        self.device = device
+        self.copier = side_stream(device)
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self.whole = nbytes <= PIN_WHOLE_MAX
+        if self.whole:
+            self._pinned = empty_pinned(self.shape, self.dtype)
+            self.out = self._pinned.numpy()
+        else:
+            self.out = np.empty(self.shape, self.dtype)
+            self._bufs = [None, None]
+            self._pending = [None, None]
+            self._k = 0
+
+    def max_block_rows(self):
+        row_bytes = max(1, int(np.prod(self.shape[1:], dtype=np.int64)) * self.dtype.itemsize)
+        return max(1, _STAGE_BYTES // row_bytes)
+
+    def _drain(self, b):
+        pend = self._pending[b]
+        if pend is not None:
+            r0, r1, done = pend
+            done.synchronize()
+            self.out[r0:r1] = self._bufs[b][: r1 - r0].numpy()
+            self._pending[b] = None
+
+    def push(self, r0, r1, d_block, compute):
+        """Queue the copy of ``d_block`` (rows r0:r1, complete once the work queued on ``compute`` so
+        far has run); returns the event that marks the end of the device-side read."""
+        ev = torch.cuda.Event()
+        ev.record(compute)
+        self.copier.wait_event(ev)
+        done = torch.cuda.Event()
+        if self.whole:
+            with torch.cuda.stream(self.copier):
+                self._pinned[r0:r1].copy_(d_block, non_blocking=True)
+                done.record(self.copier)
+            return done
+        b = self._k & 1
+        self._k += 1
+        self._drain(b)
+        n = r1 - r0
+        if self._bufs[b] is None or self._bufs[b].shape[0] < n:
+            self._bufs[b] = empty_pinned((max(n, min(self.max_block_rows(), self.shape[0])),) + self.shape[1:],
+                                         self.dtype)
+        with torch.cuda.stream(self.copier):
+            self._bufs[b][:n].copy_(d_block, non_blocking=True)
+            done.record(self.copier)
+        self._pending[b] = (r0, r1, done)
+        return done
+
+    def finish(self):
+        if not self.whole:
+            first = self._k & 1  # the older of the two pending blocks
+            self._drain(first)
+            self._drain(first ^ 1)
+        self.copier.synchronize()
+        return self.out
 
 
 def ptr(t):
@@ -155,8 +241,30 @@ def host_frequency(frequency):
 UNIFORM_RTOL = 4e-16
 
 
+_chan_mode_cache = {}  # id(tensor) -> (weakref, tensor._version, mode)
+
+
 def channel_mode(frequency):
-    f = host_frequency(frequency)
+    """AFR_CHAN_UNIFORM when the channels are equispaced (recurrence kernels), else AFR_CHAN_EXACT.
+    The check needs the values on the host; for a CUDA tensor that is a blocking copy, which a
+    millisecond-scale call (BASELINE configs[0]) cannot afford on every invocation, so the answer is
+    remembered per tensor OBJECT (weak reference) and version counter -- never per address."""
+    if is_torch(frequency) and frequency.is_cuda:
+        key = id(frequency)
+        hit = _chan_mode_cache.get(key)
+        if hit is not None and hit[0]() is frequency and hit[1] == frequency._version:
+            return hit[2]
+        mode = _channel_mode_host(host_frequency(frequency))
+        try:
+            ref = weakref.ref(frequency, lambda _r, k=key: _chan_mode_cache.pop(k, None))
+            _chan_mode_cache[key] = (ref, frequency._version, mode)
+        except TypeError:
+            pass
+        return mode
+    return _channel_mode_host(host_frequency(frequency))
+
+
+def _channel_mode_host(f):
     if f.ndim != 1:
         raise ValueError("frequency must be 1-dimensional")
     if f.shape[0] <= 1:

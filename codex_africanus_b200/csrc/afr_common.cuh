@@ -27,6 +27,8 @@ int fail(const std::string &msg);
 void note_launch(int n = 1);
 // which kernel the last afr_predict_fused call of this host thread used (AFR_PATH_*)
 void note_fused_path(int path);
+// which phasor-stream schedule the last DFT-type launch of this host thread used (AFR_DFT_*)
+void note_dft_path(int path);
 
 // call right after a <<<...>>> launch: counts it and checks the launch status
 #define AFR_LAUNCH_OK()                                                                \
@@ -56,8 +58,8 @@ inline int sm_count() {
     return n > 0 ? n : 148;
 }
 
-// keep freed scratch in the device's default memory pool instead of returning it to the
-// driver at every synchronisation (the default release threshold is 0)
+// keep up to 2 GiB of freed scratch in the device's default memory pool instead of returning it to
+// the driver at every synchronisation (the default release threshold is 0)
 void retain_pool_memory();
 
 // stream-ordered scratch allocation

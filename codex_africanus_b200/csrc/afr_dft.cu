@@ -1081,6 +1081,8 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     }
 
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nsplit);
+    note_dft_path((use_ws ? 1 : 0) | (exact ? 2 : 0) | (p.bulk ? 4 : 0) | (sizeof(ACC) == 4 ? 8 : 0) | (nck << 8) |
+                  ((int)nsplit << 16));
     if constexpr (sizeof(ACC) == 8) {
       if (use_ws) {
         // setmaxnreg can only move registers inside the CTA's launch-time pool: 640 threads

@@ -10,6 +10,7 @@ namespace afr {
 static thread_local std::string g_last_error;
 static std::atomic<unsigned long long> g_launches{0};
 static thread_local int g_fused_path = 0;
+static thread_local int g_dft_path = 0;
 
 void retain_pool_memory() {
     static std::atomic<unsigned> done_mask{0};  // one bit per device
@@ -19,7 +20,10 @@ void retain_pool_memory() {
     if (done_mask.load(std::memory_order_relaxed) & bit) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long threshold = ~0ull;
+        // keep up to 2 GiB of freed scratch cached between calls (the default threshold, 0,
+        // returns everything to the driver at every synchronisation); larger scratch -- y-split
+        // partials, wsclean spectra -- goes back, so an allocator sharing the GPU is not starved
+        unsigned long long threshold = 2ull << 30;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
     }
     done_mask.fetch_or(bit, std::memory_order_relaxed);
@@ -30,6 +34,7 @@ void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memor
 void set_error(const std::string &msg) { g_last_error = msg; }
 
 void note_fused_path(int path) { g_fused_path = path; }
+void note_dft_path(int path) { g_dft_path = path; }
 
 int fail(const std::string &msg) {
     g_last_error = msg;
@@ -69,6 +74,17 @@ extern "C" unsigned long long afr_kernel_launches(void) {
 extern "C" const char *afr_last_error(void) { return g_last_error.c_str(); }
 
 extern "C" int afr_last_fused_path(void) { return g_fused_path; }
+
+extern "C" int afr_last_dft_path(void) { return g_dft_path; }
+
+extern "C" int afr_trim_scratch(int device) {
+    // hand the stream-ordered scratch this library keeps cached in the device's default CUDA
+    // memory pool back to the driver (callers that share the GPU with another allocator)
+    cudaMemPool_t pool;
+    AFR_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, device));
+    AFR_CUDA_OK(cudaMemPoolTrimTo(pool, 0));
+    return 0;
+}
 
 extern "C" int afr_device_count(void) {
     int n = 0;

@@ -78,20 +78,16 @@ def im_to_vis(image, uvw, lm, frequency, convention="fourier", dtype=None):
         if nrow == 0 or nchan == 0 or ncorr == 0:
             launch(0, nrow)
             return np.zeros((nrow, nchan, ncorr), out_dtype)
-        h_out = pl.empty_pinned((nrow, nchan, ncorr), out_dtype)
+        sink = pl.RowSink((nrow, nchan, ncorr), out_dtype, device)
+        block = min(block, sink.max_block_rows()) if not sink.whole else block
         compute = torch.cuda.current_stream(device)
-        copier = pl.side_stream(device)
         for r0 in range(0, nrow, block):
             r1 = min(nrow, r0 + block)
             launch(r0, r1)
-            ev = torch.cuda.Event()
-            ev.record(compute)
-            copier.wait_event(ev)
-            with torch.cuda.stream(copier):
-                h_out[r0:r1].copy_(d_out[r0:r1], non_blocking=True)
-        copier.synchronize()
+            sink.push(r0, r1, d_out[r0:r1], compute)
+        out = sink.finish()
         compute.synchronize()
-        return h_out.numpy()
+        return out
 
 
 def vis_to_im(vis, uvw, lm, frequency, flags, convention="fourier", dtype=None):

@@ -25,14 +25,17 @@ _ROW_BLOCK_BYTES = 512 << 20
 
 def fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
                       dde1_jones=None, dde2_jones=None, die1_jones=None, base_vis=None,
-                      die2_jones=None, convention="fourier"):
+                      die2_jones=None, convention="fourier", dtype=None):
     """V[r,f] = G1 (B[r,f] + sum_s E1 (K[s,r,f] brightness[s,f]) E2^H) G2^H.
 
     lm (source,2), uvw (row,3), frequency (chan,) real; brightness (source,chan,corr...)
     complex with corr... in {(1,), (2,), (2,2)}; the remaining arguments are exactly those
     of ``predict_vis`` (the brightness standing in for ``source_coh`` without its row axis).
-    Output dtype is ``np.result_type`` of the complex inputs: complex128 runs the chain in
-    FP64, complex64 in FP32 with an FP64 phase argument.
+    Output dtype: that of the reference's un-fused chain -- ``phase_delay`` gives
+    ``result_type(complex64, lm, uvw, frequency)`` (rime/phase.py:26), the einsum with the brightness
+    and ``predict_vis`` promote further (rime/predict.py:542-544) -- so float64 coordinates give
+    complex128 whatever the Jones precision.  ``dtype=np.complex64`` asks for the single-precision
+    chain explicitly (FP32 Jones products and accumulators; the phase argument stays FP64).
     """
     sign = pl.convention_sign(convention)
     bshape = pl.shape_of(brightness)
@@ -52,7 +55,13 @@ def fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, ante
         raise ValueError("fused_predict_vis: uvw / time_index rows mismatch")
     cplx = [a for a in (brightness, dde1_jones, dde2_jones, die1_jones, base_vis, die2_jones)
             if a is not None]
-    out_dtype = np.result_type(np.complex64, *(pl.dtype_of(a) for a in cplx))
+    if dtype is None:
+        out_dtype = np.result_type(np.complex64, *(pl.dtype_of(a) for a in (lm, uvw, frequency)),
+                                   *(pl.dtype_of(a) for a in cplx))
+    else:
+        out_dtype = np.dtype(dtype)
+        if out_dtype not in (np.complex64, np.complex128):
+            raise TypeError("fused_predict_vis: dtype must be complex64 or complex128")
     ncorr = int(np.prod(corr_shape))
     ntime, nant = 1, 1
     if dde1_jones is not None:
@@ -97,10 +106,11 @@ def fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, ante
         # base_vis goes up and its visibilities come back on a copy stream while the next
         # block computes (the reference's own answer to configs-3-sized outputs is row
         # chunking, africanus/rime/dask_predict.py:667-726)
+        sink = pl.RowSink(out_shape, out_dtype, device)
         block = max(1024, _ROW_BLOCK_BYTES // row_bytes)
-        h_out = pl.empty_pinned(out_shape, out_dtype)
+        if not sink.whole:
+            block = min(block, sink.max_block_rows())
         compute = torch.cuda.current_stream(device)
-        copier = pl.side_stream(device)
         bufs = [pl.empty_device((min(block, nrow), nchan) + tuple(corr_shape), out_dtype, device)
                 for _ in range(2)]
         done = [None, None]
@@ -112,13 +122,7 @@ def fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, ante
                 compute.wait_event(done[i & 1])  # the copy out of this buffer has finished
             d_bvis = None if bv is None else pl.to_device(bv[r0:r1], out_dtype, device)
             launch(r0, r1, d_bvis, buf)
-            ev = torch.cuda.Event()
-            ev.record(compute)
-            copier.wait_event(ev)
-            with torch.cuda.stream(copier):
-                h_out[r0:r1].copy_(buf, non_blocking=True)
-                done[i & 1] = torch.cuda.Event()
-                done[i & 1].record(copier)
-        copier.synchronize()
+            done[i & 1] = sink.push(r0, r1, buf, compute)
+        out = sink.finish()
         compute.synchronize()
-        return h_out.numpy()
+        return out

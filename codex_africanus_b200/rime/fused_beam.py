@@ -83,10 +83,10 @@ def fused_predict_vis_beam(lm, uvw, frequency, brightness, time_index, antenna1,
             if dde.dtype != d_b.dtype:
                 dde = dde.to(d_b.dtype)
             acc = fused_predict_vis(d_lm[s0:s1], d_uvw, d_f, d_b[s0:s1], d_ti, d_a1, d_a2, dde, dde,
-                                    None, acc, None, convention=convention)
+                                    None, acc, None, convention=convention, dtype=out_dtype)
             del dde
         if acc is None:  # no sources and no base_vis
-            acc = fused_predict_vis(d_lm, d_uvw, d_f, d_b, d_ti, d_a1, d_a2, convention=convention)
+            acc = fused_predict_vis(d_lm, d_uvw, d_f, d_b, d_ti, d_a1, d_a2, convention=convention, dtype=out_dtype)
         if die1_jones is not None:
             d_g1 = pl.to_device(die1_jones, out_dtype, device)
             d_g2 = d_g1 if die2_jones is die1_jones else pl.to_device(die2_jones, out_dtype, device)

@@ -82,7 +82,7 @@ def fused_predict_vis_stokes(lm, uvw, frequency, stokes, spi, ref_freq, time_ind
                 d_e1 = pl.to_device(dde1_jones[s0:s1], out_dtype, device)
                 d_e2 = d_e1 if same_dde else pl.to_device(dde2_jones[s0:s1], out_dtype, device)
             acc = fused_predict_vis(d_lm[s0:s1], d_uvw, d_f, d_b, d_ti, d_a1, d_a2, d_e1, d_e2,
-                                    None, acc, None, convention=convention)
+                                    None, acc, None, convention=convention, dtype=out_dtype)
             del d_b, d_e1, d_e2
         if die1_jones is not None:
             d_g1 = pl.to_device(die1_jones, out_dtype, device)

@@ -68,6 +68,16 @@ unsigned long long afr_kernel_launches(void);
 #define AFR_PATH_DDE_GATHER 5   /* gather kernel (unsorted rows, diagonal Jones, complex64)   */
 #define AFR_PATH_DDE_MMA_ANT 6  /* antenna phasors, source sum as a complex GEMM on the FP64 tensor pipe */
 int afr_last_fused_path(void);
+/* Which schedule of the phasor-stream kernel the last afr_im_to_vis / afr_vis_to_im / point-source
+ * afr_predict_fused / afr_wsclean_predict launch of this host thread used (its last correlation
+ * block): bit 0 warp-specialised (16 consumer + 4 producer warps), bit 1 one sincos per term
+ * (non-equispaced channels), bit 2 W tile by TMA bulk copies, bit 3 FP32 accumulators,
+ * bits 8-15 channel runs per CTA, bits 16-31 slices of the streamed axis.  Environment overrides
+ * (AFR_WS, AFR_SANITIZE) show up here, so a benchmark can report the path it measured. */
+int afr_last_dft_path(void);
+/* Return the scratch memory this library keeps cached in `device`'s default CUDA memory pool
+ * (up to 2 GiB between calls) to the driver. */
+int afr_trim_scratch(int device);
 /* Select the CUDA device used by subsequent calls on this host thread.  The library
  * links its own (static) CUDA runtime, whose current-device state is separate from any
  * other runtime in the process (e.g. PyTorch's): bindings call this before each entry

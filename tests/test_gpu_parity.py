@@ -476,11 +476,17 @@ def test_fused_predict_vs_oracle(b200, oracle):
             got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die)
             assert_c128_close(got, ref)
             c64 = np.complex64
-            got = b200.rime.fused_predict_vis(lm, uvw, freq, bright.astype(c64), ti, ant1, ant2,
-                                              dde.astype(c64), dde.astype(c64), die.astype(c64),
-                                              bvis.astype(c64), die.astype(c64))
+            args64 = (bright.astype(c64), ti, ant1, ant2, dde.astype(c64), dde.astype(c64), die.astype(c64),
+                      bvis.astype(c64), die.astype(c64))
+            got = b200.rime.fused_predict_vis(lm, uvw, freq, *args64, dtype=c64)
             assert got.dtype == c64
             assert rel_l2(got.astype(np.complex128), ref) < 1e-5
+            # dtype promotion of the reference chain: float64 coordinates make K complex128
+            # (rime/phase.py:26) and with it the visibilities; all-float32 coordinates keep complex64
+            assert b200.rime.fused_predict_vis(lm, uvw, freq, *args64).dtype == np.complex128
+            f32 = np.float32
+            assert b200.rime.fused_predict_vis(lm.astype(f32), (uvw * 1e-3).astype(f32), freq.astype(f32),
+                                               *args64).dtype == c64
 
 
 def test_fused_dde_ws_modes_vs_oracle(b200, oracle, monkeypatch):

@@ -290,49 +290,3 @@ def run(dev, fp64_peak):
         "Gterms_per_s": terms3 / t / 1e9, "ms": 1e3 * t, "terms": terms3, "flop_per_term": 95,
         "frac_of_fp64_fma_peak": 95 * terms3 / t / fp64_peak}
     return res
-
-
-def run_distributed(dev, rank, world):
-    """configs[4]-shaped vis_to_im: per-rank partial dirty image + one NCCL all_reduce."""
-    import torch.distributed as dist
-
-    rng = np.random.default_rng(5)
-    # the geometry of configs[4]: 1024 x 1024 pixels of 4", 64 channels -> a 512 MiB float64 image;
-    # 2 of the 1550 timesteps per rank keep the default bench short
-    na, ntime, nchan, npix = 64, 2, 64, 1024
-    uvw, tidx, a1, a2 = synth.uvw_tracks(na, ntime * world, rng, ntime_total=ntime * world)
-    cell = np.deg2rad(4.0 / 3600.0)
-    x = (np.arange(npix) - npix // 2) * cell
-    ll, mm = np.meshgrid(x, x)
-    lm = np.stack([ll.ravel(), mm.ravel()], axis=1)
-    freq = synth.frequencies(nchan)
-
-    def T(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-
-    r0, r1 = D.row_shards(tidx, world)[rank]
-    g = torch.Generator(device=dev).manual_seed(100 + rank)
-    vis = torch.randn((r1 - r0, nchan, 1), dtype=torch.complex128, device=dev, generator=g)
-    flags = torch.rand((r1 - r0, nchan, 1), device=dev, generator=g) < 0.05
-    d_uvw, d_lm, d_freq = T(uvw[r0:r1]), T(lm), T(freq)
-    out = {}
-    for _ in range(2):
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record()
-        part = dft.vis_to_im(vis, d_uvw, d_lm, d_freq, flags)
-        e1.record()
-        dist.all_reduce(part, op=dist.ReduceOp.SUM)
-        e2.record()
-        torch.cuda.synchronize()
-        tt = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms, ar_ms = float(tt[0]), float(tt[1])
-    terms = float(lm.shape[0]) * uvw.shape[0] * nchan
-    out["vis_to_im_f64_allreduce"] = {
-        "Gterms_per_s": terms / (total_ms * 1e-3) / 1e9, "ms": total_ms, "allreduce_ms": ar_ms,
-        "image_bytes": int(lm.shape[0] * nchan * 8), "terms": terms,
-        "note": "%dx%d pixels, %d chan, %d rows over %d ranks; NCCL all_reduce(SUM) of the "
-                "per-rank partial image" % (npix, npix, nchan, uvw.shape[0], world)}
-    return out
