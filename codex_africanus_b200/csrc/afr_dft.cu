@@ -154,16 +154,25 @@ __device__ __forceinline__ void store_run_anchors(C2<ACC> *anch, int nck, int st
     }
 }
 
-// exp(i*phi*nu0), exp(i*phi*dnu) and the run step D = d^CH (repeated squaring) of one pair
+// FP32 runs longer than 8 channels are cut into sub-runs (see consume_run)
+constexpr int kSubRun = 16;  // channels per FP32 sub-run
+template <typename ACC, int CH>
+constexpr bool kSubRuns = sizeof(ACC) == 4 && (CH > kSubRun);
+
+// exp(i*phi*nu0), exp(i*phi*dnu) and the run step D = d^CH (repeated squaring) of one pair;
+// d8 = d^8 (an intermediate of the squaring) for the FP32 sub-runs of consume_run
 template <int CH>
 __device__ __forceinline__ void pair_anchors(double phi, double nu0, double dnu, bool need_D,
-                                             C2<double> &a, C2<double> &d, C2<double> &D) {
+                                             C2<double> &a, C2<double> &d, C2<double> &D,
+                                             C2<double> *d8 = nullptr) {
     a = cis_fast(__dmul_rn(phi, nu0));
     d = cis_fast(__dmul_rn(phi, dnu));
     D = d;
-    if (need_D) {
+    if (need_D || d8 != nullptr) {
 #pragma unroll
         for (int q = 1; q < CH; q *= 2) {
+            if (q == kSubRun && d8 != nullptr) *d8 = D;
+            if (q >= kSubRun && !need_D) break;
             const double re = D.re * D.re - D.im * D.im;
             D.im = 2.0 * D.re * D.im;
             D.re = re;
@@ -180,14 +189,25 @@ __device__ __forceinline__ void pair_anchors(double phi, double nu0, double dnu,
 // eps * (|U'_{j-1}| + |U'_{j-2}|) <= (2/3) j^3 eps (U = Chebyshev polynomials of the 2nd
 // kind), injected roundings by j^2/2 eps; measured over 2e7 steps incl. d -> 0 and d -> pi
 // the worst error after 32 channels is 1.3e-13 (oracle/../tests: uniform-vs-exact goldens),
-// three orders below the 1e-10 gate.  FP32 keeps the plain rotation (k eps growth): the
-// three-term form costs ~1e3 eps_32 = 6e-5, above the 1e-5 gate.
+// three orders below the 1e-10 gate.  In FP32 a 32-channel three-term run would cost ~1e3 eps_32 =
+// 6e-5, above the 1e-5 gate: FP32 runs are cut into sub-runs of 8 (below).
+// FP32 (complex64 / float32 outputs): the run is cut into SUB-RUNS of 8 channels.  Inside a sub-run
+// the phasor advances by the three-term form in FP32 (2 FFMA per channel sharing the coefficient
+// operand, where the plain rotation is 2 FMUL + 2 FFMA): over 7 steps its error stays below
+// ~j^2 eps_32 = 3e-6 (worst case, step angle -> 0; measured rms an order lower), inside the 1e-5
+// gate, where 31 steps would reach 6e-5.  Sub-run starts are plain FP32 rotations of the run's
+// FP64-computed anchor by d8 = d^8 (formed in FP64): 3 roundings at most.  6 -> 4.5 FP32 instructions
+// per term.
 template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int G>
 __device__ __forceinline__ void consume_run(ACC (&are)[CH][NCORR], ACC (&aim)[CH][ADJ ? 1 : NCORR],
-                                            C2<ACC> z, const C2<ACC> d, const ACC *wrow) {
+                                            C2<ACC> z, const C2<ACC> d, const ACC *wrow,
+                                            const C2<ACC> d8 = C2<ACC>{ACC(1), ACC(0)}) {
     constexpr int NV = NCORR * (WC ? 2 : 1);
-    constexpr bool kThreeTerm = sizeof(ACC) == 8 && CH > 2;
-    C2<ACC> zp = z;  // z_{j-1}
+    constexpr bool kF32 = sizeof(ACC) == 4;
+    constexpr bool kThreeTerm = CH > 2;
+    constexpr int SUB = kF32 ? kSubRun : CH;  // channels between restarts of the three-term recurrence
+    C2<ACC> zp = z;   // z_{j-1}
+    C2<ACC> zs = z;   // start of the current sub-run
     const ACC c2 = d.re + d.re;
 #pragma unroll
     for (int j = 0; j < CH; j += G) {
@@ -197,7 +217,11 @@ __device__ __forceinline__ void consume_run(ACC (&are)[CH][NCORR], ACC (&aim)[CH
         for (int g = 0; g < G; ++g) {
             accumulate<NCORR, WC, ADJ, ACC>(are[j + g], aim[j + g], z, wv + g * NV);
             if (j + g + 1 < CH) {
-                if (!kThreeTerm || j + g == 0) {
+                const int s = (j + g) % SUB;  // position inside the sub-run
+                if (s == SUB - 1) {           // next channel starts a sub-run: rotate its start by d^8
+                    zs = cmul(zs, d8);
+                    z = zs;
+                } else if (!kThreeTerm || s == 0) {
                     const C2<ACC> zn = cmul(z, d);
                     zp = z;
                     z = zn;
@@ -233,8 +257,10 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
     const long long cta_x0 = (long long)blockIdx.x * xgw;
 
     // ---- shared-memory carve-up: two {anchor, step, W} buffers + 3 y-coordinate slots
+    constexpr bool kSub = kSubRuns<ACC, CH>;  // FP32 sub-runs: the pair's d^8 rides along with d
+    constexpr int DS = kSub ? 2 : 1;
     const size_t anch_elems = (size_t)yt * nck * xgw;  // CA, or double phi[yt][xgw] (exact)
-    const size_t dstp_elems = (size_t)yt * xgw;
+    const size_t dstp_elems = (size_t)yt * xgw * DS;
     const size_t w_elems = (size_t)yt * ft * NV;
     const size_t buf_bytes = (anch_elems + dstp_elems) * sizeof(CA) + w_elems * SZ;
     double *ycs = reinterpret_cast<double *>(smem_raw + 2 * buf_bytes);  // [3][yt*3]
@@ -385,12 +411,17 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
             if (EXACT) {
                 phis[yl * xgw + px_local] = phi;
             } else {
-                C2<double> a = {0.0, 0.0}, d = {0.0, 0.0}, D = {1.0, 0.0};
-                if (live) pair_anchors<CH>(phi, nu0, dnu, nck > 1, a, d, D);
+                C2<double> a = {0.0, 0.0}, d = {0.0, 0.0}, D = {1.0, 0.0}, d8 = {0.0, 0.0};
+                if (live) pair_anchors<CH>(phi, nu0, dnu, nck > 1, a, d, D, kSub ? &d8 : nullptr);
                 CA dd;
                 dd.re = (ACC)d.re;
                 dd.im = (ACC)d.im;
-                dstp[yl * xgw + px_local] = dd;
+                dstp[(yl * xgw + px_local) * DS] = dd;
+                if (kSub) {
+                    dd.re = (ACC)d8.re;
+                    dd.im = (ACC)d8.im;
+                    dstp[(yl * xgw + px_local) * DS + 1] = dd;
+                }
                 store_run_anchors<ACC>(anch + (size_t)yl * nck * xgw + px_local, nck, xgw, a, D);
             }
         }
@@ -429,16 +460,19 @@ __global__ void __launch_bounds__(NW * 32, 1) phasor_stream_kernel(const DftPara
             // running pointers: every instruction that is not a DFMA still reads the register
             // file, whose bandwidth is what bounds the DFMA stream
             const CA *pa = anch + ck * xgw + x_local;
-            const CA *pd = dstp + x_local;
+            const CA *pd = dstp + x_local * DS;
             const ACC *pw = wt + fo * NV;
             const int w_step = ft * NV;
 #pragma unroll 1
             for (int yl = 0; yl < yt; ++yl) {
                 const CA z = *pa;
-                const CA d = *pd;
-                consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, z, d, pw);
+                const CA d = pd[0];
+                if constexpr (kSub)
+                    consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, z, d, pw, pd[1]);
+                else
+                    consume_run<NCORR, WC, ADJ, ACC, CH, G>(are, aim, z, d, pw);
                 pa += NW * 32;  // nck * xgw
-                pd += xgw;
+                pd += xgw * DS;
                 pw += w_step;
             }
         }
@@ -1030,7 +1064,8 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
 
     // y items per tile: as many (even, <= 8) as fit double-buffered in shared memory and in
     // kMaxChunks cp.async granules per thread
-    const size_t per_y = (size_t)(nck + 1) * xgw * sizeof(C2<ACC>) + (size_t)ft * NV * SZ;
+    const size_t per_y = (size_t)(nck + 1 + (kSubRuns<ACC, CH> ? 1 : 0)) * xgw * sizeof(C2<ACC>) +
+                         (size_t)ft * NV * SZ;
     // granules one thread may have in flight: 8 per thread of the whole CTA, or 16 per
     // producer thread of the warp-specialised kernel
     const long long max_chunks = use_ws ? 16LL * kProducerWarps * 32 : (long long)kMaxChunks * NT;

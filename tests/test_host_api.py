@@ -188,5 +188,7 @@ def test_bench_reference_arm_emits_one_json_line():
     for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data",
                 "config", "cpu_baseline", "e2e"):
         assert key in line, key
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the reference's own numba kernel when baseline/_ref holds it, else the oracle's C port
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline_port"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
