@@ -213,8 +213,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
     const unsigned kstep_bytes = p_bytes + q_bytes;
     const unsigned stage = kKSteps * kstep_bytes + kSrcPerStage * 64;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kNS * stage);  // full, empty, landed [kNS]
+    // a 2x2 zero matrix: the "brightness" of a source past the end of the list (the last stage of an
+    // nsrc that is not a multiple of four).  Its B slot is never copied, and 0 * (whatever shared
+    // memory held) is NaN often enough -- found by tools/fuzz_fused.py with 7 and 19 sources
+    unsigned char *zero64 = smem + kNS * stage + 16 * ((3 * kNS * sizeof(uint64_t) + 15) / 16);
     auto b_of = [&](int st) { return smem + st * stage + kKSteps * kstep_bytes; };
 
+    if (tid < 4) reinterpret_cast<double2 *>(zero64)[tid] = make_double2(0.0, 0.0);
     if (tid == 0) {
         for (int i = 0; i < kNS; ++i) {
             // full / empty: one elected lane per warp (after __syncwarp); AFR_SANITIZE=1: every lane
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
         const Cd k = {live ? kk.re : 0.0, live ? kk.im : 0.0};  // a dead item's rows become zero
         const unsigned row0 = ks * kstep_bytes + (unsigned)(2 * al * kRowBytes);
         const unsigned c0 = chunk_off(2 * sl, al), c1 = chunk_off(2 * sl + 1, al);
-        const unsigned char *bm = b_of(st) + (2 * ks + sl) * 64;
+        const unsigned char *bm = live ? b_of(st) + (2 * ks + sl) * 64 : zero64;
         // in-place panel of the raw matrix: Q (shared or a Q item) or P
         unsigned char *raw = sbase + ((shared || !is_p) ? p_bytes : 0u);
 #pragma unroll
@@ -447,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_dde_mma_kernel(const DdeMma
         xc.lmn_s = p.lmn + 3 * min(s, nsrc - 1);
         xc.uvw_a = ant_t + 3 * min(a, nant - 1);
         xc.prow = smem + st_of(sg2) * stage + ks2 * kstep_bytes + (unsigned)(2 * al * kRowBytes);
-        xc.bm = b_of(st_of(sg2)) + (2 * ks2 + sl2) * 64;
+        xc.bm = xc.live ? b_of(st_of(sg2)) + (2 * ks2 + sl2) * 64 : zero64;
         xc.cst = p.cst, xc.nu = nu, xc.p_bytes = p_bytes;
         xc.c0 = chunk_off(2 * sl2, al), xc.c1 = chunk_off(2 * sl2 + 1, al);
         xc.rowa = (unsigned)((al & 1) * kRowBytes), xc.rowb = (unsigned)(((al & 1) ^ 1) * kRowBytes);
@@ -586,7 +591,8 @@ __global__ void baseline_map_kernel(const int32_t *time_index, const int32_t *an
 }  // namespace
 
 size_t dde_mma_smem_bytes(int ni, int nj) {
-    return kNS * ((size_t)kKSteps * (ni + nj) * 16 * kRowBytes + kSrcPerStage * 64) + 3 * kNS * sizeof(uint64_t);
+    return kNS * ((size_t)kKSteps * (ni + nj) * 16 * kRowBytes + kSrcPerStage * 64) +
+           16 * ((3 * kNS * sizeof(uint64_t) + 15) / 16) + 64;  // stages | mbarriers | zero matrix
 }
 
 int launch_baseline_map(const int32_t *time_index, const int32_t *ant1, const int32_t *ant2, int64_t nrow,

@@ -654,6 +654,39 @@ def test_fused_predict_vis_beam_chunks(b200, oracle):
 
 
 
+def test_fused_dde_mma_ragged_source_counts(b200, oracle):
+    """Source counts that are not a multiple of the GEMM kernel's four sources per stage: the slots of
+    the missing sources must contribute exact zeros whatever shared memory held before (found by
+    tools/fuzz_fused.py: the brightness slot of a missing source is never copied, and 0 x stale NaN
+    poisoned the sum).  Shared memory is first filled with NaN by a DFT over a NaN image."""
+    from codex_africanus_b200 import _lib
+    rng = np.random.default_rng(99)
+    na, ntime, nchan = 12, 2, 5
+    a1, a2 = np.triu_indices(na, 1)
+    ant1, ant2 = np.tile(a1, ntime), np.tile(a2, ntime)
+    ti = np.repeat(np.arange(ntime), a1.size)
+    antpos = rng.standard_normal((ntime, na, 3)) * 1500.0
+    uvw = antpos[ti, ant1] - antpos[ti, ant2]
+    freq = np.linspace(0.856e9, 1.712e9, nchan)
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    nan_img = np.full((64, 256, 4), np.nan)
+    for nsrc in (1, 2, 3, 5, 6, 7, 19):
+        lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+        bright = rc((nsrc, nchan, 2, 2))
+        dde = 1.0 + 0.2 * rc((nsrc, ntime, na, nchan, 2, 2))
+        dde_b = 1.0 + 0.2 * rc((nsrc, ntime, na, nchan, 2, 2))
+        for d2 in (dde, dde_b):
+            b200.dft.im_to_vis(nan_img, rng.standard_normal((148 * 64, 3)), rng.uniform(-.01, .01, (64, 2)),
+                               np.linspace(1e9, 2e9, 256))
+            got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, d2)
+            assert _lib.lib().afr_last_fused_path() == 6
+            assert np.all(np.isfinite(got))
+            assert_c128_close(got, oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, d2))
+
+
 def test_fused_dde_ws_many_antennas(b200, oracle, monkeypatch):
     """140 antennas (9730 baselines): the three-stage antenna tile of the 512-row x 4-channel CTA
     does not fit in shared memory; antenna mode takes the 2048-row x 1-channel tile, random uvw the

@@ -1,4 +1,5 @@
-"""Randomised parity sweep of fused_predict_vis (DDE kernels: antenna-phasor / per-row / tiled /
+"""Randomised parity sweep of fused_predict_vis (DDE kernels: antenna-mode DMMA GEMM incl. multi-pass
+panels, swapped antenna pairs and duplicate baselines, scalar antenna-phasor / per-row / tiled /
 gather paths) against the CPU oracle.  usage: fuzz_fused.py [ncases] [seed]"""
 import os, sys
 import numpy as np
@@ -12,7 +13,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bad = 0; paths = {}
 for case in range(n):
-    na = int(rng.choice([2, 3, 7, 12, 33, 40])); ntime = int(rng.choice([1, 2, 5]))
+    na = int(rng.choice([2, 3, 7, 12, 33, 40, 64, 70, 130], p=[.14, .14, .14, .14, .14, .12, .06, .06, .06]))
+    ntime = int(rng.choice([1, 2, 5])) if na < 64 else int(rng.choice([1, 2]))
     nchan = int(rng.choice([1, 3, 4, 5, 16, 37])); nsrc = int(rng.choice([1, 2, 7, 19]))
     a1, a2 = np.triu_indices(na, 1)
     keep = [np.sort(rng.choice(a1.size, size=max(1, a1.size - int(rng.integers(0, 3))), replace=False)) for _ in range(ntime)]
@@ -21,6 +23,10 @@ for case in range(n):
     if rng.random() < 0.3:  # swap some antenna pairs (a1 > a2 rows)
         sw = rng.random(ant1.size) < 0.3
         ant1, ant2 = np.where(sw, ant2, ant1), np.where(sw, ant1, ant2)
+    if rng.random() < 0.1 and ant1.size > 3:  # a baseline listed twice in one timestep: no (t, a1, a2) -> row map
+        dup = rng.integers(0, ant1.size, 2)
+        order = np.sort(np.concatenate([np.arange(ant1.size), dup]))
+        ant1, ant2, ti = ant1[order], ant2[order], ti[order]
     antpos = rng.standard_normal((ntime, na, 3)) * 1500.0
     consistent = rng.random() < 0.6
     uvw = antpos[ti, ant1] - antpos[ti, ant2] if consistent else rng.standard_normal((ti.size, 3)) * 1500.0

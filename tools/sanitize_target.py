@@ -77,4 +77,28 @@ rime.fused_predict_vis_stokes(lm, uvw_a, freq, stokes, spi, rf, ti, ant1, ant2, 
 for _, blk in rime.stream_predict_vis_stokes(lm, uvw_a, freq, stokes, spi, rf, ti, ant1, ant2, None, None, die,
                                              None, die, rows_per_block=a1.size):
     blk.sum()
+# plane-interpolated beam kernel (needs >= 64 channels), rows with per-channel pointing errors
+# falling back to the element path, out-of-band channels, the feed-rotation epilogue
+f80 = np.linspace(0.75e9, 1.85e9, 80)
+pe80 = np.zeros((ntime, na, 80, 2)); pe80[1] = rng.uniform(-1e-3, 1e-3, (na, 80, 2))
+for bm in (beam, beam[..., 0, :], beam[..., 0, :1]):
+    rime.beam_cube_dde(bm, np.array([[-0.03, 0.03], [-0.03, 0.03]]), np.linspace(0.8e9, 1.8e9, 5), lm, pa, pe80,
+                       np.ones((na, 80, 2)), f80)
+rime.beam_cube_dde_rotated(beam.astype(np.complex64), np.array([[-0.03, 0.03], [-0.03, 0.03]]),
+                           np.linspace(0.8e9, 1.8e9, 5), lm, pa, pe80, np.ones((na, 80, 2)), f80,
+                           rime.feed_rotation(pa, "linear").astype(np.complex64))
+# antenna-mode GEMM kernel over several panels (70 antennas: 9 tile rows in panels of 6), E1 != E2,
+# an odd number of sources, rows with antenna1 > antenna2
+na_m, ns_m, nc_m = 70, 5, 3
+m1, m2 = np.triu_indices(na_m, 1)
+m1, m2 = np.where(np.arange(m1.size) % 7 == 0, m2, m1), np.where(np.arange(m1.size) % 7 == 0, m1, m2)
+pos_m = rng.standard_normal((1, na_m, 3)) * 1500.0
+uvw_m = pos_m[0, m1] - pos_m[0, m2]
+dm1, dm2 = rc((ns_m, 1, na_m, nc_m, 2, 2)), rc((ns_m, 1, na_m, nc_m, 2, 2))
+rime.fused_predict_vis(lm[:ns_m], uvw_m, fw, rc((ns_m, nc_m, 2, 2)), np.zeros(m1.size, int), m1, m2, dm1, dm2)
+rime.fused_predict_vis(lm[:ns_m], uvw_m, fw, rc((ns_m, nc_m, 2, 2)), np.zeros(m1.size, int), m1, m2, dm1, dm1)
+# padded image grid beyond the unit disc (NaN sources muted / poisoned), im_to_vis
+lm_big = np.stack(np.meshgrid(np.linspace(-1.2, 1.2, 5), np.linspace(-1.2, 1.2, 5)), -1).reshape(-1, 2)
+img_big = rng.standard_normal((25, nchan, 2)); img_big[(lm_big ** 2).sum(1) >= 1] = 0; img_big[0, 3, 1] = 1.0
+dft.im_to_vis(img_big, uvw, lm_big, freq)
 print("sanitize target done")
