@@ -29,9 +29,9 @@ def _free_port():
     return port
 
 
-def _problem():
+def _problem(ntime=7):
     rng = np.random.default_rng(77)
-    na, ntime, nchan, nsrc = 12, 7, 96, 33
+    na, nchan, nsrc = 12, 96, 33
     a1, a2 = np.triu_indices(na, 1)
     ant1, ant2 = np.tile(a1, ntime).astype(np.int32), np.tile(a2, ntime).astype(np.int32)
     ti = (np.repeat(np.arange(ntime), a1.size) + 5).astype(np.int32)
@@ -51,7 +51,7 @@ def _problem():
                 die=np.eye(2) + 0.1 * rc((ntime, na, nchan, 2, 2)), bvis=rc((nrow, nchan, 2, 2)))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, ntime):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -63,13 +63,14 @@ def _worker(rank, world, port, out_dir):
     from codex_africanus_b200 import _lib
     from codex_africanus_b200 import distributed as D
 
-    p = _problem()
+    p = _problem(ntime)
     vis, _ = D.sharded_im_to_vis(p["image"], p["uvw"], p["lm"], p["freq"], p["ti"], gather=True)
     img = D.sharded_vis_to_im(p["vis"], p["uvw"], p["lm"], p["freq"], p["flags"], p["ti"])
     pred, _ = D.sharded_fused_predict_vis(p["lm"], p["uvw"], p["freq"], p["bright"], p["ti"], p["ant1"],
                                           p["ant2"], p["dde"], p["dde"], p["die"], p["bvis"], p["die"],
                                           gather=True)
-    path = _lib.lib().afr_last_fused_path()
+    r0, r1 = D.row_shards(p["ti"], world)[rank]
+    path = _lib.lib().afr_last_fused_path() if r1 > r0 else -1  # -1: this rank's shard is empty
     # device-resident variant: torch CUDA tensors in, the all_reduce runs on the kernel's output
     dev = torch.device("cuda", rank)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
@@ -80,8 +81,10 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_nccl_sharded_paths_match_one_gpu_and_oracle(tmp_path, oracle, world):
+@pytest.mark.parametrize("world,ntime", [(2, 7), (2, 1), (4, 7), (8, 7)])
+def test_nccl_sharded_paths_match_one_gpu_and_oracle(tmp_path, oracle, world, ntime):
+    """7 timesteps over 2 / 4 / 8 ranks (at 8 ranks one shard is empty); 1 timestep over 2 ranks
+    (rank 0 empty): an empty shard contributes nothing and must not upset the collectives."""
     import torch
     import torch.multiprocessing as mp
 
@@ -91,8 +94,8 @@ def test_nccl_sharded_paths_match_one_gpu_and_oracle(tmp_path, oracle, world):
 
     from codex_africanus_b200 import dft, rime
 
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    p = _problem()
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), ntime), nprocs=world, join=True)
+    p = _problem(ntime)
     one_vis = dft.im_to_vis(p["image"], p["uvw"], p["lm"], p["freq"])
     one_img = dft.vis_to_im(p["vis"], p["uvw"], p["lm"], p["freq"], p["flags"])
     one_pred = rime.fused_predict_vis(p["lm"], p["uvw"], p["freq"], p["bright"], p["ti"], p["ant1"], p["ant2"],
@@ -102,7 +105,7 @@ def test_nccl_sharded_paths_match_one_gpu_and_oracle(tmp_path, oracle, world):
                                     p["dde"], p["dde"], p["die"], p["bvis"], p["die"])
     for rank in range(world):
         got = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
-        assert int(got["path"]) == 6  # every shard ran the antenna-mode GEMM kernel
+        assert int(got["path"]) in (6, -1)  # every non-empty shard ran the antenna-mode GEMM kernel
         # rows are independent: the gathered blocks are the one-GPU rows (same kernels, same order
         # of the source sum); the image differs by the summation order over row shards only
         assert_c128_close(got["vis"], one_vis, rtol=1e-13)
