@@ -554,11 +554,13 @@ constexpr int kProducerWarps = 4;
 // NCKT: channel runs per CTA as a compile-time constant (0 = runtime).  NCKT == NWC ("full
 // width"): the CTA's 16 consumer warps are 16 channel runs of the same 32 owners (nck == NWC,
 // the shape of every launch with >= 16 * CH channels): strides become immediates.
+// PW producer warps: 4, or 8 for the adjoint with few channels per CTA, where the anchor work per
+// (owner, streamed item) pair is spread over so few terms that four producer warps fall behind.
 template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NWC, bool EXACT, int CREGS, int PREGS,
-          int NCKT>
-__global__ void __launch_bounds__((NWC + kProducerWarps) * 32, 1)
+          int NCKT, int PW = kProducerWarps>
+__global__ void __launch_bounds__((NWC + PW) * 32, 1)
     phasor_stream_ws_kernel(const DftParams p) {
-    constexpr int NTP = kProducerWarps * 32;  // producer threads
+    constexpr int NTP = PW * 32;  // producer threads
     constexpr int NV = NCORR * (WC ? 2 : 1);
     constexpr int G = (NV * (int)sizeof(ACC) >= 16) ? 1 : 16 / (NV * (int)sizeof(ACC));
     constexpr int SZ = (int)sizeof(ACC);
@@ -1035,7 +1037,12 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     const bool kPreferWS = (!ADJ || bulk_ok) && nck_ws * CH * kDpPerTerm >= 500;
     // FP32 variants gain nothing from it (measured 3.10 vs 3.07 Tterm/s): they are bound by
     // the register-file bandwidth of three-operand FFMAs, not by the anchor work
-    const bool use_ws = (sizeof(ACC) == 8) && (ws_env ? atoi(ws_env) != 0 : kPreferWS);
+    // Below the crossover the ADJOINT still gains from dedicated producers if there are eight producer
+    // warps (24 warps: 512 x 88 + 256 x 64 registers): configs[4] has 64 channels.  AFR_WS8=0 disables.
+    const char *ws8_env = getenv("AFR_WS8");
+    const bool use_ws8 = ADJ && sizeof(ACC) == 8 && bulk_ok && !exact && !ws_env && !kPreferWS && nck_ws <= NW / 2 &&
+                         nck_ws * CH >= 32 && !(ws8_env && atoi(ws8_env) == 0);
+    const bool use_ws = (sizeof(ACC) == 8) && ((ws_env ? atoi(ws_env) != 0 : kPreferWS) || use_ws8);
     // channel runs per CTA: the single-role kernel keeps nck <= NW/2 so that every thread
     // owns an (x,y) pair per tile; dedicated producers do not need that, and anchors are
     // cheaper per term the more channels a CTA covers (measured +9 % at 16 runs vs 8)
@@ -1068,7 +1075,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
                          (size_t)ft * NV * SZ;
     // granules one thread may have in flight: 8 per thread of the whole CTA, or 16 per
     // producer thread of the warp-specialised kernel
-    const long long max_chunks = use_ws ? 16LL * kProducerWarps * 32 : (long long)kMaxChunks * NT;
+    const long long max_chunks = use_ws ? 16LL * (use_ws8 ? 8 : kProducerWarps) * 32 : (long long)kMaxChunks * NT;
     int yt = 8;
     while (yt > 2 && (2 * yt * per_y > 200 * 1024 || (long long)yt * row_chunks > max_chunks))
         yt -= 2;
@@ -1116,7 +1123,8 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     }
 
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nsplit);
-    note_dft_path((use_ws ? 1 : 0) | (exact ? 2 : 0) | (p.bulk ? 4 : 0) | (sizeof(ACC) == 4 ? 8 : 0) | (nck << 8) |
+    note_dft_path((use_ws ? 1 : 0) | (exact ? 2 : 0) | (p.bulk ? 4 : 0) | (sizeof(ACC) == 4 ? 8 : 0) |
+                  (use_ws8 ? 16 : 0) | (nck << 8) |
                   ((int)nsplit << 16));
     if constexpr (sizeof(ACC) == 8) {
       if (use_ws) {
@@ -1139,7 +1147,22 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
         int rc;
         bool launched = false;
         rc = 0;
-        if (exact) {
+        if constexpr (ADJ) {
+            if (use_ws8) {
+                constexpr int PW8 = 8, C8 = 88, P8 = 64;
+                auto kern = phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, C8, P8, 0, PW8>;
+                const int threads8 = (NW + PW8) * 32;
+                cudaFuncAttributes attr;
+                AFR_CUDA_OK(cudaFuncGetAttributes(&attr, kern));
+                AFR_REQUIRE(threads8 * attr.numRegs >= NW * 32 * C8 + PW8 * 32 * P8,
+                            "phasor_stream_ws (8 producer warps): launch-time register pool too small");
+                AFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+                kern<<<grid, threads8, smem_ws, stream>>>(p);
+                launched = true;
+            }
+        }
+        if (launched) {
+        } else if (exact) {
             rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, true, CREGS, PREGS, 0>);
             launched = true;
         } else if (nck == NW && yt == 8) {

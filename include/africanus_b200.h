@@ -71,7 +71,8 @@ int afr_last_fused_path(void);
 /* Which schedule of the phasor-stream kernel the last afr_im_to_vis / afr_vis_to_im / point-source
  * afr_predict_fused / afr_wsclean_predict launch of this host thread used (its last correlation
  * block): bit 0 warp-specialised (16 consumer + 4 producer warps), bit 1 one sincos per term
- * (non-equispaced channels), bit 2 W tile by TMA bulk copies, bit 3 FP32 accumulators,
+ * (non-equispaced channels), bit 2 W tile by TMA bulk copies, bit 3 FP32 accumulators, bit 4 eight
+ * producer warps (few-channel adjoint),
  * bits 8-15 channel runs per CTA, bits 16-31 slices of the streamed axis.  Environment overrides
  * (AFR_WS, AFR_SANITIZE) show up here, so a benchmark can report the path it measured. */
 int afr_last_dft_path(void);
