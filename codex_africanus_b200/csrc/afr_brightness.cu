@@ -104,37 +104,83 @@ __global__ void convert_kernel(const double *__restrict__ in, long long n, int n
     }
 }
 
+// spectral_value with the logarithm of nu/rf hoisted out of the polarisation loop: the kernel below
+// is thread <-> (source, chan), and pow(ratio, spi) per (polarisation, index) made it FP64-pipe bound
+// (4 pow = ~600 FP64 instructions per 64 bytes stored: 1.36 TB/s).  x**y = exp(y*ln x) with one ln per
+// thread costs a quarter of that; |y*ln x| stays O(1) for spectral indices, so the result is within a
+// few ulp of pow's (the parity gate is 1e-10).  Non-positive or non-finite ratios keep pow's own
+// special cases.
+__device__ __forceinline__ double spectral_value_ln(int base, double st, const double *spi_sp, long long pol_stride,
+                                                    int nspi, double ratio, double ln_ratio, double lg_ratio,
+                                                    bool regular) {
+    if (base == 0) {
+        double v = st;
+        if (regular)
+            for (int i = 0; i < nspi; ++i) v = __dmul_rn(v, exp(__dmul_rn(spi_sp[i * pol_stride], ln_ratio)));
+        else
+            for (int i = 0; i < nspi; ++i) v = __dmul_rn(v, pow(ratio, spi_sp[i * pol_stride]));
+        return v;
+    }
+    const double lr = base == 1 ? ln_ratio : lg_ratio;
+    double acc = 0.0;
+    for (int i = 0; i < nspi; ++i) acc = __dadd_rn(acc, __dmul_rn(spi_sp[i * pol_stride], ipow(lr, i + 1)));
+    return __dmul_rn(st, base == 1 ? exp(acc) : pow(10.0, acc));
+}
+
 // stokes (nsrc, npol) -> brightness (nsrc, nchan, nout) complex128 (or complex64): the spectral
-// model of each polarisation in registers, then the schema mapping.  Thread per (source, chan).
-template <typename OUT2>
-__global__ void stokes_brightness_kernel(const double *__restrict__ stokes, const double *__restrict__ spi,
-                                         const double *__restrict__ ref_freq, const double *__restrict__ freq,
-                                         Bases bases, Mapping map, long long nsrc, int nspi, int npol,
-                                         long long nchan, int nout, OUT2 *__restrict__ out) {
+// model of each polarisation in registers, then the schema mapping.  Thread per (source, chan);
+// a CTA's 256 x nout results are staged in shared memory (STAGED: nout <= 4) and leave as
+// contiguous 16-byte stores -- per-thread stores would be nout segments at a 16*nout-byte stride.
+constexpr int kSbThreads = 256;
+template <typename OUT2, bool STAGED>
+__global__ void __launch_bounds__(kSbThreads)
+stokes_brightness_kernel(const double *__restrict__ stokes, const double *__restrict__ spi,
+                         const double *__restrict__ ref_freq, const double *__restrict__ freq, Bases bases,
+                         Mapping map, long long nsrc, int nspi, int npol, long long nchan, int nout,
+                         int need_lg, OUT2 *__restrict__ out) {
+    __shared__ OUT2 stage[STAGED ? kSbThreads * 4 : 1];
     const long long total = nsrc * nchan;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long s = i / nchan, f = i - s * nchan;
-        const double nu = freq[f], rf = ref_freq[s];
-        double sm[4];
+    const long long nblk = (total + kSbThreads - 1) / kSbThreads;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long long i0 = blk * kSbThreads, i = i0 + threadIdx.x;
+        if (i < total) {
+            const long long s = i / nchan, f = i - s * nchan;
+            const double nu = freq[f], rf = ref_freq[s];
+            const double ratio = nu / rf;
+            const bool regular = ratio > 0.0 && ratio < 1.7976931348623157e308;
+            const double ln_ratio = log(ratio);
+            const double lg_ratio = need_lg ? log10(ratio) : 0.0;
+            double sm[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
-            sm[p] = p < npol ? spectral_value(bases.b[p], stokes[s * npol + p], spi + (s * nspi) * npol + p,
-                                              npol, nspi, nu, rf)
-                             : 0.0;
-        for (int o = 0; o < nout; ++o) {
-            const int s1 = map.s1[o], s2 = map.s2[o];
-            double2 a = make_double2(0.0, 0.0), b = a;
+            for (int p = 0; p < 4; ++p)
+                sm[p] = p < npol ? spectral_value_ln(bases.b[p], stokes[s * npol + p], spi + (s * nspi) * npol + p,
+                                                     npol, nspi, ratio, ln_ratio, lg_ratio, regular)
+                                 : 0.0;
+            for (int o = 0; o < nout; ++o) {
+                const int s1 = map.s1[o], s2 = map.s2[o];
+                double2 a = make_double2(0.0, 0.0), b = a;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {  // register select (no local-memory indexing)
-                if (s1 == p) a.x = sm[p];
-                if (s2 == p) b.x = sm[p];
+                for (int p = 0; p < 4; ++p) {  // register select (no local-memory indexing)
+                    if (s1 == p) a.x = sm[p];
+                    if (s2 == p) b.x = sm[p];
+                }
+                const double2 v = convert_op(map.op[o], a, b);
+                OUT2 w;
+                w.x = v.x;
+                w.y = v.y;
+                if (STAGED)
+                    stage[threadIdx.x * nout + o] = w;
+                else
+                    out[i * nout + o] = w;
             }
-            const double2 v = convert_op(map.op[o], a, b);
-            OUT2 w;
-            w.x = v.x;
-            w.y = v.y;
-            out[i * nout + o] = w;
+        }
+        if (STAGED) {
+            __syncthreads();
+            const long long left = total - i0;
+            const int n = (int)(left < kSbThreads ? left : kSbThreads) * nout;
+            OUT2 *dst = out + i0 * nout;
+            for (int j = threadIdx.x; j < n; j += kSbThreads) dst[j] = stage[j];
+            __syncthreads();
         }
     }
 }
@@ -220,12 +266,20 @@ extern "C" int afr_stokes_brightness(const double *stokes, const double *spi, co
     if (int rc = fill_mapping(src1, src2, op, npol, nout, m)) return rc;
     const long long total = nsrc * nchan;
     if (total == 0) return 0;
-    if (is_c64)
-        stokes_brightness_kernel<float2><<<grid_for(total), 256, 0, stream>>>(
-            stokes, spi, ref_freq, freq, b, m, nsrc, (int)nspi, (int)npol, nchan, (int)nout, (float2 *)out);
-    else
-        stokes_brightness_kernel<double2><<<grid_for(total), 256, 0, stream>>>(
-            stokes, spi, ref_freq, freq, b, m, nsrc, (int)nspi, (int)npol, nchan, (int)nout, (double2 *)out);
+    int need_lg = 0;
+    for (int64_t p = 0; p < npol; ++p) need_lg |= base[p] == 2;
+    const long long nblk = (total + kSbThreads - 1) / kSbThreads;
+    const long long cap = 8LL * sm_count();
+    const unsigned grid = (unsigned)(nblk < cap ? nblk : cap);
+#define AFR_SB_LAUNCH(T, STAGED)                                                                             \
+    stokes_brightness_kernel<T, STAGED><<<grid, kSbThreads, 0, stream>>>(                                    \
+        stokes, spi, ref_freq, freq, b, m, nsrc, (int)nspi, (int)npol, nchan, (int)nout, need_lg, (T *)out)
+    if (is_c64) {
+        if (nout <= 4) AFR_SB_LAUNCH(float2, true); else AFR_SB_LAUNCH(float2, false);
+    } else {
+        if (nout <= 4) AFR_SB_LAUNCH(double2, true); else AFR_SB_LAUNCH(double2, false);
+    }
+#undef AFR_SB_LAUNCH
     AFR_LAUNCH_OK();
     return 0;
 }

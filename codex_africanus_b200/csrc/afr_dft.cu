@@ -58,6 +58,8 @@ struct DftParams {
     int row_chunks_log2;  // log2(granules per W tile row)
     int bulk;             // warp-specialised kernel: W tile by TMA bulk copies
     int arrive_all;       // every consumer lane arrives on the "empty" mbarrier (AFR_SANITIZE=1)
+    int one;              // 1 (opaque to the compiler: trip count of the scalar-burst blocks, see the MMA consumers)
+    int ablate;           // diagnostics (AFR_POINT_MMA_ABLATE, wrong results): 1 no anchor maths, 2 no recurrence, 4 no DMMA
 };
 
 __device__ __forceinline__ void cp_async(unsigned dst, const void *src, int granule, int src_bytes) {
@@ -557,9 +559,12 @@ constexpr int kProducerWarps = 4;
 // PW producer warps: 4, or 8 for the adjoint with few channels per CTA, where the anchor work per
 // (owner, streamed item) pair is spread over so few terms that four producer warps fall behind.
 template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NWC, bool EXACT, int CREGS, int PREGS,
-          int NCKT, int PW = kProducerWarps>
+          int NCKT, int PW = kProducerWarps, bool MMA = false>
 __global__ void __launch_bounds__((NWC + PW) * 32, 1)
     phasor_stream_ws_kernel(const DftParams p) {
+    static_assert(!MMA || (NCORR == 4 && WC && !ADJ && sizeof(ACC) == 8 && !EXACT && (CH == 4 || CH == 8 || CH == 16)),
+                  "tensor-pipe consumers: 2x2 complex W, forward, FP64, equispaced channels");
+    constexpr int RG = MMA ? 16 / CH : 4;  // tensor-pipe consumers: row groups of 8 owners per warp
     constexpr int NTP = PW * 32;  // producer threads
     constexpr int NV = NCORR * (WC ? 2 : 1);
     constexpr int G = (NV * (int)sizeof(ACC) >= 16) ? 1 : 16 / (NV * (int)sizeof(ACC));
@@ -571,16 +576,22 @@ __global__ void __launch_bounds__((NWC + PW) * 32, 1)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr bool FULLW = NCKT == NWC;
-    constexpr bool kUnrollTile = FULLW && !ADJ && NCORR >= 2;  // see the consumer loop
+    constexpr bool kUnrollTile = FULLW && !ADJ && NCORR >= 2 && !MMA;  // see the consumer loop
     const int nck = NCKT ? NCKT : p.nck, yt = kUnrollTile ? 8 : p.yt;
-    const int xgw = (NWC / nck) * 32;
+    const int xgw = (NWC / nck) * (MMA ? 8 * RG : 32);
     const int ft = nck * CH;
     const int cta_f0 = blockIdx.y * ft;
     const long long cta_x0 = (long long)blockIdx.x * xgw;
 
-    const size_t anch_elems = (size_t)yt * nck * xgw;
-    const size_t dstp_elems = (size_t)yt * xgw;
-    const size_t w_elems = (size_t)yt * ft * NV;
+    // Tensor-pipe consumers read the anchors / W of TWO streamed items per fragment load: their
+    // per-item pitches get 32 bytes of padding, so that the two items fall into different bank
+    // groups (unpadded, the pitches are multiples of 128 bytes: two-way conflicts on every load).
+    const int apitch = nck * xgw + (MMA ? 2 : 0);  // CA per streamed item
+    const int dpitch = xgw + (MMA ? 2 : 0);        // CA per streamed item
+    const int wpitch = ft * NV + (MMA ? 4 : 0);    // ACC per streamed item
+    const size_t anch_elems = (size_t)yt * apitch;
+    const size_t dstp_elems = (size_t)yt * dpitch;
+    const size_t w_elems = (size_t)yt * wpitch;
     const size_t buf_bytes = (anch_elems + dstp_elems) * sizeof(CA) + w_elems * SZ;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * buf_bytes);  // full[2], empty[2], wland[2]
     double *fq = reinterpret_cast<double *>(bars + 6);                        // [ft] (exact)
@@ -655,7 +666,7 @@ __global__ void __launch_bounds__((NWC + PW) * 32, 1)
                 // accounted on the tile's "full" barrier (expect_tx now, this thread's arrival
                 // after its anchors), so no producer thread spends instructions on the copy
                 const int rows_valid = (int)min((long long)yt, ye - y0);
-                const int row_smem = ft * NV * SZ;
+                const int row_smem = wpitch * SZ;
                 const bool edit = ADJ && p.anyflag != nullptr;
                 if (ptid == 0) {
                     uint64_t *landed = edit ? &bars[4 + b] : &bars[b];
@@ -688,7 +699,7 @@ __global__ void __launch_bounds__((NWC + PW) * 32, 1)
                 }
                 // rows past the end of the slice must read as zero (their anchors are zero,
                 // but 0 * stale NaN would poison the sum)
-                for (int idx = rows_valid * ft * NV + ptid; idx < yt * ft * NV; idx += NTP) wt[idx] = ACC(0);
+                for (int idx = rows_valid * wpitch + ptid; idx < yt * wpitch; idx += NTP) wt[idx] = ACC(0);
             } else if (p.fast) {
                 const int rows_valid = (int)min((long long)yt, ye - y0);
                 const char *src_tile = w_cta + y0 * row_pitch;
@@ -733,7 +744,7 @@ __global__ void __launch_bounds__((NWC + PW) * 32, 1)
             CA *anch = anch_of(b);
             CA *dstp = dstp_of(b);
             double *phis = reinterpret_cast<double *>(anch);
-            for (int q0 = ptid; q0 < npairs; q0 += 2 * NTP) {
+            for (int q0 = ptid; q0 < ((MMA && (p.ablate & 1)) ? 0 : npairs); q0 += 2 * NTP) {
                 double phi[2];
                 bool live[2];
 #pragma unroll
@@ -766,10 +777,15 @@ __global__ void __launch_bounds__((NWC + PW) * 32, 1)
                             CA dd;
                             dd.re = (ACC)d[i].re;
                             dd.im = (ACC)d[i].im;
-                            dstp[q] = dd;
-                            // anchors of pair (yl, xo) start at (yl * nck) * xgw + xo
-                            store_run_anchors<ACC>(anch + (((q >> lxgw) * nck) << lxgw) + (q & (xgw - 1)),
-                                                   nck, xgw, a[i], D[i]);
+                            if constexpr (MMA) {
+                                dstp[(q >> lxgw) * dpitch + (q & (xgw - 1))] = dd;
+                                store_run_anchors<ACC>(anch + (q >> lxgw) * apitch + (q & (xgw - 1)), nck, xgw, a[i], D[i]);
+                            } else {
+                                dstp[q] = dd;
+                                // anchors of pair (yl, xo) start at (yl * nck) * xgw + xo
+                                store_run_anchors<ACC>(anch + (((q >> lxgw) * nck) << lxgw) + (q & (xgw - 1)),
+                                                       nck, xgw, a[i], D[i]);
+                            }
                         }
                     }
                 }
@@ -817,6 +833,123 @@ __global__ void __launch_bounds__((NWC + PW) * 32, 1)
     const int x_local = (warp / nck) * 32 + lane;
     const long long x = cta_x0 + x_local;
     const int fo = ck * CH;
+
+    if constexpr (MMA) {
+        // ---- consumers on the FP64 tensor pipe (2x2 complex W, forward).  For one channel the source
+        // sum acc[row][c] += z[row,s] W[s,c] is a complex (rows x sources) x (sources x 4) product; as a
+        // real GEMM with the phasor parts as the k index it is exactly the DMMA shape m8n8k4:
+        //   A[row][k = 2 s + part] = part ? Im z : Re z                       (8 rows x 2 sources)
+        //   B[k][n = 2 c + opart]  = (part ^ opart) ? (+-)Im W[s,c] : Re W[s,c]   (minus for part = 1, opart = 0)
+        //   C[row][n] = Re / Im acc[row][c]
+        // -- all 256 FMAs of the instruction are useful (16 terms x 16 real FMAs), where the scalar loop
+        // spends 16 DFMA per term on a pipe that a DFMA with three distinct register operands only
+        // fills to two thirds and 4 broadcast LDS.128 per term (ncu: l1tex 79 %).  Each lane
+        // advances ONE real component of z by the three-term recurrence (re and im share the
+        // coefficient): at most one DFMA per DMMA, and one double of W per k-step and channel, shared
+        // by the warp's RG row groups.
+        const int grp = lane >> 2, kq = lane & 3;
+        const int s_local = kq >> 1, part = kq & 1;
+        const int opart = grp & 1, cb = grp >> 1;
+        const int comp = part ^ opart;
+        const int bflip = (part & (opart ^ 1)) ? (int)0x80000000 : 0;
+        const int xrow0 = (warp / nck) * (8 * RG);
+        const int tflip = part ? 0 : (int)0x80000000;
+        const bool no_dmma = (p.ablate & 4) != 0;
+        double acc[RG][CH][2];
+#pragma unroll
+        for (int g = 0; g < RG; ++g)
+#pragma unroll
+            for (int j = 0; j < CH; ++j) acc[g][j][0] = acc[g][j][1] = 0.0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int b = t & 1;
+            mbar_wait(&bars[b], (t >> 1) & 1);
+            const CA *pa = anch_of(b) + (size_t)s_local * apitch + ck * xgw + xrow0 + grp;
+            const CA *pd = dstp_of(b) + (size_t)s_local * dpitch + xrow0 + grp;
+            const double *pw = reinterpret_cast<const double *>(w_of(b)) + (size_t)s_local * wpitch + fo * NV + 2 * cb + comp;
+            auto bload = [&](int j) {
+                const double bw = pw[j * NV];
+                return __hiloint2double(__double2hiint(bw) ^ bflip, __double2loint(bw));
+            };
+            auto mma = [&](double (&c)[2], double a, double bw) {
+                if (!no_dmma) asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c[0]), "+d"(c[1])
+                             : "d"(a), "d"(bw));
+            };
+#pragma unroll 1
+            for (int ys = 0; ys < yt; ys += 2) {
+                // Scalar FP64 instructions are issued in dense bursts of independent instructions, not
+                // sprinkled between the DMMAs: every DMMA -> DFMA -> DMMA switch of the FP64 pipe costs
+                // ~8 cycles on top of the 2.2 per DFMA (tools/dmma_mix_microbench.cu: 1 DFMA between
+                // DMMAs costs 10 cycles, 16 in a row 2.8 each).
+                double xm[RG], xc[RG], c2[RG];  // z_{j-1}, z_j (this lane's part), 2 Re d
+                CA z[RG], d[RG];
+#pragma unroll
+                for (int g = 0; g < RG; ++g) z[g] = pa[8 * g], d[g] = pd[8 * g];
+#pragma unroll
+                for (int g = 0; g < RG; ++g) xm[g] = z[g].re, xc[g] = z[g].im, c2[g] = d[g].re;  // (ablation only)
+                double bw0 = bload(0), bw1 = bload(1);
+                // burst 1: z_1 = z_0 d (this lane's part: re = z.re d.re - z.im d.im, im = z.re d.im + z.im d.re)
+                // (each burst is the body of a loop that runs once, trip count opaque to the compiler:
+                // ptxas schedules inside basic blocks and otherwise spreads the DFMAs between the DMMAs)
+#pragma unroll 1
+                for (int once = 0; once < ((p.ablate & 2) ? 0 : p.one); ++once) {
+                    double tq[RG];
+#pragma unroll
+                    for (int g = 0; g < RG; ++g) tq[g] = z[g].im * (part ? d[g].re : d[g].im);
+#pragma unroll
+                    for (int g = 0; g < RG; ++g) c2[g] = d[g].re + d[g].re;
+#pragma unroll
+                    for (int g = 0; g < RG; ++g) {
+                        const double t = __hiloint2double(__double2hiint(tq[g]) ^ tflip, __double2loint(tq[g]));
+                        xm[g] = part ? z[g].im : z[g].re;
+                        xc[g] = fma(z[g].re, part ? d[g].im : d[g].re, t);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < RG; ++g) mma(acc[g][0], xm[g], bw0);
+#pragma unroll
+                for (int g = 0; g < RG; ++g) mma(acc[g][1], xc[g], bw1);
+#pragma unroll
+                for (int j0 = 2; j0 < CH; j0 += 2) {
+                    bw0 = bload(j0), bw1 = bload(j0 + 1);
+                    // burst: two recurrence steps of every row group
+#pragma unroll 1
+                    for (int once = 0; once < ((p.ablate & 2) ? 0 : p.one); ++once) {
+#pragma unroll
+                        for (int g = 0; g < RG; ++g) xm[g] = fma(c2[g], xc[g], -xm[g]);  // z_{j0}
+#pragma unroll
+                        for (int g = 0; g < RG; ++g) xc[g] = fma(c2[g], xm[g], -xc[g]);  // z_{j0+1}
+                    }
+#pragma unroll
+                    for (int g = 0; g < RG; ++g) mma(acc[g][j0], xm[g], bw0);
+#pragma unroll
+                    for (int g = 0; g < RG; ++g) mma(acc[g][j0 + 1], xc[g], bw1);
+                }
+                pa += 2 * apitch;
+                pd += 2 * dpitch;
+                pw += 2 * wpitch;
+            }
+            __syncwarp();
+            if (p.arrive_all || lane == 0) mbar_arrive(&bars[2 + b]);
+        }
+        C2<double> *o = reinterpret_cast<C2<double> *>(reinterpret_cast<double *>(p.out) +
+                                                       (size_t)blockIdx.z * p.out_split_stride);
+#pragma unroll
+        for (int g = 0; g < RG; ++g) {
+            const long long xo = cta_x0 + xrow0 + 8 * g + grp;
+            if (xo >= p.nx) continue;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int f = cta_f0 + fo + j;
+                if (f < p.nchan) {
+                    C2<double> v;
+                    v.re = acc[g][j][0], v.im = acc[g][j][1];
+                    o[(xo * p.nchan + f) * p.wstride + p.coff + kq] = v;
+                }
+            }
+        }
+        return;
+    }
 
     ACC are[CH][NCORR];
     ACC aim[CH][ADJ ? 1 : NCORR];
@@ -1007,7 +1140,9 @@ int ilog2(long long v) {
     return r;
 }
 
-template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NW>
+// MMA: consumers on the FP64 tensor pipe (2x2 complex W, forward, FP64, equispaced channels; the
+// caller checked that the W rows are 16-byte aligned and cover every correlation)
+template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NW, bool MMA = false>
 int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     constexpr int NV = NCORR * (WC ? 2 : 1);
     constexpr int SZ = (int)sizeof(ACC);
@@ -1042,7 +1177,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     const char *ws8_env = getenv("AFR_WS8");
     const bool use_ws8 = ADJ && sizeof(ACC) == 8 && bulk_ok && !exact && !ws_env && !kPreferWS && nck_ws <= NW / 2 &&
                          nck_ws * CH >= 32 && !(ws8_env && atoi(ws8_env) == 0);
-    const bool use_ws = (sizeof(ACC) == 8) && ((ws_env ? atoi(ws_env) != 0 : kPreferWS) || use_ws8);
+    const bool use_ws = (sizeof(ACC) == 8) && ((ws_env ? atoi(ws_env) != 0 : kPreferWS) || use_ws8 || MMA);
     // channel runs per CTA: the single-role kernel keeps nck <= NW/2 so that every thread
     // owns an (x,y) pair per tile; dedicated producers do not need that, and anchors are
     // cheaper per term the more channels a CTA covers (measured +9 % at 16 runs vs 8)
@@ -1052,7 +1187,9 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     while (nck < runs && nck < nck_max) nck *= 2;
     p.nck = nck;
     p.arrive_all = (getenv("AFR_SANITIZE") && atoi(getenv("AFR_SANITIZE")) != 0) ? 1 : 0;
-    const int xgw = (NW / nck) * 32;
+    p.one = 1;
+    p.ablate = getenv("AFR_POINT_MMA_ABLATE") ? atoi(getenv("AFR_POINT_MMA_ABLATE")) : 0;
+    const int xgw = (NW / nck) * (MMA ? 8 * (16 / CH) : 32);
     const int ft = nck * CH;
     const long long gx = (p.nx + xgw - 1) / xgw;
     const int gy = (p.nchan + ft - 1) / ft;
@@ -1072,17 +1209,20 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     // y items per tile: as many (even, <= 8) as fit double-buffered in shared memory and in
     // kMaxChunks cp.async granules per thread
     const size_t per_y = (size_t)(nck + 1 + (kSubRuns<ACC, CH> ? 1 : 0)) * xgw * sizeof(C2<ACC>) +
-                         (size_t)ft * NV * SZ;
+                         (size_t)ft * NV * SZ + (MMA ? 96 : 0);  // MMA: 32 bytes of padding per array
     // granules one thread may have in flight: 8 per thread of the whole CTA, or 16 per
     // producer thread of the warp-specialised kernel
     const long long max_chunks = use_ws ? 16LL * (use_ws8 ? 8 : kProducerWarps) * 32 : (long long)kMaxChunks * NT;
+    // (the granule limit does not apply when the tile will arrive by TMA bulk copies)
+    const bool will_bulk = use_ws && p.fast && granule == 16 && bulk_ok;
     int yt = 8;
-    while (yt > 2 && (2 * yt * per_y > 200 * 1024 || (long long)yt * row_chunks > max_chunks))
+    while (yt > 2 && (2 * yt * per_y > 200 * 1024 || (!will_bulk && (long long)yt * row_chunks > max_chunks)))
         yt -= 2;
-    if ((long long)yt * row_chunks > max_chunks) p.fast = 0;
+    if (!will_bulk && (long long)yt * row_chunks > max_chunks) p.fast = 0;
     p.yt = yt;
     // TMA bulk copies need 16-byte aligned rows and no flag post-processing of the tile
     p.bulk = (use_ws && p.fast && granule == 16 && bulk_ok) ? 1 : 0;
+    if constexpr (MMA) AFR_REQUIRE(p.bulk, "phasor_stream (tensor-pipe consumers): W tile must arrive by bulk copies");
     const size_t smem = 2 * yt * per_y + 3 * (size_t)yt * 3 * sizeof(double) + (size_t)ft * sizeof(double);
 
     // split the streamed axis when the owners alone cannot fill the machine; pick the
@@ -1124,7 +1264,7 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
 
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nsplit);
     note_dft_path((use_ws ? 1 : 0) | (exact ? 2 : 0) | (p.bulk ? 4 : 0) | (sizeof(ACC) == 4 ? 8 : 0) |
-                  (use_ws8 ? 16 : 0) | (nck << 8) |
+                  (use_ws8 ? 16 : 0) | (MMA ? 32 : 0) | (nck << 8) |
                   ((int)nsplit << 16));
     if constexpr (sizeof(ACC) == 8) {
       if (use_ws) {
@@ -1164,6 +1304,16 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
         if (launched) {
         } else if (exact) {
             rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, true, CREGS, PREGS, 0>);
+            launched = true;
+        } else if (MMA) {
+            if constexpr (MMA) {
+                if (nck == NW)
+                    rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, NW,
+                                                           kProducerWarps, true>);
+                else
+                    rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, 0,
+                                                           kProducerWarps, true>);
+            }
             launched = true;
         } else if (nck == NW && yt == 8) {
             rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, NW>);
@@ -1222,7 +1372,26 @@ int launch_corr_blocks(DftParams p, bool exact, cudaStream_t stream) {
         int rc;
         if (ncorr - c >= 4) {
             constexpr int CH = ADJ ? (F32 ? 16 : 8) : (F32 ? 8 : 4);
-            rc = launch_one<4, WC, ADJ, ACC, CH, 16>(p, exact, stream);
+            // 2x2 complex W, forward, FP64, equispaced channels, 16-byte W rows: tensor-pipe consumers
+            // (AFR_POINT_MMA=0 keeps the scalar loop, AFR_POINT_MMA_CH=4|8|16 picks the run length)
+            const char *mma_env = getenv("AFR_POINT_MMA"), *ws_env = getenv("AFR_WS");
+            const bool mma = WC && !ADJ && !F32 && !exact && ncorr == 4 && p.nchan % 2 == 0 &&
+                             reinterpret_cast<uintptr_t>(p.w) % 16 == 0 && !(mma_env && atoi(mma_env) == 0) &&
+                             !(ws_env && atoi(ws_env) == 0);
+            if constexpr (WC && !ADJ && !F32) {
+                const char *ch_env = getenv("AFR_POINT_MMA_CH");
+                const int mch = ch_env ? atoi(ch_env) : 8;
+                if (mma && mch == 4)
+                    rc = launch_one<4, WC, ADJ, ACC, 4, 16, true>(p, exact, stream);
+                else if (mma && mch == 16)
+                    rc = launch_one<4, WC, ADJ, ACC, 16, 16, true>(p, exact, stream);
+                else if (mma)
+                    rc = launch_one<4, WC, ADJ, ACC, 8, 16, true>(p, exact, stream);
+                else
+                    rc = launch_one<4, WC, ADJ, ACC, CH, 16>(p, exact, stream);
+            } else {
+                rc = launch_one<4, WC, ADJ, ACC, CH, 16>(p, exact, stream);
+            }
             c += 4;
         } else if (ncorr - c >= 2) {
             constexpr int CH = ADJ ? (F32 ? 32 : 16) : (F32 ? 16 : 8);
