@@ -90,9 +90,9 @@ def describe_dft_path(code=None):
     code = lib().afr_last_dft_path() if code is None else code
     if code == 0:
         return "none"
-    return "%s, %s, %s W tile, %s accumulators, %d channel runs per CTA, %d slice(s) of the streamed axis" % (
+    return "%s%s, %s, %s W tile, %s accumulators, %d channel runs per CTA, %d slice(s) of the streamed axis" % (
         ("warp-specialised (16 consumer + %d producer warps)" % (8 if code & 16 else 4)) if code & 1
-        else "single-role (16 warps)",
+        else "single-role (16 warps)", ", DMMA consumers" if code & 32 else "",
         "one sincos per term" if code & 2 else "three-term / rotation recurrence",
         "TMA bulk-copied" if code & 4 else "cp.async / staged", "FP32" if code & 8 else "FP64",
         (code >> 8) & 0xFF, (code >> 16) & 0xFFFF)

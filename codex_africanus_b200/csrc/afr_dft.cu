@@ -59,7 +59,7 @@ struct DftParams {
     int bulk;             // warp-specialised kernel: W tile by TMA bulk copies
     int arrive_all;       // every consumer lane arrives on the "empty" mbarrier (AFR_SANITIZE=1)
     int one;              // 1 (opaque to the compiler: trip count of the scalar-burst blocks, see the MMA consumers)
-    int ablate;           // diagnostics (AFR_POINT_MMA_ABLATE, wrong results): 1 no anchor maths, 2 no recurrence, 4 no DMMA
+    int ablate;           // diagnostics (AFR_POINT_MMA_ABLATE, wrong results): 1 no anchor maths, 2 no consumer recurrence
 };
 
 __device__ __forceinline__ void cp_async(unsigned dst, const void *src, int granule, int src_bytes) {
@@ -562,7 +562,7 @@ template <int NCORR, bool WC, bool ADJ, typename ACC, int CH, int NWC, bool EXAC
           int NCKT, int PW = kProducerWarps, bool MMA = false>
 __global__ void __launch_bounds__((NWC + PW) * 32, 1)
     phasor_stream_ws_kernel(const DftParams p) {
-    static_assert(!MMA || (NCORR == 4 && WC && !ADJ && sizeof(ACC) == 8 && !EXACT && (CH == 4 || CH == 8 || CH == 16)),
+    static_assert(!MMA || (NCORR == 4 && WC && !ADJ && sizeof(ACC) == 8 && !EXACT && CH == 8),
                   "tensor-pipe consumers: 2x2 complex W, forward, FP64, equispaced channels");
     constexpr int RG = MMA ? 16 / CH : 4;  // tensor-pipe consumers: row groups of 8 owners per warp
     constexpr int NTP = PW * 32;  // producer threads
@@ -854,7 +854,6 @@ __global__ void __launch_bounds__((NWC + PW) * 32, 1)
         const int bflip = (part & (opart ^ 1)) ? (int)0x80000000 : 0;
         const int xrow0 = (warp / nck) * (8 * RG);
         const int tflip = part ? 0 : (int)0x80000000;
-        const bool no_dmma = (p.ablate & 4) != 0;
         double acc[RG][CH][2];
 #pragma unroll
         for (int g = 0; g < RG; ++g)
@@ -871,7 +870,7 @@ __global__ void __launch_bounds__((NWC + PW) * 32, 1)
                 return __hiloint2double(__double2hiint(bw) ^ bflip, __double2loint(bw));
             };
             auto mma = [&](double (&c)[2], double a, double bw) {
-                if (!no_dmma) asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                              : "+d"(c[0]), "+d"(c[1])
                              : "d"(a), "d"(bw));
             };
@@ -1182,7 +1181,8 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
     // owns an (x,y) pair per tile; dedicated producers do not need that, and anchors are
     // cheaper per term the more channels a CTA covers (measured +9 % at 16 runs vs 8)
     const int runs = (p.nchan + CH - 1) / CH;
-    const int nck_max = use_ws ? NW : NW / 2;
+    int nck_max = use_ws ? NW : NW / 2;
+    if (MMA && getenv("AFR_POINT_MMA_NCK")) nck_max = std::max(1, std::min(NW, atoi(getenv("AFR_POINT_MMA_NCK"))));
     int nck = 1;
     while (nck < runs && nck < nck_max) nck *= 2;
     p.nck = nck;
@@ -1310,6 +1310,9 @@ int launch_one(DftParams p, bool exact, cudaStream_t stream) {
                 if (nck == NW)
                     rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, NW,
                                                            kProducerWarps, true>);
+                else if (nck == NW / 2)
+                    rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, NW / 2,
+                                                           kProducerWarps, true>);
                 else
                     rc = launch_ws(phasor_stream_ws_kernel<NCORR, WC, ADJ, ACC, CH, NW, false, CREGS, PREGS, 0,
                                                            kProducerWarps, true>);
@@ -1373,19 +1376,15 @@ int launch_corr_blocks(DftParams p, bool exact, cudaStream_t stream) {
         if (ncorr - c >= 4) {
             constexpr int CH = ADJ ? (F32 ? 16 : 8) : (F32 ? 8 : 4);
             // 2x2 complex W, forward, FP64, equispaced channels, 16-byte W rows: tensor-pipe consumers
-            // (AFR_POINT_MMA=0 keeps the scalar loop, AFR_POINT_MMA_CH=4|8|16 picks the run length)
+            // (AFR_POINT_MMA=0 keeps the scalar loop)
             const char *mma_env = getenv("AFR_POINT_MMA"), *ws_env = getenv("AFR_WS");
             const bool mma = WC && !ADJ && !F32 && !exact && ncorr == 4 && p.nchan % 2 == 0 &&
                              reinterpret_cast<uintptr_t>(p.w) % 16 == 0 && !(mma_env && atoi(mma_env) == 0) &&
                              !(ws_env && atoi(ws_env) == 0);
             if constexpr (WC && !ADJ && !F32) {
-                const char *ch_env = getenv("AFR_POINT_MMA_CH");
-                const int mch = ch_env ? atoi(ch_env) : 8;
-                if (mma && mch == 4)
-                    rc = launch_one<4, WC, ADJ, ACC, 4, 16, true>(p, exact, stream);
-                else if (mma && mch == 16)
-                    rc = launch_one<4, WC, ADJ, ACC, 16, 16, true>(p, exact, stream);
-                else if (mma)
+                // runs of 8 channels x 2 row groups per warp: measured against 4 x 4 (more anchors per
+                // term, 511-636 Gterms/s) and 16 x 1 (8-row tiles re-read W too often, 414): 744
+                if (mma)
                     rc = launch_one<4, WC, ADJ, ACC, 8, 16, true>(p, exact, stream);
                 else
                     rc = launch_one<4, WC, ADJ, ACC, CH, 16>(p, exact, stream);

@@ -72,9 +72,10 @@ int afr_last_fused_path(void);
  * afr_predict_fused / afr_wsclean_predict launch of this host thread used (its last correlation
  * block): bit 0 warp-specialised (16 consumer + 4 producer warps), bit 1 one sincos per term
  * (non-equispaced channels), bit 2 W tile by TMA bulk copies, bit 3 FP32 accumulators, bit 4 eight
- * producer warps (few-channel adjoint),
+ * producer warps (few-channel adjoint), bit 5 consumers on the FP64 tensor pipe (DMMA; 2x2 complex
+ * brightness, forward, equispaced channels),
  * bits 8-15 channel runs per CTA, bits 16-31 slices of the streamed axis.  Environment overrides
- * (AFR_WS, AFR_SANITIZE) show up here, so a benchmark can report the path it measured. */
+ * (AFR_WS, AFR_POINT_MMA, AFR_SANITIZE) show up here, so a benchmark can report the path it measured. */
 int afr_last_dft_path(void);
 /* Return the scratch memory this library keeps cached in `device`'s default CUDA memory pool
  * (up to 2 GiB between calls) to the driver. */

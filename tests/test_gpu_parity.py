@@ -489,6 +489,56 @@ def test_fused_predict_vs_oracle(b200, oracle):
                                                *args64).dtype == c64
 
 
+def test_fused_point_predict_tensor_pipe(b200, oracle, monkeypatch):
+    """2x2 complex brightness without DDEs on equispaced channels runs the phasor-stream kernel with
+    DMMA consumers (afr_last_dft_path bit 5).  Ragged shapes: rows that do not fill the 16-row tile,
+    odd source counts (the k-step holds two sources), source counts that are not a multiple of the
+    8-item tile, channel counts from one partial run to several CTAs of 128, long baselines; each
+    against the oracle, and the scalar schedule (AFR_POINT_MMA=0) against the same oracle values."""
+    from codex_africanus_b200 import _lib
+    rng = np.random.default_rng(77)
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    cases = [(37, 1, 6, 3e3), (100, 7, 8, 3e3), (53, 19, 40, 3e3), (210, 33, 136, 3e3), (64, 64, 300, 1.5e5),
+             (17, 250, 2, 3e3)]
+    for nrow, nsrc, nchan, scale in cases:
+        uvw = rng.standard_normal((nrow, 3)) * scale
+        lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+        freq = np.linspace(0.856e9, 1.712e9, nchan)
+        bright = rc((nsrc, nchan, 2, 2))
+        ti = np.zeros(nrow, np.int32)
+        a1 = np.zeros(nrow, np.int32)
+        a2 = np.ones(nrow, np.int32)
+        die = 1.0 + 0.1 * rc((1, 2, nchan, 2, 2))
+        bvis = rc((nrow, nchan, 2, 2))
+        ref = oracle.fused_predict(lm, uvw, freq, bright, ti, a1, a2)
+        got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, a1, a2)
+        assert _lib.lib().afr_last_dft_path() & 32, (nrow, nsrc, nchan)
+        assert_c128_close(got, ref)
+        ref2 = oracle.fused_predict(lm, uvw, freq, bright, ti, a1, a2, None, None, die, bvis, die)
+        assert_c128_close(b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, a1, a2, None, None, die, bvis, die),
+                          ref2)
+        monkeypatch.setenv("AFR_POINT_MMA", "0")
+        got0 = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, a1, a2)
+        assert not (_lib.lib().afr_last_dft_path() & 32)
+        monkeypatch.delenv("AFR_POINT_MMA")
+        assert_c128_close(got0, ref)
+        # the schedules anchor their recurrences at different channels (runs of 8 vs 4, 128 vs 64 channels
+        # per CTA); at 150 km the anchor phases themselves carry ulp(1e5 rad) = 1.5e-11
+        assert np.abs(got - got0).max() <= 1e-10 * np.abs(ref).max()
+    # non-equispaced channels and diagonal brightness keep the scalar consumers
+    freq = np.sort(rng.uniform(0.856e9, 1.712e9, 24))
+    uvw = rng.standard_normal((40, 3)) * 3e3
+    lm = rng.uniform(-0.02, 0.02, (9, 2))
+    ti = np.zeros(40, np.int32)
+    bright = rc((9, 24, 2, 2))
+    got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ti, ti + 1)
+    assert not (_lib.lib().afr_last_dft_path() & 32)
+    assert_c128_close(got, oracle.fused_predict(lm, uvw, freq, bright, ti, ti, ti + 1))
+
+
 def test_fused_dde_ws_modes_vs_oracle(b200, oracle, monkeypatch):
     """The DDE kernels: antenna-phasor mode (baseline uvw that are differences of per-antenna
     coordinates, as in a Measurement Set) as a DMMA GEMM (afr_rime_mma.cu) and as the scalar
