@@ -23,6 +23,92 @@ from .predict import normalise_indices, predict_checks
 _ROW_BLOCK_BYTES = 512 << 20
 
 
+# (source, row, chan) terms from which DDE predicts in a layout without a fast kernel of its own are
+# re-expressed as the complex128 2x2 time-ordered problem (below); smaller calls are launch-bound
+_ADAPTER_MIN_TERMS = 1 << 24
+# device bytes of re-expressed DDEs per source chunk
+_ADAPTER_CHUNK_BYTES = 1 << 30
+
+
+def _time_ordered(time_index):
+    if pl.is_torch(time_index):
+        return time_index.numel() < 2 or bool((time_index[1:] >= time_index[:-1]).all().item())
+    ti = np.asarray(time_index)
+    return ti.size < 2 or bool(np.all(ti[1:] >= ti[:-1]))
+
+
+def _embed_2x2(x, corr_shape):
+    """(..., c) diagonal Jones / coherency, c in (1, 2), or (..., 2, 2) -> complex128 (..., 2, 2)."""
+    if tuple(corr_shape) == (2, 2):
+        return x.to(torch.complex128)
+    out = torch.zeros(tuple(x.shape[:-1]) + (2, 2), dtype=torch.complex128, device=x.device)
+    out[..., 0, 0] = x[..., 0]
+    if corr_shape[0] == 2:
+        out[..., 1, 1] = x[..., 1]
+    return out
+
+
+def _predict_as_2x2_c128(lm, uvw, frequency, brightness, time_index, antenna1, antenna2, dde1_jones,
+                         dde2_jones, die1_jones, base_vis, die2_jones, convention, corr_shape, out_dtype,
+                         device):
+    """DDE predicts whose layout has no fast kernel of its own -- diagonal Jones ((1,) / (2,)
+    correlations, africanus/rime/predict.py:15-53,93-98), complex64 chains, rows that are not ordered
+    by time -- through the kernels that have one: rows stably sorted by time, diagonal terms embedded
+    as diagonal 2x2 matrices (the off-diagonal visibilities are exact zeros and are dropped), complex64
+    promoted to complex128 (the result is rounded once, inside the 1e-5 gate by five orders), one chunk
+    of sources at a time with the visibilities as the accumulator.  The GEMM kernel multiplies the
+    embedded zeros too, and still runs at 4-8x the gather kernel these layouts used to get.  The DIEs
+    are applied at the end in the caller's own layout and precision (``apply_gains``)."""
+    from .predict import apply_gains
+    f64 = np.float64
+    nsrc = pl.shape_of(lm)[0]
+    brightness, dde1_jones, dde2_jones = (a if pl.is_torch(a) or a is None else np.asarray(a)
+                                          for a in (brightness, dde1_jones, dde2_jones))
+    if dde2_jones is not dde1_jones and not pl.is_torch(dde1_jones) and dde2_jones.base is not None and \
+            dde2_jones.base is dde1_jones.base and dde2_jones.shape == dde1_jones.shape and \
+            dde2_jones.__array_interface__["data"] == dde1_jones.__array_interface__["data"]:
+        dde2_jones = dde1_jones
+    with torch.cuda.device(device):
+        d_lm, d_uvw, d_f = (pl.to_device(a, f64, device) for a in (lm, uvw, frequency))
+        ti, a1, a2 = normalise_indices(time_index, antenna1, antenna2, device)
+        perm = None
+        if not _time_ordered(time_index):
+            perm = torch.argsort(ti, stable=True)
+            d_uvw, ti, a1, a2 = d_uvw[perm].contiguous(), ti[perm].contiguous(), a1[perm].contiguous(), a2[perm].contiguous()
+        acc = None
+        if base_vis is not None:
+            bv = pl.to_device(base_vis, pl.dtype_of(base_vis), device)
+            acc = _embed_2x2(bv if perm is None else bv[perm], corr_shape)
+        dshape = pl.shape_of(dde1_jones)
+        per_source = max(1, int(np.prod(dshape[1:4])) * 64 * (1 if dde2_jones is dde1_jones else 2))
+        chunk = int(max(1, min(nsrc, _ADAPTER_CHUNK_BYTES // per_source)))
+        for s0 in range(0, nsrc, chunk):
+            s1 = min(nsrc, s0 + chunk)
+            e1 = _embed_2x2(pl.to_device(dde1_jones[s0:s1], pl.dtype_of(dde1_jones), device), corr_shape)
+            e2 = e1 if dde2_jones is dde1_jones else \
+                _embed_2x2(pl.to_device(dde2_jones[s0:s1], pl.dtype_of(dde2_jones), device), corr_shape)
+            b = _embed_2x2(pl.to_device(brightness[s0:s1], pl.dtype_of(brightness), device), corr_shape)
+            acc = fused_predict_vis(d_lm[s0:s1], d_uvw, d_f, b, ti, a1, a2, e1, e2, None, acc, None,
+                                    convention=convention, dtype=np.complex128)
+            del e1, e2, b
+        if tuple(corr_shape) == (2, 2):
+            res = acc
+        elif corr_shape[0] == 2:
+            res = torch.stack((acc[..., 0, 0], acc[..., 1, 1]), dim=-1)
+        else:
+            res = acc[..., 0, 0].unsqueeze(-1)
+        res = res.to(pl.torch_dtype(out_dtype)).contiguous()
+        if die1_jones is not None:
+            g1 = pl.to_device(die1_jones, out_dtype, device)
+            g2 = g1 if die2_jones is die1_jones else pl.to_device(die2_jones, out_dtype, device)
+            res = apply_gains(ti, a1, a2, g1, res, g2)
+        if perm is not None:
+            out = torch.empty_like(res)
+            out[perm] = res
+            res = out
+        return res
+
+
 def fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
                       dde1_jones=None, dde2_jones=None, die1_jones=None, base_vis=None,
                       die2_jones=None, convention="fourier", dtype=None):
@@ -73,6 +159,13 @@ def fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, ante
                   dde2_jones, die1_jones, base_vis, die2_jones)
     device = pl.pick_device(*everything)
     as_torch = pl.wants_torch(*everything)
+    if dde1_jones is not None and nsrc * nrow * nchan >= _ADAPTER_MIN_TERMS:
+        diagonal = mode == _lib.AFR_JONES_DIAG and ncorr in (1, 2)
+        if diagonal or out_dtype == np.complex64 or not _time_ordered(time_index):
+            out = _predict_as_2x2_c128(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
+                                       dde1_jones, dde2_jones, die1_jones, base_vis, die2_jones, convention,
+                                       corr_shape, out_dtype, device)
+            return out if as_torch else pl.to_host(out)
     chan_mode = pl.channel_mode(frequency)
     c64 = int(out_dtype == np.complex64)
     with torch.cuda.device(device):

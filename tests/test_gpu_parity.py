@@ -539,6 +539,62 @@ def test_fused_point_predict_tensor_pipe(b200, oracle, monkeypatch):
     assert_c128_close(got, oracle.fused_predict(lm, uvw, freq, bright, ti, ti, ti + 1))
 
 
+def test_fused_dde_layout_adapter(b200, oracle, monkeypatch):
+    """Diagonal Jones ((2,), (1,)), complex64 chains and rows that are not ordered by time have no fast
+    DDE kernel of their own: above a size threshold they are re-expressed as the time-ordered complex128
+    2x2 problem (rime/fused.py) and must land on the GEMM / warp-specialised kernels with the oracle's
+    values; below it the gather kernel still serves them (covered by the tests above)."""
+    from codex_africanus_b200 import _lib
+    from codex_africanus_b200.rime import fused as fused_mod
+    monkeypatch.setattr(fused_mod, "_ADAPTER_MIN_TERMS", 0)
+    monkeypatch.setattr(fused_mod, "_ADAPTER_CHUNK_BYTES", 1 << 20)  # several source chunks
+    rng = np.random.default_rng(97)
+    na, ntime, nsrc, nchan = 10, 3, 23, 20
+    a1, a2 = np.triu_indices(na, 1)
+    ant1, ant2 = np.tile(a1, ntime), np.tile(a2, ntime)
+    ti = np.repeat(np.arange(ntime), a1.size) + 3
+    pos = rng.standard_normal((ntime, na, 3)) * 1500.0
+    uvw = (pos[:, a1] - pos[:, a2]).reshape(-1, 3)
+    nrow = ant1.size
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    freq = np.linspace(0.856e9, 1.712e9, nchan)
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    import torch
+    fast = (6, 2, 3)  # AFR_PATH_DDE_MMA_ANT, AFR_PATH_DDE_WS_ANT, AFR_PATH_DDE_WS_ROW
+    for corr in ((2,), (1,), (2, 2)):
+        bright = rc((nsrc, nchan) + corr)
+        dde = 1.0 + 0.2 * rc((nsrc, ntime, na, nchan) + corr)
+        dde_b = 1.0 + 0.2 * rc((nsrc, ntime, na, nchan) + corr)
+        die = 1.0 + 0.1 * rc((ntime, na, nchan) + corr)
+        bvis = rc((nrow, nchan) + corr)
+        if corr != (2, 2):
+            for d2 in (dde, dde_b):
+                ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, d2, die, bvis, die)
+                got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, d2, die, bvis, die)
+                assert _lib.lib().afr_last_fused_path() in fast
+                assert got.shape == ref.shape
+                assert_c128_close(got, ref)
+            ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde)
+            assert_c128_close(b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde), ref)
+        # complex64 chain
+        c64 = np.complex64
+        ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die)
+        got = b200.rime.fused_predict_vis(lm, uvw, freq, bright.astype(c64), ti, ant1, ant2, dde.astype(c64),
+                                          dde.astype(c64), die.astype(c64), bvis.astype(c64), die.astype(c64),
+                                          dtype=c64)
+        assert got.dtype == c64 and _lib.lib().afr_last_fused_path() in fast
+        assert rel_l2(got.astype(np.complex128), ref) < 1e-5
+        # rows in a random order (torch inputs: the result stays on the device)
+        perm = rng.permutation(nrow)
+        got = b200.rime.fused_predict_vis(*(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (
+            lm, uvw[perm], freq, bright, ti[perm], ant1[perm], ant2[perm], dde, dde, die, bvis[perm], die)))
+        assert got.is_cuda and _lib.lib().afr_last_fused_path() in fast
+        assert_c128_close(got.cpu().numpy(), ref[perm])
+
+
 def test_fused_dde_ws_modes_vs_oracle(b200, oracle, monkeypatch):
     """The DDE kernels: antenna-phasor mode (baseline uvw that are differences of per-antenna
     coordinates, as in a Measurement Set) as a DMMA GEMM (afr_rime_mma.cu) and as the scalar
