@@ -1378,7 +1378,7 @@ int launch_corr_blocks(DftParams p, bool exact, cudaStream_t stream) {
             // 2x2 complex W, forward, FP64, equispaced channels, 16-byte W rows: tensor-pipe consumers
             // (AFR_POINT_MMA=0 keeps the scalar loop)
             const char *mma_env = getenv("AFR_POINT_MMA"), *ws_env = getenv("AFR_WS");
-            const bool mma = WC && !ADJ && !F32 && !exact && ncorr == 4 && p.nchan % 2 == 0 &&
+            const bool mma = WC && !ADJ && !F32 && !exact && ncorr == 4 &&
                              reinterpret_cast<uintptr_t>(p.w) % 16 == 0 && !(mma_env && atoi(mma_env) == 0) &&
                              !(ws_env && atoi(ws_env) == 0);
             if constexpr (WC && !ADJ && !F32) {

@@ -501,7 +501,7 @@ def test_fused_point_predict_tensor_pipe(b200, oracle, monkeypatch):
     def rc(shape):
         return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
 
-    cases = [(37, 1, 6, 3e3), (100, 7, 8, 3e3), (53, 19, 40, 3e3), (210, 33, 136, 3e3), (64, 64, 300, 1.5e5),
+    cases = [(37, 1, 6, 3e3), (100, 7, 8, 3e3), (53, 19, 41, 3e3), (210, 33, 137, 3e3), (64, 64, 300, 1.5e5), (9, 5, 1, 3e3),
              (17, 250, 2, 3e3)]
     for nrow, nsrc, nchan, scale in cases:
         uvw = rng.standard_normal((nrow, 3)) * scale
