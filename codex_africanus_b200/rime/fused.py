@@ -149,6 +149,22 @@ def fused_predict_vis(lm, uvw, frequency, brightness, time_index, antenna1, ante
         if out_dtype not in (np.complex64, np.complex128):
             raise TypeError("fused_predict_vis: dtype must be complex64 or complex128")
     ncorr = int(np.prod(corr_shape))
+    if dde1_jones is not None and mode == _lib.AFR_JONES_DIAG and ncorr not in (1, 2, 4):
+        # element-wise Jones with another correlation count (predict_vis takes any, rime/predict.py:15-53):
+        # correlations are independent, so they run as blocks of 4 / 2 / 1 like the DFT kernels do
+        parts, c = [], 0
+        while c < ncorr:
+            nc = 4 if ncorr - c >= 4 else (2 if ncorr - c >= 2 else 1)
+            sl = [None if a is None else (a if pl.is_torch(a) else np.asarray(a))[..., c:c + nc]
+                  for a in (brightness, dde1_jones, dde2_jones, die1_jones, base_vis, die2_jones)]
+            if dde2_jones is dde1_jones:
+                sl[2] = sl[1]
+            if die2_jones is die1_jones:
+                sl[5] = sl[3]
+            parts.append(fused_predict_vis(lm, uvw, frequency, sl[0], time_index, antenna1, antenna2, sl[1], sl[2],
+                                           sl[3], sl[4], sl[5], convention=convention, dtype=out_dtype))
+            c += nc
+        return torch.cat(parts, dim=-1) if pl.is_torch(parts[0]) else np.concatenate(parts, axis=-1)
     ntime, nant = 1, 1
     if dde1_jones is not None:
         ntime, nant = pl.shape_of(dde1_jones)[1:3]

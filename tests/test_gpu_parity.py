@@ -539,6 +539,32 @@ def test_fused_point_predict_tensor_pipe(b200, oracle, monkeypatch):
     assert_c128_close(got, oracle.fused_predict(lm, uvw, freq, bright, ti, ti, ti + 1))
 
 
+def test_fused_dde_diagonal_any_ncorr(b200, oracle):
+    """Element-wise Jones with 3, 5 and 7 correlations and DDEs (predict_vis accepts any count; the
+    fused kernels have 1 / 2 / 4): blocks of correlations, concatenated."""
+    rng = np.random.default_rng(53)
+    na, ntime, nsrc, nchan = 5, 2, 6, 9
+    a1, a2 = np.triu_indices(na, 1)
+    ant1, ant2 = np.tile(a1, ntime), np.tile(a2, ntime)
+    ti = np.repeat(np.arange(ntime), a1.size)
+    uvw = rng.standard_normal((ti.size, 3)) * 900.0
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    freq = np.linspace(0.9e9, 1.1e9, nchan)
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    for ncorr in (3, 5, 7):
+        bright = rc((nsrc, nchan, ncorr))
+        dde = 1.0 + 0.2 * rc((nsrc, ntime, na, nchan, ncorr))
+        die = 1.0 + 0.1 * rc((ntime, na, nchan, ncorr))
+        bvis = rc((ti.size, nchan, ncorr))
+        ref = oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die)
+        got = b200.rime.fused_predict_vis(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die)
+        assert got.shape == ref.shape
+        assert_c128_close(got, ref)
+
+
 def test_fused_dde_layout_adapter(b200, oracle, monkeypatch):
     """Diagonal Jones ((2,), (1,)), complex64 chains and rows that are not ordered by time have no fast
     DDE kernel of their own: above a size threshold they are re-expressed as the time-ordered complex128

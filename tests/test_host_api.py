@@ -192,3 +192,25 @@ def test_bench_reference_arm_emits_one_json_line():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline_port"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+
+
+def test_layout_adapter_host_logic():
+    """Host pieces of the DDE layout adapter (rime/fused.py): diagonal terms embedded as diagonal 2x2
+    matrices in complex128, the time-order test on numpy and torch indices."""
+    import torch
+    from codex_africanus_b200.rime import fused
+    rng = np.random.default_rng(0)
+    x2 = torch.from_numpy((rng.standard_normal((3, 4, 2)) + 1j * rng.standard_normal((3, 4, 2))).astype(np.complex64))
+    e = fused._embed_2x2(x2, (2,))
+    assert e.dtype == torch.complex128 and tuple(e.shape) == (3, 4, 2, 2)
+    assert torch.equal(e[..., 0, 0], x2[..., 0].to(torch.complex128))
+    assert torch.equal(e[..., 1, 1], x2[..., 1].to(torch.complex128))
+    assert not e[..., 0, 1].any() and not e[..., 1, 0].any()
+    x1 = x2[..., :1]
+    e = fused._embed_2x2(x1, (1,))
+    assert torch.equal(e[..., 0, 0], x1[..., 0].to(torch.complex128)) and not e[..., 1, 1].any()
+    full = torch.from_numpy(rng.standard_normal((2, 2, 2)) + 1j * rng.standard_normal((2, 2, 2)))
+    assert torch.equal(fused._embed_2x2(full, (2, 2)), full)
+    assert fused._time_ordered(np.array([3, 3, 4, 9])) and not fused._time_ordered(np.array([3, 2, 4]))
+    assert fused._time_ordered(torch.tensor([1, 1, 2])) and not fused._time_ordered(torch.tensor([2, 1]))
+    assert fused._time_ordered(np.array([], dtype=np.int64)) and fused._time_ordered([5])
