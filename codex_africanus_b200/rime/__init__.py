@@ -7,6 +7,7 @@ from .feeds import feed_rotation  # noqa: F401
 from .fused import fused_predict_vis  # noqa: F401
 from .fused_beam import fused_predict_vis_beam  # noqa: F401
 from .fused_stokes import fused_predict_vis_stokes  # noqa: F401
+from .fused_spec import rime as rime_from_spec  # noqa: F401  (africanus.experimental.rime.fused.core.rime)
 from .stream import (stream_fused_predict_vis, stream_fused_predict_vis_beam,  # noqa: F401
                      stream_predict_vis_stokes, timestep_row_blocks)
 from .wsclean_predict import spectra as wsclean_spectra, wsclean_predict  # noqa: F401

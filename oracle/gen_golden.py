@@ -466,6 +466,60 @@ def gen_corrupt_vis():
     save("corrupt_vis", **out)
 
 
+def gen_fused_spec():
+    """The reference's fused-RIME spec front end (africanus/experimental/rime/fused/core.py:227-241,
+    tests: experimental/rime/fused/tests/test_rime.py:225-297,97-219): (Kpq, Bpq) for both feed schemas, a
+    two-correlation schema, the three spectral bases and both conventions; feed rotation (Lp .. Lq) and
+    the beam cube (Ep .. Eq) with the parallactic-angle arrays supplied directly (the transformer that
+    derives them needs casacore, absent here)."""
+    from africanus.experimental.rime.fused.core import rime
+
+    rng = np.random.default_rng(4242)
+    nsrc, nspi, nchan, na, ntime = 7, 2, 6, 4, 3
+    a1, a2 = np.triu_indices(na, 1)
+    ant1, ant2 = np.tile(a1, ntime).astype(np.int32), np.tile(a2, ntime).astype(np.int32)
+    nrow = ant1.size
+    time = np.repeat(np.linspace(0.1, 1.0, ntime), a1.size)
+    feed = np.zeros(nrow, np.int32)
+    radec = rng.random((nsrc, 2)) * 2e-2
+    phase_dir = rng.random(2) * 1e-2
+    uvw = rng.standard_normal((nrow, 3)) * 300.0
+    chan_freq = np.linspace(0.856e9, 2 * 0.856e9, nchan)
+    stokes = rng.normal(size=(nsrc, 4))
+    stokes[:, 0] = np.sqrt((stokes[:, 1:] ** 2).sum(axis=-1))
+    spi = rng.random((nsrc, nspi, 4))
+    ref_freq = rng.uniform(0.5 * 0.856e9, 4 * 0.856e9, nsrc)
+    ds = dict(time=time, antenna1=ant1, antenna2=ant2, feed1=feed, feed2=feed, radec=radec, phase_dir=phase_dir,
+              uvw=uvw, chan_freq=chan_freq, stokes=stokes, spi=spi, ref_freq=ref_freq)
+    out = dict(ds)
+    lin, circ = "[XX,XY,YX,YY]", "[RR,RL,LR,LL]"
+    for tag, corrs, conv, base in (("kb_lin_casa_std", lin, "casa", "standard"), ("kb_circ_fourier_log", circ, "fourier", "log"),
+                                   ("kb_lin_fourier_log10", lin, "fourier", "log10"), ("kb_rrll_fourier_std", "[RR,LL]", "fourier", "standard")):
+        out[tag] = rime("(Kpq, Bpq): [I,Q,U,V] -> %s" % corrs, ds, convention=conv, spi_base=base)
+    # parallactic angles per (time, antenna); one feed, receptor angles zero
+    pa = rng.uniform(-1.0, 1.0, (ntime, na))
+    feed_pa = np.empty((ntime, 1, na, 2, 2))
+    feed_pa[:, 0, :, 0, 0] = feed_pa[:, 0, :, 1, 0] = np.sin(pa)
+    feed_pa[:, 0, :, 0, 1] = feed_pa[:, 0, :, 1, 1] = np.cos(pa)
+    beam_pa = np.stack((np.sin(pa), np.cos(pa)), axis=-1)[:, None]
+    out.update(parallactic_angles=pa, feed_parangle=feed_pa, beam_parangle=beam_pa)
+    for tag, corrs in (("lkbl_lin", lin), ("lkbl_circ", circ)):
+        out[tag] = rime("(Lp, Kpq, Bpq, Lq): [I,Q,U,V] -> %s" % corrs, {**ds, "feed_parangle": feed_pa},
+                        convention="casa", spi_base="standard")
+    lw = mh = nud = 10
+    beam = rc(rng, (lw, mh, nud, 4))
+    ext = np.array([[-0.05, 0.05], [-0.05, 0.05]])
+    bfm = np.sort(rng.uniform(chan_freq[0], chan_freq[-1], nud))
+    out.update(beam=beam, beam_lm_extents=ext, beam_freq_map=bfm)
+    eds = {**ds, "beam": beam, "beam_lm_extents": ext, "beam_freq_map": bfm, "beam_parangle": beam_pa}
+    out["ekbe_lin"] = rime("(Ep, Kpq, Bpq, Eq): [I,Q,U,V] -> %s" % lin, eds, convention="casa", spi_base="standard")
+    out["lekbel_lin"] = rime("(Lp, Ep, Kpq, Bpq, Eq, Lq): [I,Q,U,V] -> %s" % lin, {**eds, "feed_parangle": feed_pa},
+                             convention="fourier", spi_base="standard")
+    out["elkble_lin"] = rime("(Ep, Lp, Kpq, Bpq, Lq, Eq): [I,Q,U,V] -> %s" % lin, {**eds, "feed_parangle": feed_pa},
+                             convention="fourier", spi_base="standard")
+    save("fused_spec", **out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     if only:  # e.g. `python oracle/gen_golden.py gen_dft_padded`: (re)write the named files only
@@ -482,3 +536,4 @@ if __name__ == "__main__":
     gen_brightness()
     gen_feeds()
     gen_corrupt_vis()
+    gen_fused_spec()

@@ -1189,3 +1189,46 @@ def test_predict_vis_equals_reference_corrupt_vis(b200, golden, tag):
     ti, a1, a2, jones, model = _corrupt_vis_case(g, tag)
     got = b200.rime.predict_vis(ti, a1, a2, dde1_jones=jones, source_coh=model, dde2_jones=jones)
     assert_c128_close(got, g[tag + "_vis"])
+
+
+def test_fused_spec_front_end_golden(b200, golden):
+    """``rime(spec, dataset)`` against the reference's own fused-RIME front end
+    (africanus/experimental/rime/fused/core.py:227-241; goldens generated by oracle/gen_golden.py from the
+    unmodified reference): (Kpq, Bpq) for linear / circular / two-correlation schemas, the three spectral
+    bases and both conventions; feed rotation outside and inside the beam term; the beam cube term."""
+    from codex_africanus_b200.rime.fused_spec import rime
+    g = golden("fused_spec")
+    ds = {k: g[k] for k in ("time", "antenna1", "antenna2", "feed1", "feed2", "radec", "phase_dir", "uvw", "chan_freq",
+                           "stokes", "spi", "ref_freq")}
+    lin, circ = "[XX,XY,YX,YY]", "[RR,RL,LR,LL]"
+    for tag, corrs, conv, base in (("kb_lin_casa_std", lin, "casa", "standard"), ("kb_circ_fourier_log", circ, "fourier", "log"),
+                                   ("kb_lin_fourier_log10", lin, "fourier", "log10"), ("kb_rrll_fourier_std", "[RR,LL]", "fourier", "standard")):
+        got = rime("(Kpq, Bpq): [I,Q,U,V] -> %s" % corrs, ds, convention=conv, spi_base=base)
+        assert isinstance(got, np.ndarray)
+        assert_c128_close(got, g[tag])
+    for tag, corrs in (("lkbl_lin", lin), ("lkbl_circ", circ)):
+        got = rime("(Lp, Kpq, Bpq, Lq): [I,Q,U,V] -> %s" % corrs, ds, feed_parangle=g["feed_parangle"],
+                   convention="casa", spi_base="standard")
+        assert_c128_close(got, g[tag])
+        got = rime("(Lp, Kpq, Bpq, Lq): [I,Q,U,V] -> %s" % corrs, ds, parallactic_angles=g["parallactic_angles"],
+                   convention="casa")
+        assert_c128_close(got, g[tag])
+    eds = {**ds, "beam": g["beam"], "beam_lm_extents": g["beam_lm_extents"], "beam_freq_map": g["beam_freq_map"],
+           "beam_parangle": g["beam_parangle"]}
+    assert_c128_close(rime("(Ep, Kpq, Bpq, Eq): [I,Q,U,V] -> %s" % lin, eds, convention="casa"), g["ekbe_lin"])
+    assert_c128_close(rime("(Lp, Ep, Kpq, Bpq, Eq, Lq): [I,Q,U,V] -> %s" % lin, eds, feed_parangle=g["feed_parangle"]),
+                      g["lekbel_lin"])
+    assert_c128_close(rime("(Ep, Lp, Kpq, Bpq, Lq, Eq): [I,Q,U,V] -> %s" % lin, eds, feed_parangle=g["feed_parangle"]),
+                      g["elkble_lin"])
+    # the five required arrays may be given positionally, the rest by keyword; CUDA tensors in -> CUDA tensor out
+    import torch
+    kw = {k: (torch.from_numpy(v).cuda() if k in ("uvw", "chan_freq", "stokes", "spi", "ref_freq") else v)
+          for k, v in ds.items() if k not in fs_required()}
+    got = rime("(Kpq, Bpq): [I,Q,U,V] -> %s" % lin, *(ds[k] for k in fs_required()), convention="casa", **kw)
+    assert got.is_cuda
+    assert_c128_close(got.cpu().numpy(), g["kb_lin_casa_std"])
+
+
+def fs_required():
+    from codex_africanus_b200.rime.fused_spec import REQUIRED_ARGS
+    return REQUIRED_ARGS

@@ -214,3 +214,35 @@ def test_layout_adapter_host_logic():
     assert fused._time_ordered(np.array([3, 3, 4, 9])) and not fused._time_ordered(np.array([3, 2, 4]))
     assert fused._time_ordered(torch.tensor([1, 1, 2])) and not fused._time_ordered(torch.tensor([2, 1]))
     assert fused._time_ordered(np.array([], dtype=np.int64)) and fused._time_ordered([5])
+
+
+def test_fused_spec_parser_and_term_rules():
+    """Grammar and term rules of the fused-RIME specification front end (reference:
+    experimental/rime/fused/specification.py:78-115,166-185,440-453) -- host logic only."""
+    from codex_africanus_b200.rime import fused_spec as fs
+    terms, stokes, corrs = fs.parse_rime("(Lp, Ep, Kpq, Bpq, Eq, Lq): [I,Q,U,V] -> [XX,XY,YX,YY]")
+    assert terms == ["Lp", "Ep", "Kpq", "Bpq", "Eq", "Lq"] and stokes == ["I", "Q", "U", "V"]
+    assert corrs == ["XX", "XY", "YX", "YY"]
+    assert fs.parse_rime(fs.DEFAULT_SPEC)[0] == ["Kpq", "Bpq"]
+    assert fs.parse_rime("[Kpq, Bpq,]: [I, Q] -> [RR, LL]") == (["Kpq", "Bpq"], ["I", "Q"], ["RR", "LL"])
+    for bad in ("(Kpq, Bpq)", "(Kpq, Bpq): [I,Q,U,V]", "Kpq, Bpq: [I] -> [XX]", "(Kpq, (Bpq)): [I] -> [XX]",
+                "(Kpq, Bpq): I,Q -> [XX]"):
+        with pytest.raises(fs.RimeParseError):
+            fs.parse_rime(bad)
+    assert fs.split_terms(["Lp", "Ep", "Kpq", "Bpq", "Eq", "Lq"]) == (["L", "E"], ["K", "B"], ["E", "L"])
+    assert fs.split_terms(["Bpq"]) == ([], ["B"], [])
+    for bad in (["Ep", "Kpq", "Bpq", "Lq"], ["Kpq", "Ep", "Bpq", "Eq"], ["Kp", "Bpq", "Kq"], ["Zp", "Kpq", "Bpq", "Zq"],
+                ["Kpq", "Bpq", "Kpq"], ["kpq", "Bpq"]):
+        with pytest.raises(fs.RimeSpecificationError):
+            fs.split_terms(bad)
+    with pytest.raises(NotImplementedError):
+        fs.split_terms(["Cpq", "Kpq", "Bpq"])
+    assert fs.feed_type_of(["XX", "YY"]) == "linear" and fs.feed_type_of(["RR", "RL", "LR", "LL"]) == "circular"
+    with pytest.raises(fs.RimeSpecificationError):
+        fs.feed_type_of(["XX", "RR"])
+    m = fs.consolidate_args(({"TIME": 1, "uvw": 2}, 10, 11), {"convention": "casa"})
+    assert m == {"time": 10, "uvw": 2, "antenna1": 11, "convention": "casa"}
+    # lm of transformers/lm.py against the direction cosines of a small offset
+    lm = fs.radec_to_lm(np.array([[0.01, -0.5], [0.0, -0.49]]), np.array([0.0, -0.5]))
+    assert np.allclose(lm[0], [np.cos(-0.5) * np.sin(0.01), np.sin(-0.5) * np.cos(-0.5) * (1 - np.cos(0.01))])
+    assert np.allclose(lm[1], [0.0, np.sin(0.01)])
