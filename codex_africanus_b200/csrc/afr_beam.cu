@@ -410,6 +410,63 @@ __global__ void __launch_bounds__(256) beam_cube_dde_planes_kernel(const __grid_
     }
 }
 
+// Stage 1 of beam_cube_dde_planes_kernel on its own: the four spatial corners of every frequency
+// plane reduced per (source, time, antenna) row and written out, planes[row][g][re 0..3 | im 0..3 |
+// |.| 0..3] (2x2 complex128 beams).  43x smaller than the (source,time,ant,chan,2,2) Jones array at
+// 4096 channels; the predict kernel's producers combine the two planes of a channel themselves
+// (afr_rime_ws.cu, SAMPLE), so the interpolated Jones never exist in memory.
+__global__ void __launch_bounds__(256) beam_plane_reduce_kernel(const __grid_constant__ BeamParams p, double *planes) {
+    const double *beam = (const double *)p.beam;
+    const double *babs = (const double *)p.babs;
+    for (long long sta = blockIdx.x; sta < p.nsrc * p.ntime * p.nant; sta += gridDim.x) {
+        const long long a = sta % p.nant, t = (sta / p.nant) % p.ntime, s = sta / (p.nant * p.ntime);
+        const double sin_pa = p.pa_sc[2 * (t * p.nant + a)], cos_pa = p.pa_sc[2 * (t * p.nant + a) + 1];
+        // the operations of beam_cube_dde_planes_kernel (fast_beam_cubes.py:130-163), lm scale 1
+        const double l = p.lm[2 * s], m = p.lm[2 * s + 1];
+        const double2 pe = *reinterpret_cast<const double2 *>(p.perr + ((t * p.nant + a) * p.nchan) * 2);
+        const double2 as = *reinterpret_cast<const double2 *>(p.ascale + (a * p.nchan) * 2);
+        const double tl = __dadd_rn(__dmul_rn(l, 1.0), pe.x), tm = __dadd_rn(__dmul_rn(m, 1.0), pe.y);
+        double vl = __dsub_rn(__dmul_rn(tl, cos_pa), __dmul_rn(tm, sin_pa));
+        double vm = __dadd_rn(__dmul_rn(tl, sin_pa), __dmul_rn(tm, cos_pa));
+        vl = __dmul_rn(vl, as.x), vm = __dmul_rn(vm, as.y);
+        vl = __dmul_rn(p.lscale, __dsub_rn(vl, p.lower_l));
+        vm = __dmul_rn(p.mscale, __dsub_rn(vm, p.lower_m));
+        vl = fmax(0.0, fmin(vl, p.lmaxf)), vm = fmax(0.0, fmin(vm, p.mmaxf));
+        const long long gl0 = (long long)(int)floor(vl), gm0 = (long long)(int)floor(vm);
+        const long long gl1 = min(gl0 + 1, p.lw - 1), gm1 = min(gm0 + 1, p.mh - 1);
+        const double ld = __dsub_rn(vl, (double)gl0), md = __dsub_rn(vm, (double)gm0);
+        const double oml = __dsub_rn(1.0, ld), omm = __dsub_rn(1.0, md);
+        const double w4[4] = {__dmul_rn(oml, omm), __dmul_rn(ld, omm), __dmul_rn(oml, md), __dmul_rn(ld, md)};
+        const long long corner[4] = {gl0 * p.mh + gm0, gl1 * p.mh + gm0, gl0 * p.mh + gm1, gl1 * p.mh + gm1};
+        double *row = planes + sta * p.nud * 12;
+        for (int idx = threadIdx.x; idx < (int)p.nud * 4; idx += blockDim.x) {
+            const int g = idx >> 2, c = idx & 3;
+            double re = 0.0, im = 0.0, ab = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long e = (corner[k] * p.nud + g) * 4 + c;
+                const double2 bv = reinterpret_cast<const double2 *>(beam)[e];
+                re = __dadd_rn(re, __dmul_rn(w4[k], bv.x));
+                im = __dadd_rn(im, __dmul_rn(w4[k], bv.y));
+                ab = __dadd_rn(ab, __dmul_rn(w4[k], babs[e]));
+            }
+            row[g * 12 + c] = re, row[g * 12 + 4 + c] = im, row[g * 12 + 8 + c] = ab;
+        }
+    }
+}
+
+// ok[0] = 1 when every (time, antenna) row keeps one grid position along the channel axis and every
+// channel is inside the cube's frequency range: the conditions under which a channel's Jones is the
+// combination of two planes
+__global__ void beam_planes_ok_kernel(const uint8_t *row_flag, long long nrows, const double *fd, long long nchan,
+                                      int *ok) {
+    bool good = true;
+    for (long long i = threadIdx.x; i < nrows; i += blockDim.x) good = good && row_flag[i] != 0;
+    for (long long f = threadIdx.x; f < nchan; f += blockDim.x) good = good && fd[3 * f] == 1.0;
+    const int all = __syncthreads_and(good ? 1 : 0);
+    if (threadIdx.x == 0) ok[0] = all;
+}
+
 // africanus/rime/feeds.py:13-48: (n,) parallactic angles -> (n,2,2) complex.
 // linear [[cos, sin], [-sin, cos]]; circular diag(exp(-i pa), exp(+i pa))
 template <typename T>
@@ -595,4 +652,63 @@ extern "C" int afr_beam_cube_dde_rot(const void *beam, const double *ext_host_or
     p.ncorr = (int)ncorr;
     p.row_flag = (const uint8_t *)rflag.ptr;
     return is_c64 ? launch_beam<float>(p, stream) : launch_beam<double>(p, stream);
+}
+
+// Plane-reduced beam for in-kernel sampling: planes (nsrc,ntime,nant,nud,12) float64,
+// fd (nchan,3) the frequency-grid table of freq_grid_interp, ok (device int) = 1 when every channel of
+// every row is the combination of two planes.  2x2 complex128 beams.
+extern "C" int afr_beam_plane_reduce(const void *beam, const double *ext_host_or_dev, const double *beam_freq_map,
+                                     const double *lm, const double *parallactic_angles,
+                                     const double *point_errors, const double *antenna_scaling,
+                                     const double *freq, int64_t lw, int64_t mh, int64_t nud, int64_t nsrc,
+                                     int64_t ntime, int64_t nant, int64_t nchan, double *planes, double *fd,
+                                     int *ok, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AFR_REQUIRE(reinterpret_cast<uintptr_t>(beam) % 16 == 0 && reinterpret_cast<uintptr_t>(planes) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(point_errors) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(antenna_scaling) % 16 == 0,
+                "afr_beam_plane_reduce: beam / planes / point_errors / antenna_scaling must be 16-byte aligned");
+    AFR_REQUIRE(lw >= 2 && mh >= 2 && nud >= 2, "beam_lw, beam_mh and beam_nud must be >= 2");
+    AFR_REQUIRE(nsrc >= 0 && ntime >= 1 && nant >= 1 && nchan >= 1, "bad extent");
+    int rc = afr_freq_grid_interp(freq, beam_freq_map, nchan, nud, fd, stream_);
+    if (rc) return rc;
+    double ext[4];
+    AFR_CUDA_OK(cudaMemcpyAsync(ext, ext_host_or_dev, sizeof(ext), cudaMemcpyDefault, stream));
+    AFR_CUDA_OK(cudaStreamSynchronize(stream));
+    Scratch rflag, babs, pasc;
+    AFR_CUDA_OK(rflag.alloc((size_t)(ntime * nant), stream));
+    beam_row_flag_kernel<<<(unsigned)(ntime * nant), 256, 0, stream>>>(point_errors, antenna_scaling, nant, nchan,
+                                                                      (uint8_t *)rflag.ptr);
+    AFR_LAUNCH_OK();
+    beam_planes_ok_kernel<<<1, 256, 0, stream>>>((const uint8_t *)rflag.ptr, ntime * nant, fd, nchan, ok);
+    AFR_LAUNCH_OK();
+    if (nsrc == 0) return 0;
+    const long long nbeam = lw * mh * nud * 4;
+    AFR_CUDA_OK(babs.alloc((size_t)nbeam * 8, stream));
+    AFR_CUDA_OK(pasc.alloc(sizeof(double) * 2 * (size_t)(ntime * nant), stream));
+    beam_abs_kernel<double><<<(int)std::min<long long>((nbeam + 255) / 256, 32LL * sm_count()), 256, 0, stream>>>(
+        (const double *)beam, nbeam, (double *)babs.ptr);
+    AFR_LAUNCH_OK();
+    pa_sincos_kernel<<<(int)((ntime * nant + 255) / 256), 256, 0, stream>>>(parallactic_angles, ntime * nant,
+                                                                           (double *)pasc.ptr);
+    AFR_LAUNCH_OK();
+    BeamParams p{};
+    p.beam = beam;
+    p.babs = babs.ptr;
+    p.pa_sc = (const double *)pasc.ptr;
+    p.lm = lm;
+    p.perr = point_errors;
+    p.ascale = antenna_scaling;
+    p.lower_l = ext[0];
+    p.lower_m = ext[2];
+    p.lmaxf = (double)(lw - 1);
+    p.mmaxf = (double)(mh - 1);
+    p.lscale = p.lmaxf / (ext[1] - ext[0]);
+    p.mscale = p.mmaxf / (ext[3] - ext[2]);
+    p.lw = lw, p.mh = mh, p.nud = nud, p.nsrc = nsrc, p.ntime = ntime, p.nant = nant, p.nchan = nchan;
+    p.ncorr = 4;
+    const long long rows = nsrc * ntime * nant;
+    beam_plane_reduce_kernel<<<(unsigned)std::min<long long>(rows, 64LL * sm_count()), 256, 0, stream>>>(p, planes);
+    AFR_LAUNCH_OK();
+    return 0;
 }

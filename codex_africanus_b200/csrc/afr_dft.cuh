@@ -45,8 +45,13 @@ struct DdeWsParams {
     int nchan;
     int same_dde;
     int arrive_all;  // AFR_SANITIZE=1: every consumer lane arrives on the "empty" barriers
+    // in-kernel beam sampling (antenna mode, E1 = E2 = the beam): instead of dde1 / dde2 the producers
+    // fetch the two frequency planes of each channel from the plane-reduced beam and form the Jones
+    const double *planes;  // (nsrc,ntime,nant,nud,12) or nullptr
+    const double *fd;      // (nchan,3) frequency-grid table (scale, weight of the lower plane, lower plane)
+    int nud;
 };
-size_t dde_ws_smem_bytes(int64_t nant, int ft, bool ant);
+size_t dde_ws_smem_bytes(int64_t nant, int ft, bool ant, bool sample = false);
 int dde_ws_row_tile_channels(int64_t nant);
 // per-timestep antenna coordinates from baseline uvw; ok[0] is cleared when the rows of any
 // timestep are not differences of per-antenna coordinates

@@ -891,3 +891,107 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
     }
     return 0;
 }
+
+// Full-RIME predict with the DDE Jones sampled from the plane-reduced beam INSIDE the predict kernel
+// (SURVEY 8f-1 proper; reference: experimental/rime/fused/terms/cube_dde.py:96-313 samples the cube in
+// its fused loop): antenna-phasor mode of the warp-specialised kernel, whose producers form each
+// antenna's Jones from the two frequency planes of the channel (afr_beam_plane_reduce) before they
+// precombine it with the brightness -- the (source,time,ant,chan,2,2) array never exists.
+// used[0] (host) = 1 when the predict ran; 0 when this path does not apply (uvw that are not
+// differences of antenna coordinates within the admission bound, rows not ordered by time, antenna
+// tile too large for shared memory): the caller then takes the chunked route, nothing was written.
+extern "C" int afr_predict_fused_planes(const double *lm, const double *uvw, const double *freq,
+                                        const void *brightness, const int32_t *time_index,
+                                        const int32_t *antenna1, const int32_t *antenna2, const double *planes,
+                                        const double *fd, int64_t nud, const void *die1, const void *base_vis,
+                                        const void *die2, int64_t nsrc, int64_t nrow, int64_t ntime,
+                                        int64_t nant, int64_t nchan, int convention, int *used, void *out,
+                                        void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AFR_REQUIRE(used != nullptr, "afr_predict_fused_planes: used must not be NULL");
+    *used = 0;
+    AFR_REQUIRE(convention == AFR_FOURIER || convention == AFR_CASA, "convention not in ('fourier', 'casa')");
+    AFR_REQUIRE((die1 == nullptr) == (die2 == nullptr),
+                "Both die1_jones and die2_jones must be present or absent");
+    AFR_REQUIRE(nsrc >= 1 && nrow >= 1 && nchan >= 1 && ntime >= 1 && nant >= 1 && nud >= 2 &&
+                    nchan < (1LL << 30) && nrow < (1LL << 31) && nant <= 1024,
+                "afr_predict_fused_planes: bad extent");
+    if (reinterpret_cast<uintptr_t>(planes) % 16 != 0 || reinterpret_cast<uintptr_t>(brightness) % 16 != 0 ||
+        dde_ws_smem_bytes(nant, 1, true, true) > 220 * 1024)
+        return 0;
+    const double cst = convention == AFR_FOURIER ? -kTwoPiOverC : kTwoPiOverC;
+    Scratch lmn, rs, fl, antuvw, antok, perm;
+    AFR_CUDA_OK(lmn.alloc(sizeof(double) * 3 * (size_t)nsrc, stream));
+    int rc = launch_lm_to_lmn(lm, nsrc, kLmnPhaseClamp, false, (double *)lmn.ptr, stream);
+    if (rc) return rc;
+    AFR_CUDA_OK(rs.alloc(sizeof(int32_t) * (size_t)(ntime + 1), stream));
+    AFR_CUDA_OK(fl.alloc(sizeof(int) * 2, stream));
+    AFR_CUDA_OK(cudaMemsetAsync(fl.ptr, 0, sizeof(int) * 2, stream));
+    const long long n = std::max<long long>(nrow, ntime + 1);
+    time_ranges_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(time_index, nrow, ntime, (int32_t *)rs.ptr,
+                                                                   (int *)fl.ptr);
+    AFR_LAUNCH_OK();
+    max_rows_kernel<<<(int)((ntime + 255) / 256), 256, 0, stream>>>((const int32_t *)rs.ptr, ntime, (int *)fl.ptr);
+    AFR_LAUNCH_OK();
+    AFR_CUDA_OK(antuvw.alloc(sizeof(double) * 3 * (size_t)(ntime * nant), stream));
+    AFR_CUDA_OK(antok.alloc(sizeof(int), stream));
+    const int one = 1;
+    AFR_CUDA_OK(cudaMemcpyAsync(antok.ptr, &one, sizeof(int), cudaMemcpyHostToDevice, stream));
+    rc = launch_antenna_uvw(uvw, antenna1, antenna2, (const int32_t *)rs.ptr, ntime, nant, (const double *)lmn.ptr,
+                            nsrc, freq, nchan, cst, (double *)antuvw.ptr, (int *)antok.ptr, stream);
+    if (rc) return rc;
+    int hflags[2] = {0, 0}, hant = 0;
+    AFR_CUDA_OK(cudaMemcpyAsync(hflags, fl.ptr, sizeof(hflags), cudaMemcpyDeviceToHost, stream));
+    AFR_CUDA_OK(cudaMemcpyAsync(&hant, antok.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    AFR_CUDA_OK(cudaStreamSynchronize(stream));
+    const char *am_env = getenv("AFR_DDE_ANT");
+    if (hant == 0 || hflags[0] != 0 || hflags[1] <= 0 || (am_env && atoi(am_env) == 0)) return 0;
+    AFR_CUDA_OK(perm.alloc(sizeof(int32_t) * (size_t)nrow, stream));
+    rc = launch_row_tile_order(time_index, antenna1, antenna2, nrow, ntime, hflags[1] > 512, (int32_t *)perm.ptr,
+                               stream);
+    if (rc) return rc;
+    DdeWsParams wp{};
+    wp.perm = (const int32_t *)perm.ptr;
+    wp.lmn = (const double *)lmn.ptr;
+    wp.uvw = uvw;
+    wp.freq = freq;
+    wp.bright = (const double *)brightness;
+    wp.ant1 = antenna1;
+    wp.ant2 = antenna2;
+    wp.row_start = (const int32_t *)rs.ptr;
+    wp.ant_uvw = (const double *)antuvw.ptr;
+    wp.out = (double *)out;
+    wp.cst = cst;
+    wp.nsrc = nsrc;
+    wp.nrow = nrow;
+    wp.ntime = ntime;
+    wp.nant = nant;
+    wp.nchan = (int)nchan;
+    wp.same_dde = 1;
+    wp.planes = planes;
+    wp.fd = fd;
+    wp.nud = (int)nud;
+    rc = launch_fused_dde_ws(wp, hflags[1], false, true, stream);
+    if (rc) return rc;
+    note_fused_path(AFR_PATH_DDE_WS_ANT_SAMPLED);
+    if (base_vis != nullptr || die1 != nullptr) {
+        PredictParams p{};
+        p.time_index = time_index;
+        p.ant1 = antenna1;
+        p.ant2 = antenna2;
+        p.die1 = die1;
+        p.bvis = base_vis;
+        p.die2 = die2;
+        p.acc_init = out;
+        p.out = out;
+        p.nsrc = 0;
+        p.nrow = nrow;
+        p.ntime = ntime;
+        p.nant = nant;
+        p.nfc = nchan;
+        rc = launch_predict<double>(p, AFR_JONES_2X2, stream);
+        if (rc) return rc;
+    }
+    *used = 1;
+    return 0;
+}

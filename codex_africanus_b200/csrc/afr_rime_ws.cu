@@ -83,10 +83,11 @@ __device__ __forceinline__ void sts_c(unsigned char *p, Cd v) {
 // banks) and lanes reading the same antenna broadcast
 __host__ __device__ constexpr int ant_stride(int ft) { return ft * kMatBytes + 16; }
 
-size_t stage_bytes(int na, int ft, bool ant) {
-    // E2 (or E) | E1 -> A (or A) | B
+constexpr int kPlaneBytes = 192;  // two frequency planes x (re, im, |.|) x 4 correlations of one (antenna, channel)
+size_t stage_bytes(int na, int ft, bool ant, bool sample = false) {
+    // E2 (or E) | E1 -> A (or A) | B | (sampling: the raw planes)
     (void)ant;
-    return 2 * (size_t)na * ant_stride(ft) + (size_t)ft * kMatBytes;
+    return 2 * (size_t)na * ant_stride(ft) + (size_t)ft * kMatBytes + (sample ? (size_t)na * ft * kPlaneBytes : 0);
 }
 
 // FT channels and RPT rows per consumer thread (FT * RPT = 4: 64 accumulator doubles).
@@ -94,10 +95,11 @@ size_t stage_bytes(int na, int ft, bool ant) {
 //   <1,4>: a CTA owns 2048 rows x 1 channel -- antenna mode: a MeerKAT timestep (2016
 //          baselines) is ONE row tile, so every E element is fetched, scaled and precombined
 //          exactly once per (source, time, channel) instead of once per 512-row tile.
-template <bool EXACT, bool ANT, int FT, int RPT>
+template <bool EXACT, bool ANT, int FT, int RPT, bool SAMPLE = false>
 __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
     fused_dde_ws_kernel(const DdeWsParams p) {
     static_assert(ANT || RPT == 1, "per-row phasors advance along the thread's channel run");
+    static_assert(!SAMPLE || (ANT && !EXACT), "in-kernel beam sampling runs in antenna mode");
     static_assert(FT == 1 || FT == 2 || FT == 4, "FT");
     constexpr int AS = ant_stride(FT);
     constexpr int kRows = kConsThreads * RPT;
@@ -112,9 +114,10 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
     if (rbeg >= rend) return;
 
     const size_t mat_region = (size_t)na * AS;
-    const size_t stage = 2 * mat_region + FT * kMatBytes;
+    const size_t stage = 2 * mat_region + FT * kMatBytes + (SAMPLE ? (size_t)na * FT * kPlaneBytes : 0);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kNS * stage);  // full, empty, landed [kNS]
     double *fq = reinterpret_cast<double *>(bars + 3 * kNS);            // [FT]
+    auto pl_of = [&](int st) { return smem + st * stage + 2 * mat_region + FT * kMatBytes; };  // SAMPLE: raw planes
     auto e2_of = [&](int st) { return smem + st * stage; };
     auto a_of = [&](int st) { return smem + st * stage + mat_region; };
     auto b_of = [&](int st) { return smem + st * stage + 2 * mat_region; };
@@ -128,7 +131,9 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
             mbar_init(&bars[2 * kNS + i], kNTP);   // landed: the cp.async of every producer thread
         }
     }
+    double *fw = fq + FT;  // [FT] (SAMPLE) weight of the lower frequency plane
     if (tid < FT) fq[tid] = p.freq[min(f0 + tid, p.nchan - 1)];
+    if (SAMPLE && tid < FT) fw[tid] = p.fd[3 * min(f0 + tid, p.nchan - 1) + 1];
     __syncthreads();
 
     const int valid_ch = min(FT, p.nchan - f0);
@@ -154,7 +159,22 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
             const char *src2 = reinterpret_cast<const char *>(p.dde2) + base;
             const char *src1 = reinterpret_cast<const char *>(p.dde1) + base;
             const unsigned d2 = smem_addr(e2_of(st)), d1 = smem_addr(a_of(st));
-            for (int g = ptid; g < na * FT * 4; g += kNTP) {
+            if constexpr (SAMPLE) {
+                // the two planes (192 contiguous bytes) of every (antenna, channel) of this tile
+                const char *psrc = reinterpret_cast<const char *>(p.planes) +
+                                   ((s * p.ntime + t) * p.nant) * (long long)p.nud * 96;
+                const unsigned dp = smem_addr(pl_of(st));
+                for (int g = ptid; g < na * FT * 12; g += kNTP) {
+                    const int item = g / 12, c = g - item * 12;
+                    const int a = item >> LFT, fl = item & (FT - 1);
+                    if (fl < valid_ch) {
+                        const int gl = (int)p.fd[3 * (f0 + fl) + 2];
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dp + item * kPlaneBytes + c * 16),
+                                     "l"(psrc + ((long long)a * p.nud + gl) * 96 + c * 16));
+                    }
+                }
+            }
+            for (int g = ptid; !SAMPLE && g < na * FT * 4; g += kNTP) {
                 const int a = g >> (LFT + 2), c = g & (FT * 4 - 1);
                 if (c < gran_valid) {
                     const unsigned doff = (unsigned)(a * AS + c * 16);
@@ -195,7 +215,34 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
                 const unsigned char *e1 = (p.same_dde ? e2 : am) + off;
                 const unsigned char *bm = bsm + fl * kMatBytes;
                 const Cd b0 = lds_c(bm), b1 = lds_c(bm + 16), b2 = lds_c(bm + 32), b3 = lds_c(bm + 48);
-                const Cd x0 = lds_c(e1), x1 = lds_c(e1 + 16);
+                Cd x0, x1;
+                if constexpr (SAMPLE) {
+                    // row h of the beam Jones of antenna a at channel fl from its two frequency planes:
+                    // the arithmetic of beam_cube_dde_planes_kernel's stage 2 (afr_beam.cu), i.e. the
+                    // reference's interpolation and amplitude renormalisation (fast_beam_cubes.py:169-238)
+                    const double *pr = reinterpret_cast<const double *>(pl_of(st) + (size_t)((a << LFT) + fl) * kPlaneBytes);
+                    const double wlo = fw[fl], whi = 1.0 - wlo;  // exact: fd holds the weight, 1 - w as the beam kernel forms it
+                    Cd xs[2];
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = 2 * h + cc;
+                        const double csr = fma(wlo, pr[c], whi * pr[12 + c]);
+                        const double csi = fma(wlo, pr[4 + c], whi * pr[16 + c]);
+                        const double asum = fma(wlo, pr[8 + c], whi * pr[20 + c]);
+                        const double tt = fma(csr, csr, csi * csi);
+                        double kk;
+                        if (tt > 1e-290 && tt < 1e290) {
+                            kk = asum * rsqrt(tt);
+                        } else {
+                            const double div = hypot(csr, csi);
+                            kk = (div == 0.0) ? asum : asum / div;
+                        }
+                        xs[cc] = {csr * kk, csi * kk};
+                    }
+                    x0 = xs[0], x1 = xs[1];
+                } else {
+                    x0 = lds_c(e1), x1 = lds_c(e1 + 16);
+                }
                 Cd m0 = cadd_(cmul_(x0, b0), cmul_(x1, b2));
                 Cd m1 = cadd_(cmul_(x0, b1), cmul_(x1, b3));
                 if (ANT) {
@@ -519,8 +566,8 @@ int launch_row_tile_order(const int32_t *time_index, const int32_t *ant1, const 
     return 0;
 }
 
-size_t dde_ws_smem_bytes(int64_t nant, int ft, bool ant) {
-    return kNS * stage_bytes((int)nant, ft, ant) + 3 * kNS * sizeof(uint64_t) + 4 * sizeof(double);
+size_t dde_ws_smem_bytes(int64_t nant, int ft, bool ant, bool sample) {
+    return kNS * stage_bytes((int)nant, ft, ant, sample) + 3 * kNS * sizeof(uint64_t) + 8 * sizeof(double);
 }
 
 int launch_antenna_uvw(const double *uvw, const int32_t *ant1, const int32_t *ant2,
@@ -546,9 +593,14 @@ int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact,
                         cudaStream_t stream) {
     // antenna mode with more than one 512-row tile per timestep: 2048 rows x 1 channel per CTA
     const bool wide_rows = ant_mode && max_rows_per_time > kConsThreads;
-    const int ft = wide_rows ? 1 : dde_ws_row_tile_channels(p.nant), rpt = wide_rows ? 4 : 1;
-    AFR_REQUIRE(ft > 0, "afr_predict_fused: antenna tile does not fit in shared memory");
-    const size_t smem = dde_ws_smem_bytes(p.nant, ft, ant_mode);
+    const bool sample = p.planes != nullptr;
+    AFR_REQUIRE(!sample || (ant_mode && p.same_dde && !exact), "in-kernel beam sampling needs antenna mode");
+    int ft = wide_rows ? 1 : dde_ws_row_tile_channels(p.nant);
+    const int rpt = wide_rows ? 4 : 1;
+    while (sample && ft > 1 && dde_ws_smem_bytes(p.nant, ft, true, true) > 220 * 1024) ft /= 2;
+    AFR_REQUIRE(ft > 0 && dde_ws_smem_bytes(p.nant, ft, ant_mode, sample) <= 220 * 1024,
+                "afr_predict_fused: antenna tile does not fit in shared memory");
+    const size_t smem = dde_ws_smem_bytes(p.nant, ft, ant_mode, sample);
     const int rows = kConsThreads * rpt;
     dim3 grid((unsigned)((max_rows_per_time + rows - 1) / rows), (unsigned)p.ntime,
               (unsigned)((p.nchan + ft - 1) / ft));
@@ -568,7 +620,13 @@ int launch_fused_dde_ws(const DdeWsParams &p, int max_rows_per_time, bool exact,
         return 0;
     };
     int rc;
-    if (wide_rows)  // antenna phasors are evaluated per channel: any frequency array
+    if (sample && wide_rows)
+        rc = go(fused_dde_ws_kernel<false, true, 1, 4, true>);
+    else if (sample)
+        rc = ft == 4 ? go(fused_dde_ws_kernel<false, true, 4, 1, true>)
+                     : (ft == 2 ? go(fused_dde_ws_kernel<false, true, 2, 1, true>)
+                                : go(fused_dde_ws_kernel<false, true, 1, 1, true>));
+    else if (wide_rows)  // antenna phasors are evaluated per channel: any frequency array
         rc = go(fused_dde_ws_kernel<false, true, 1, 4>);
     else if (ant_mode)
         rc = ft == 4 ? go(fused_dde_ws_kernel<false, true, 4, 1>)

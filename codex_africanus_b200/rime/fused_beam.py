@@ -34,17 +34,75 @@ def _chunk_budget(device):
     return int(max(256 << 20, min(_DDE_CHUNK_BYTES, free // 4)))
 
 
+# device bytes of plane-reduced beam per launch of the in-kernel sampling route
+_PLANES_CHUNK_BYTES = 4 << 30
+
+
+def _predict_sampling_in_kernel(d_lm, d_uvw, d_f, d_b, d_ti, d_a1, d_a2, d_beam, d_ext, d_bfm, d_pa, d_pe, d_as,
+                                die1_jones, acc, die2_jones, convention, device):
+    """The in-kernel sampling route of ``fused_predict_vis_beam`` on device tensors; None when it does
+    not apply (nothing was computed)."""
+    import ctypes
+
+    from .predict import normalise_indices
+    nsrc = d_lm.shape[0]
+    nrow = d_uvw.shape[0]
+    ntime, nant = d_pa.shape
+    nchan = d_f.shape[0]
+    lw, mh, nud = d_beam.shape[:3]
+    sign = pl.convention_sign(convention)
+    ti, a1, a2 = normalise_indices(d_ti, d_a1, d_a2, device)
+    c128 = np.complex128
+    g1 = None if die1_jones is None else pl.to_device(die1_jones, c128, device)
+    g2 = g1 if die2_jones is die1_jones else (None if die2_jones is None else pl.to_device(die2_jones, c128, device))
+    per_source = max(1, ntime * nant * nud * 96)
+    chunk = int(max(1, min(nsrc, _PLANES_CHUNK_BYTES // per_source)))
+    fd = pl.empty_device((nchan, 3), np.float64, device)
+    ok = torch.zeros(1, dtype=torch.int32, device=device)
+    used = ctypes.c_int(0)
+    out = None
+    for s0 in range(0, nsrc, chunk):
+        s1 = min(nsrc, s0 + chunk)
+        planes = pl.empty_device((s1 - s0, ntime, nant, nud, 12), np.float64, device)
+        pl.call("afr_beam_plane_reduce", device, pl.ptr(d_beam), pl.ptr(d_ext), pl.ptr(d_bfm), pl.ptr(d_lm[s0:s1]),
+                pl.ptr(d_pa), pl.ptr(d_pe), pl.ptr(d_as), pl.ptr(d_f), lw, mh, nud, s1 - s0, ntime, nant, nchan,
+                pl.ptr(planes), pl.ptr(fd), pl.ptr(ok), pl.stream_ptr(device))
+        if s0 == 0 and int(ok.item()) == 0:
+            return None  # some channel / row has its own grid position: the element kernel's business
+        last = s1 == nsrc
+        nxt = pl.empty_device((nrow, nchan, 2, 2), c128, device)
+        pl.call("afr_predict_fused_planes", device, pl.ptr(d_lm[s0:s1]), pl.ptr(d_uvw), pl.ptr(d_f),
+                pl.ptr(d_b[s0:s1]), pl.ptr(ti), pl.ptr(a1), pl.ptr(a2), pl.ptr(planes), pl.ptr(fd), nud,
+                pl.ptr(g1 if last else None), pl.ptr(acc if out is None else out), pl.ptr(g2 if last else None),
+                s1 - s0, nrow, ntime, nant, nchan, sign, ctypes.byref(used), pl.ptr(nxt), pl.stream_ptr(device))
+        if not used.value:
+            return None  # (decided on the first chunk: the admission test does not depend on the sources' count)
+        out = nxt
+        del planes
+    return out
+
+
 def fused_predict_vis_beam(lm, uvw, frequency, brightness, time_index, antenna1, antenna2,
                            beam, beam_lm_extents, beam_freq_map, parallactic_angles,
                            point_errors, antenna_scaling, die1_jones=None, base_vis=None,
-                           die2_jones=None, convention="fourier", source_chunk=None, feed_type=None):
+                           die2_jones=None, convention="fourier", source_chunk=None, feed_type=None,
+                           in_kernel=False):
     """``fused_predict_vis(..., dde1 = dde2 = beam_cube_dde(beam, ..., lm, ...))`` without the
     full DDE array.  Arguments: those of ``fused_predict_vis`` with the two DDE arrays replaced
     by the arguments of ``beam_cube_dde``; ``source_chunk`` (sources per chunk) defaults to
     what fits ``_DDE_CHUNK_BYTES``.  ``feed_type`` "linear" / "circular" additionally multiplies
     the beam by the feed rotation of the same parallactic angles, ``dde = beam_dde . L[t,a]``
     (africanus/rime/examples/predict.py:469-472, rime/feeds.py:13-48), inside the interpolation
-    kernel.  Returns (row, chan, corr...) like ``predict_vis``."""
+    kernel.  ``in_kernel=True`` (2x2 complex128, no ``feed_type``) samples the beam INSIDE the predict
+    kernel (SURVEY 8f-1 proper; the reference's fused RIME does the same,
+    experimental/rime/fused/terms/cube_dde.py:96-313): a pre-pass reduces the four spatial corners of
+    every frequency plane per (source, time, antenna) -- 43x smaller than the Jones array at 4096
+    channels -- and the kernel's producers combine the two planes of each channel; no
+    (source, time, ant, chan, 2, 2) array exists, not even per chunk.  It applies when pointing errors and
+    antenna scaling are constant along the channel axis, every channel lies inside the cube's frequency
+    range and the baseline uvw are differences of antenna coordinates; otherwise (and by default: the
+    chunked route through the GEMM kernel is 8 % faster) the beam is sampled per source chunk.
+    Returns (row, chan, corr...) like ``predict_vis``."""
     if (die1_jones is None) != (die2_jones is None):
         raise ValueError("Both die1_jones and die2_jones must be present or absent")
     bshape = pl.shape_of(beam)
@@ -86,6 +144,12 @@ def fused_predict_vis_beam(lm, uvw, frequency, brightness, time_index, antenna1,
             d_rot = feed_rotation(d_pa, feed_type)
             if pl.dtype_of(d_rot) != bdt:
                 d_rot = d_rot.to(pl.torch_dtype(bdt))
+        if in_kernel and feed_type is None and tuple(bshape[3:]) == (2, 2) and bdt == np.complex128 and \
+                out_dtype == np.complex128 and nsrc > 0 and pl.shape_of(uvw)[0] > 0:
+            res = _predict_sampling_in_kernel(d_lm, d_uvw, d_f, d_b, d_ti, d_a1, d_a2, d_beam, d_ext, d_bfm, d_pa,
+                                              d_pe, d_as, die1_jones, acc, die2_jones, convention, device)
+            if res is not None:
+                return res if as_torch else pl.to_host(res)
         for s0 in range(0, nsrc, source_chunk):
             s1 = min(nsrc, s0 + source_chunk)
             dde = beam_cube_dde_rotated(d_beam, d_ext, d_bfm, d_lm[s0:s1], d_pa, d_pe, d_as, d_f, d_rot)

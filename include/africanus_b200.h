@@ -67,6 +67,7 @@ unsigned long long afr_kernel_launches(void);
 #define AFR_PATH_DDE_TILED 4    /* antenna-tiled single-role kernel                           */
 #define AFR_PATH_DDE_GATHER 5   /* gather kernel (unsorted rows, diagonal Jones, complex64)   */
 #define AFR_PATH_DDE_MMA_ANT 6  /* antenna phasors, source sum as a complex GEMM on the FP64 tensor pipe */
+#define AFR_PATH_DDE_WS_ANT_SAMPLED 7 /* AFR_PATH_DDE_WS_ANT with the beam sampled inside the kernel */
 int afr_last_fused_path(void);
 /* Which schedule of the phasor-stream kernel the last afr_im_to_vis / afr_vis_to_im / point-source
  * afr_predict_fused / afr_wsclean_predict launch of this host thread used (its last correlation
@@ -174,6 +175,29 @@ int afr_beam_cube_dde_rot(const void *beam, const double *beam_lm_extents,
                           const void *feed_rotation, int64_t lw, int64_t mh, int64_t nud,
                           int64_t ncorr, int64_t nsrc, int64_t ntime, int64_t nant, int64_t nchan,
                           int is_c64, void *out, void *stream);
+/* ---- SURVEY 8f-1 proper: the beam sampled inside the predict kernel
+ * (africanus/experimental/rime/fused/terms/cube_dde.py:96-313 samples the cube inside the reference's
+ * fused loop; africanus/rime/examples/predict.py:390-401 materialises beam_cube_dde instead).
+ * afr_beam_plane_reduce: the four spatial corners of every frequency plane reduced per (source, time,
+ * antenna): planes (nsrc,ntime,nant,nud,12) float64 = re[4] | im[4] | abs[4] per plane (2x2 complex128
+ * beam), fd (nchan,3) = freq_grid_interp, ok[0] (device int) = 1 when every channel of every row is the
+ * combination of two planes (pointing errors / antenna scaling constant along chan, all channels inside
+ * the cube's frequency range).
+ * afr_predict_fused_planes: afr_predict_fused with dde1 = dde2 = the beam Jones formed by the kernel's
+ * producers from `planes` (never materialised).  used[0] (HOST int) = 1 when it ran, 0 when the path does
+ * not apply (uvw not differences of antenna coordinates within the admission bound, rows not ordered by
+ * time, antenna tile too large): nothing was written and the caller takes the chunked route. */
+int afr_beam_plane_reduce(const void *beam, const double *beam_lm_extents, const double *beam_freq_map,
+                          const double *lm, const double *parallactic_angles, const double *point_errors,
+                          const double *antenna_scaling, const double *freq, int64_t lw, int64_t mh,
+                          int64_t nud, int64_t nsrc, int64_t ntime, int64_t nant, int64_t nchan,
+                          double *planes, double *fd, int *ok, void *stream);
+int afr_predict_fused_planes(const double *lm, const double *uvw, const double *freq, const void *brightness,
+                             const int32_t *time_index, const int32_t *antenna1, const int32_t *antenna2,
+                             const double *planes, const double *fd, int64_t nud, const void *die1,
+                             const void *base_vis, const void *die2, int64_t nsrc, int64_t nrow,
+                             int64_t ntime, int64_t nant, int64_t nchan, int convention, int *used, void *out,
+                             void *stream);
 /* feed_rotation (africanus/rime/feeds.py:13-71): parallactic_angles (n,) float64 -> out (n,2,2)
  * complex128 (is_c64 0) / complex64 (1).  AFR_FEED_LINEAR [[cos,sin],[-sin,cos]],
  * AFR_FEED_CIRCULAR diag(exp(-i pa), exp(+i pa)). */

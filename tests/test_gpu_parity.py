@@ -1232,3 +1232,71 @@ def test_fused_spec_front_end_golden(b200, golden):
 def fs_required():
     from codex_africanus_b200.rime.fused_spec import REQUIRED_ARGS
     return REQUIRED_ARGS
+
+
+def test_fused_predict_vis_beam_sampled_in_kernel(b200, oracle, monkeypatch):
+    """SURVEY 8f-1 proper: ``fused_predict_vis_beam(in_kernel=True)`` forms the beam Jones inside the
+    predict kernel from the plane-reduced beam (no (source,time,ant,chan,2,2) array, not even per chunk).
+    Same values as the oracle's beam_cube_dde -> fused_predict chain and as the chunked route; the
+    kernel that ran is asserted; inputs the route does not cover fall back to the chunked one."""
+    from codex_africanus_b200 import _lib
+    from codex_africanus_b200.rime import fused_beam
+    rng = np.random.default_rng(1618)
+
+    def rc(shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    for na, ntime, nsrc, nchan in ((7, 3, 13, 24), (40, 2, 6, 5), (3, 1, 1, 1)):
+        a1, a2 = np.triu_indices(na, 1)
+        ant1, ant2 = np.tile(a1, ntime), np.tile(a2, ntime)
+        ti = np.repeat(np.arange(ntime), a1.size) + 4
+        nrow = ti.size
+        antpos = rng.standard_normal((ntime, na, 3)) * 1200.0
+        uvw = antpos[ti - 4, ant1] - antpos[ti - 4, ant2]
+        lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+        freq = np.linspace(0.9e9, 1.7e9, nchan) if nchan > 1 else np.array([1.2e9])
+        beam = rc((11, 9, 6, 2, 2))
+        ext = np.array([[-0.03, 0.03], [-0.03, 0.03]])
+        bfm = np.linspace(0.8e9, 1.8e9, 6)
+        pa = rng.uniform(-1, 1, (ntime, na))
+        pe = np.broadcast_to(rng.uniform(-1e-3, 1e-3, (ntime, na, 1, 2)), (ntime, na, nchan, 2)).copy()
+        asc = np.broadcast_to(rng.uniform(0.9, 1.1, (na, 1, 2)), (na, nchan, 2)).copy()
+        bright = rc((nsrc, nchan, 2, 2))
+        die = 1.0 + 0.1 * rc((ntime, na, nchan, 2, 2))
+        bvis = rc((nrow, nchan, 2, 2))
+        dde = oracle.beam_cube_dde(beam, ext, bfm, lm, pa, pe, asc, freq)
+        args = (lm, uvw, freq, bright, ti, ant1, ant2, beam, ext, bfm, pa, pe, asc)
+        for extra, ref in (((die, bvis, die), oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die)),
+                           ((), oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde))):
+            got = b200.rime.fused_predict_vis_beam(*args, *extra, in_kernel=True)
+            assert _lib.lib().afr_last_fused_path() == 7, (na, ntime, nsrc, nchan)
+            assert_c128_close(got, ref)
+            assert_c128_close(b200.rime.fused_predict_vis_beam(*args, *extra), ref)
+        # several plane chunks (sources per launch bounded by _PLANES_CHUNK_BYTES)
+        monkeypatch.setattr(fused_beam, "_PLANES_CHUNK_BYTES", 4 * ntime * na * 6 * 96)
+        got = b200.rime.fused_predict_vis_beam(*args, die, bvis, die, in_kernel=True)
+        monkeypatch.undo()
+        assert_c128_close(got, oracle.fused_predict(lm, uvw, freq, bright, ti, ant1, ant2, dde, dde, die, bvis, die))
+    # not covered: pointing errors that change along the channel axis; uvw that are not antenna differences;
+    # a channel outside the cube's frequency range -> the chunked route, same values
+    pe2 = rng.uniform(-1e-3, 1e-3, pe.shape)
+    na, ntime, nsrc, nchan = 7, 3, 13, 24
+    a1, a2 = np.triu_indices(na, 1)
+    ant1, ant2 = np.tile(a1, ntime), np.tile(a2, ntime)
+    ti = np.repeat(np.arange(ntime), a1.size)
+    antpos = rng.standard_normal((ntime, na, 3)) * 1200.0
+    uvw = antpos[ti, ant1] - antpos[ti, ant2]
+    lm = rng.uniform(-0.02, 0.02, (nsrc, 2))
+    bright = rc((nsrc, nchan, 2, 2))
+    pa = rng.uniform(-1, 1, (ntime, na))
+    pe = np.zeros((ntime, na, nchan, 2))
+    asc = np.ones((na, nchan, 2))
+    for freq, uv, perr in ((np.linspace(0.9e9, 1.7e9, nchan), uvw, rng.uniform(-1e-3, 1e-3, pe.shape)),
+                           (np.linspace(0.9e9, 1.7e9, nchan), rng.standard_normal(uvw.shape) * 900.0, pe),
+                           (np.linspace(0.7e9, 1.7e9, nchan), uvw, pe)):
+        dde = oracle.beam_cube_dde(beam, ext, bfm, lm, pa, perr, asc, freq)
+        ref = oracle.fused_predict(lm, uv, freq, bright, ti, ant1, ant2, dde, dde)
+        got = b200.rime.fused_predict_vis_beam(lm, uv, freq, bright, ti, ant1, ant2, beam, ext, bfm, pa, perr, asc,
+                                               in_kernel=True)
+        assert _lib.lib().afr_last_fused_path() != 7
+        assert_c128_close(got, ref)
