@@ -83,11 +83,13 @@ __device__ __forceinline__ void sts_c(unsigned char *p, Cd v) {
 // banks) and lanes reading the same antenna broadcast
 __host__ __device__ constexpr int ant_stride(int ft) { return ft * kMatBytes + 16; }
 
-constexpr int kPlaneBytes = 192;  // two frequency planes x (re, im, |.|) x 4 correlations of one (antenna, channel)
+constexpr int kPlaneBytes = 192;   // two frequency planes x (re, im, |.|) x 4 correlations of one (antenna, channel)
+constexpr int kPlaneStride = 224;  // their pitch in shared memory: 128 k + 32, so that the 16-byte loads of a quarter-warp
+                                   // (4 items x 2 rows) fall into distinct bank groups (192: 8-way conflicts, ncu 6.8e8)
 size_t stage_bytes(int na, int ft, bool ant, bool sample = false) {
     // E2 (or E) | E1 -> A (or A) | B | (sampling: the raw planes)
     (void)ant;
-    return 2 * (size_t)na * ant_stride(ft) + (size_t)ft * kMatBytes + (sample ? (size_t)na * ft * kPlaneBytes : 0);
+    return 2 * (size_t)na * ant_stride(ft) + (size_t)ft * kMatBytes + (sample ? (size_t)na * ft * kPlaneStride : 0);
 }
 
 // FT channels and RPT rows per consumer thread (FT * RPT = 4: 64 accumulator doubles).
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
     if (rbeg >= rend) return;
 
     const size_t mat_region = (size_t)na * AS;
-    const size_t stage = 2 * mat_region + FT * kMatBytes + (SAMPLE ? (size_t)na * FT * kPlaneBytes : 0);
+    const size_t stage = 2 * mat_region + FT * kMatBytes + (SAMPLE ? (size_t)na * FT * kPlaneStride : 0);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kNS * stage);  // full, empty, landed [kNS]
     double *fq = reinterpret_cast<double *>(bars + 3 * kNS);            // [FT]
     auto pl_of = [&](int st) { return smem + st * stage + 2 * mat_region + FT * kMatBytes; };  // SAMPLE: raw planes
@@ -133,7 +135,11 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
     }
     double *fw = fq + FT;  // [FT] (SAMPLE) weight of the lower frequency plane
     if (tid < FT) fq[tid] = p.freq[min(f0 + tid, p.nchan - 1)];
-    if (SAMPLE && tid < FT) fw[tid] = p.fd[3 * min(f0 + tid, p.nchan - 1) + 1];
+    int *fg = reinterpret_cast<int *>(fw + FT);  // [FT] (SAMPLE) index of the lower frequency plane
+    if (SAMPLE && tid < FT) {
+        fw[tid] = p.fd[3 * min(f0 + tid, p.nchan - 1) + 1];
+        fg[tid] = (int)p.fd[3 * min(f0 + tid, p.nchan - 1) + 2];
+    }
     __syncthreads();
 
     const int valid_ch = min(FT, p.nchan - f0);
@@ -168,8 +174,8 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
                     const int item = g / 12, c = g - item * 12;
                     const int a = item >> LFT, fl = item & (FT - 1);
                     if (fl < valid_ch) {
-                        const int gl = (int)p.fd[3 * (f0 + fl) + 2];
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dp + item * kPlaneBytes + c * 16),
+                        const int gl = fg[fl];  // (a global load here sat in front of every copy: ncu long-scoreboard)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dp + item * kPlaneStride + c * 16),
                                      "l"(psrc + ((long long)a * p.nud + gl) * 96 + c * 16));
                     }
                 }
@@ -220,15 +226,16 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
                     // row h of the beam Jones of antenna a at channel fl from its two frequency planes:
                     // the arithmetic of beam_cube_dde_planes_kernel's stage 2 (afr_beam.cu), i.e. the
                     // reference's interpolation and amplitude renormalisation (fast_beam_cubes.py:169-238)
-                    const double *pr = reinterpret_cast<const double *>(pl_of(st) + (size_t)((a << LFT) + fl) * kPlaneBytes);
-                    const double wlo = fw[fl], whi = 1.0 - wlo;  // exact: fd holds the weight, 1 - w as the beam kernel forms it
+                    const double2 *pr = reinterpret_cast<const double2 *>(pl_of(st) + (size_t)((a << LFT) + fl) * kPlaneStride) + h;
+                    const double wlo = fw[fl], whi = 1.0 - wlo;  // fd holds the weight; 1 - w as the beam kernel forms it
+                    // the row's two correlations are adjacent: one 16-byte load per (plane, re / im / |.|)
+                    const double2 rlo = pr[0], ilo = pr[2], alo = pr[4], rhi = pr[6], ihi = pr[8], ahi = pr[10];
                     Cd xs[2];
 #pragma unroll
                     for (int cc = 0; cc < 2; ++cc) {
-                        const int c = 2 * h + cc;
-                        const double csr = fma(wlo, pr[c], whi * pr[12 + c]);
-                        const double csi = fma(wlo, pr[4 + c], whi * pr[16 + c]);
-                        const double asum = fma(wlo, pr[8 + c], whi * pr[20 + c]);
+                        const double csr = fma(wlo, cc ? rlo.y : rlo.x, whi * (cc ? rhi.y : rhi.x));
+                        const double csi = fma(wlo, cc ? ilo.y : ilo.x, whi * (cc ? ihi.y : ihi.x));
+                        const double asum = fma(wlo, cc ? alo.y : alo.x, whi * (cc ? ahi.y : ahi.x));
                         const double tt = fma(csr, csr, csi * csi);
                         double kk;
                         if (tt > 1e-290 && tt < 1e290) {
@@ -567,7 +574,7 @@ int launch_row_tile_order(const int32_t *time_index, const int32_t *ant1, const 
 }
 
 size_t dde_ws_smem_bytes(int64_t nant, int ft, bool ant, bool sample) {
-    return kNS * stage_bytes((int)nant, ft, ant, sample) + 3 * kNS * sizeof(uint64_t) + 8 * sizeof(double);
+    return kNS * stage_bytes((int)nant, ft, ant, sample) + 3 * kNS * sizeof(uint64_t) + 12 * sizeof(double);
 }
 
 int launch_antenna_uvw(const double *uvw, const int32_t *ant1, const int32_t *ant2,
