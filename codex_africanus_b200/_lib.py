@@ -48,7 +48,7 @@ PROTOTYPES = {
     "afr_beam_cube_dde": (_int, [_vp] * 8 + [_i64] * 8 + [_int, _vp, _vp]),
     "afr_beam_cube_dde_rot": (_int, [_vp] * 9 + [_i64] * 8 + [_int, _vp, _vp]),
     "afr_beam_plane_reduce": (_int, [_vp] * 8 + [_i64] * 7 + [_vp] * 4),
-    "afr_predict_fused_planes": (_int, [_vp] * 9 + [_i64] + [_vp] * 3 + [_i64] * 5 + [_int] + [_vp] * 3),
+    "afr_predict_fused_planes": (_int, [_vp] * 9 + [_i64] + [_vp] * 4 + [_i64] * 5 + [_int] + [_vp] * 3),
     "afr_feed_rotation": (_int, [_vp, _i64, _int, _int, _vp, _vp]),
     "afr_freq_grid_interp": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "afr_wsclean_spectra": (_int, [_vp] * 5 + [_i64] * 3 + [_vp, _vp]),

@@ -49,6 +49,7 @@ struct DdeWsParams {
     // fetch the two frequency planes of each channel from the plane-reduced beam and form the Jones
     const double *planes;  // (nsrc,ntime,nant,nud,12) or nullptr
     const double *fd;      // (nchan,3) frequency-grid table (scale, weight of the lower plane, lower plane)
+    const double *feed;    // optional (ntime,nant,2,2) complex128 feed rotation applied on the right of the beam Jones
     int nud;
 };
 size_t dde_ws_smem_bytes(int64_t nant, int ft, bool ant, bool sample = false);

@@ -903,7 +903,8 @@ extern "C" int afr_predict_fused(const double *lm, const double *uvw, const doub
 extern "C" int afr_predict_fused_planes(const double *lm, const double *uvw, const double *freq,
                                         const void *brightness, const int32_t *time_index,
                                         const int32_t *antenna1, const int32_t *antenna2, const double *planes,
-                                        const double *fd, int64_t nud, const void *die1, const void *base_vis,
+                                        const double *fd, int64_t nud, const void *feed_rotation,
+                                        const void *die1, const void *base_vis,
                                         const void *die2, int64_t nsrc, int64_t nrow, int64_t ntime,
                                         int64_t nant, int64_t nchan, int convention, int *used, void *out,
                                         void *stream_) {
@@ -917,6 +918,7 @@ extern "C" int afr_predict_fused_planes(const double *lm, const double *uvw, con
                     nchan < (1LL << 30) && nrow < (1LL << 31) && nant <= 1024,
                 "afr_predict_fused_planes: bad extent");
     if (reinterpret_cast<uintptr_t>(planes) % 16 != 0 || reinterpret_cast<uintptr_t>(brightness) % 16 != 0 ||
+        reinterpret_cast<uintptr_t>(feed_rotation) % 16 != 0 ||
         dde_ws_smem_bytes(nant, 1, true, true) > 220 * 1024)
         return 0;
     const double cst = convention == AFR_FOURIER ? -kTwoPiOverC : kTwoPiOverC;
@@ -970,6 +972,7 @@ extern "C" int afr_predict_fused_planes(const double *lm, const double *uvw, con
     wp.same_dde = 1;
     wp.planes = planes;
     wp.fd = fd;
+    wp.feed = (const double *)feed_rotation;
     wp.nud = (int)nud;
     rc = launch_fused_dde_ws(wp, hflags[1], false, true, stream);
     if (rc) return rc;

@@ -247,6 +247,14 @@ __global__ void __launch_bounds__((kConsWarps + kProdWarps) * 32, 1)
                         xs[cc] = {csr * kk, csi * kk};
                     }
                     x0 = xs[0], x1 = xs[1];
+                    if (p.feed != nullptr) {
+                        // dde = beam . L[t,a] (rime/examples/predict.py:469-472): row h of E times the feed rotation
+                        const double2 *L = reinterpret_cast<const double2 *>(p.feed) + ((long long)t * p.nant + a) * 4;
+                        const double2 l00 = L[0], l01 = L[1], l10 = L[2], l11 = L[3];
+                        const Cd y0 = cadd_(cmul_(x0, Cd{l00.x, l00.y}), cmul_(x1, Cd{l10.x, l10.y}));
+                        const Cd y1 = cadd_(cmul_(x0, Cd{l01.x, l01.y}), cmul_(x1, Cd{l11.x, l11.y}));
+                        x0 = y0, x1 = y1;
+                    }
                 } else {
                     x0 = lds_c(e1), x1 = lds_c(e1 + 16);
                 }

@@ -39,7 +39,7 @@ _PLANES_CHUNK_BYTES = 4 << 30
 
 
 def _predict_sampling_in_kernel(d_lm, d_uvw, d_f, d_b, d_ti, d_a1, d_a2, d_beam, d_ext, d_bfm, d_pa, d_pe, d_as,
-                                die1_jones, acc, die2_jones, convention, device):
+                                die1_jones, acc, die2_jones, convention, device, d_rot=None):
     """The in-kernel sampling route of ``fused_predict_vis_beam`` on device tensors; None when it does
     not apply (nothing was computed)."""
     import ctypes
@@ -72,7 +72,7 @@ def _predict_sampling_in_kernel(d_lm, d_uvw, d_f, d_b, d_ti, d_a1, d_a2, d_beam,
         last = s1 == nsrc
         nxt = pl.empty_device((nrow, nchan, 2, 2), c128, device)
         pl.call("afr_predict_fused_planes", device, pl.ptr(d_lm[s0:s1]), pl.ptr(d_uvw), pl.ptr(d_f),
-                pl.ptr(d_b[s0:s1]), pl.ptr(ti), pl.ptr(a1), pl.ptr(a2), pl.ptr(planes), pl.ptr(fd), nud,
+                pl.ptr(d_b[s0:s1]), pl.ptr(ti), pl.ptr(a1), pl.ptr(a2), pl.ptr(planes), pl.ptr(fd), nud, pl.ptr(d_rot),
                 pl.ptr(g1 if last else None), pl.ptr(acc if out is None else out), pl.ptr(g2 if last else None),
                 s1 - s0, nrow, ntime, nant, nchan, sign, ctypes.byref(used), pl.ptr(nxt), pl.stream_ptr(device))
         if not used.value:
@@ -93,7 +93,7 @@ def fused_predict_vis_beam(lm, uvw, frequency, brightness, time_index, antenna1,
     what fits ``_DDE_CHUNK_BYTES``.  ``feed_type`` "linear" / "circular" additionally multiplies
     the beam by the feed rotation of the same parallactic angles, ``dde = beam_dde . L[t,a]``
     (africanus/rime/examples/predict.py:469-472, rime/feeds.py:13-48), inside the interpolation
-    kernel.  ``in_kernel=True`` (2x2 complex128, no ``feed_type``) samples the beam INSIDE the predict
+    kernel.  ``in_kernel=True`` (2x2 complex128) samples the beam INSIDE the predict
     kernel (SURVEY 8f-1 proper; the reference's fused RIME does the same,
     experimental/rime/fused/terms/cube_dde.py:96-313): a pre-pass reduces the four spatial corners of
     every frequency plane per (source, time, antenna) -- 43x smaller than the Jones array at 4096
@@ -144,10 +144,11 @@ def fused_predict_vis_beam(lm, uvw, frequency, brightness, time_index, antenna1,
             d_rot = feed_rotation(d_pa, feed_type)
             if pl.dtype_of(d_rot) != bdt:
                 d_rot = d_rot.to(pl.torch_dtype(bdt))
-        if in_kernel and feed_type is None and tuple(bshape[3:]) == (2, 2) and bdt == np.complex128 and \
+        if in_kernel and tuple(bshape[3:]) == (2, 2) and bdt == np.complex128 and \
                 out_dtype == np.complex128 and nsrc > 0 and pl.shape_of(uvw)[0] > 0:
             res = _predict_sampling_in_kernel(d_lm, d_uvw, d_f, d_b, d_ti, d_a1, d_a2, d_beam, d_ext, d_bfm, d_pa,
-                                              d_pe, d_as, die1_jones, acc, die2_jones, convention, device)
+                                              d_pe, d_as, die1_jones, acc, die2_jones, convention, device,
+                                              None if d_rot is None else d_rot.contiguous())
             if res is not None:
                 return res if as_torch else pl.to_host(res)
         for s0 in range(0, nsrc, source_chunk):

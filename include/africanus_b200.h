@@ -184,7 +184,8 @@ int afr_beam_cube_dde_rot(const void *beam, const double *beam_lm_extents,
  * combination of two planes (pointing errors / antenna scaling constant along chan, all channels inside
  * the cube's frequency range).
  * afr_predict_fused_planes: afr_predict_fused with dde1 = dde2 = the beam Jones formed by the kernel's
- * producers from `planes` (never materialised).  used[0] (HOST int) = 1 when it ran, 0 when the path does
+ * producers from `planes` (never materialised), times the optional feed rotation (ntime,nant,2,2) complex128
+ * on its right (as afr_beam_cube_dde_rot).  used[0] (HOST int) = 1 when it ran, 0 when the path does
  * not apply (uvw not differences of antenna coordinates within the admission bound, rows not ordered by
  * time, antenna tile too large): nothing was written and the caller takes the chunked route. */
 int afr_beam_plane_reduce(const void *beam, const double *beam_lm_extents, const double *beam_freq_map,
@@ -194,8 +195,8 @@ int afr_beam_plane_reduce(const void *beam, const double *beam_lm_extents, const
                           double *planes, double *fd, int *ok, void *stream);
 int afr_predict_fused_planes(const double *lm, const double *uvw, const double *freq, const void *brightness,
                              const int32_t *time_index, const int32_t *antenna1, const int32_t *antenna2,
-                             const double *planes, const double *fd, int64_t nud, const void *die1,
-                             const void *base_vis, const void *die2, int64_t nsrc, int64_t nrow,
+                             const double *planes, const double *fd, int64_t nud, const void *feed_rotation,
+                             const void *die1, const void *base_vis, const void *die2, int64_t nsrc, int64_t nrow,
                              int64_t ntime, int64_t nant, int64_t nchan, int convention, int *used, void *out,
                              void *stream);
 /* feed_rotation (africanus/rime/feeds.py:13-71): parallactic_angles (n,) float64 -> out (n,2,2)

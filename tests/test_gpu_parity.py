@@ -1272,6 +1272,12 @@ def test_fused_predict_vis_beam_sampled_in_kernel(b200, oracle, monkeypatch):
             assert _lib.lib().afr_last_fused_path() == 7, (na, ntime, nsrc, nchan)
             assert_c128_close(got, ref)
             assert_c128_close(b200.rime.fused_predict_vis_beam(*args, *extra), ref)
+        # with the feed rotation on the right of the beam Jones (dde = beam . L), both feed types
+        for ft in ("linear", "circular"):
+            want = b200.rime.fused_predict_vis_beam(*args, die, bvis, die, feed_type=ft)
+            got = b200.rime.fused_predict_vis_beam(*args, die, bvis, die, feed_type=ft, in_kernel=True)
+            assert _lib.lib().afr_last_fused_path() == 7
+            assert_c128_close(got, want)
         # several plane chunks (sources per launch bounded by _PLANES_CHUNK_BYTES)
         monkeypatch.setattr(fused_beam, "_PLANES_CHUNK_BYTES", 4 * ntime * na * 6 * 96)
         got = b200.rime.fused_predict_vis_beam(*args, die, bvis, die, in_kernel=True)
