@@ -20,7 +20,8 @@ The parallactic-angle arrays are taken in the layouts the reference's transforme
 (transformers/parangle.py:80-117: ``feed_parangle (time, feed, ant, 2, 2)`` and ``beam_parangle
 (time, feed, ant, 2)`` holding sin / cos) or as plain ``parallactic_angles (time, ant)``; they are
 not derived from antenna positions here (the reference calls casacore for that).  One feed per
-antenna; the Gaussian shape term (Cpq) is not built.
+antenna; the Gaussian shape term (Cpq) is not built.  ``in_kernel=True`` asks for the beam to be sampled
+inside the predict kernel as the reference's fused loop does (``fused_predict_vis_beam(in_kernel=True)``).
 """
 import re
 from collections.abc import Mapping
@@ -271,7 +272,7 @@ def rime(rime_spec, *args, **kw):
         ascale = np.ones((nant, nchan, 2))
         out = fused_predict_vis_beam(lm, uvw, freq, bright, time_index, ant1, ant2, beam, m["beam_lm_extents"],
                                      m["beam_freq_map"], pa, perr, ascale, die, None, die, convention=convention,
-                                     feed_type=feed_type)
+                                     feed_type=feed_type, in_kernel=bool(m.get("in_kernel", False)))
         if not as_torch and pl.is_torch(out):
             out = pl.to_host(out)
     nrow = pl.shape_of(out)[0]

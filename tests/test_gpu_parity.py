@@ -1216,6 +1216,7 @@ def test_fused_spec_front_end_golden(b200, golden):
     eds = {**ds, "beam": g["beam"], "beam_lm_extents": g["beam_lm_extents"], "beam_freq_map": g["beam_freq_map"],
            "beam_parangle": g["beam_parangle"]}
     assert_c128_close(rime("(Ep, Kpq, Bpq, Eq): [I,Q,U,V] -> %s" % lin, eds, convention="casa"), g["ekbe_lin"])
+    assert_c128_close(rime("(Ep, Kpq, Bpq, Eq): [I,Q,U,V] -> %s" % lin, eds, convention="casa", in_kernel=True), g["ekbe_lin"])
     assert_c128_close(rime("(Lp, Ep, Kpq, Bpq, Eq, Lq): [I,Q,U,V] -> %s" % lin, eds, feed_parangle=g["feed_parangle"]),
                       g["lekbel_lin"])
     assert_c128_close(rime("(Ep, Lp, Kpq, Bpq, Lq, Eq): [I,Q,U,V] -> %s" % lin, eds, feed_parangle=g["feed_parangle"]),
